@@ -1,0 +1,260 @@
+"""ctypes binding of include/fmsi_gpu.h. Plumbing only — every call lands in libfmsi_gpu.so.
+
+The product path fails loudly when the CUDA library is missing: `lib()` raises, nothing here
+computes anything on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+MODE_OR, MODE_ALL = 0, 1
+OUT_PRESENCE, OUT_ORDERS = 0, 1
+STRANDS_LAZY, STRANDS_BOTH = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+MAX_STREAM_KMERS = 64
+
+# every symbol include/fmsi_gpu.h declares (tests check the .so exports exactly these)
+EXPORTED_SYMBOLS = [
+    "fmsi_gpu_last_error", "fmsi_gpu_abi_version", "fmsi_gpu_device_count", "fmsi_gpu_index_load",
+    "fmsi_gpu_index_from_bits", "fmsi_gpu_index_free", "fmsi_gpu_index_get_info", "fmsi_gpu_rank",
+    "fmsi_gpu_update_range", "fmsi_gpu_extend_range_with_klcp", "fmsi_gpu_get_range_with_pattern",
+    "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
+    "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count",
+]
+
+
+class FmsiGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfmsi_gpu error {code}: {msg}")
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("prefix_t", C.c_int32), ("sb_shift_log2", C.c_int32), ("reserved", C.c_int64 * 6)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [
+        ("n_bwt", C.c_uint64), ("counts", C.c_uint64 * 4), ("dollar_position", C.c_uint64),
+        ("mask_ones", C.c_uint64), ("hbm_bytes", C.c_uint64), ("k", C.c_int32), ("has_klcp", C.c_int32),
+        ("prefix_t", C.c_int32), ("wide", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.environ.get("FMSI_GPU_LIB", os.path.join(HERE, "libfmsi_gpu.so"))
+
+
+def lib() -> C.CDLL:
+    """Load libfmsi_gpu.so (built in-tree by fmsi_b200/build.py). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FmsiGpuError(-3, f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u64p, u8p, i8p, i64p, u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.POINTER(C.c_int64), C.POINTER(C.c_uint32)
+    L.fmsi_gpu_last_error.restype = C.c_char_p
+    L.fmsi_gpu_abi_version.restype = C.c_int
+    L.fmsi_gpu_device_count.restype = C.c_int
+    L.fmsi_gpu_launch_count.restype = C.c_uint64
+    L.fmsi_gpu_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.fmsi_gpu_index_from_bits.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t, u64p,
+                                           C.c_uint64, u8p, C.c_size_t, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.fmsi_gpu_index_free.argtypes = [vp]
+    L.fmsi_gpu_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
+    L.fmsi_gpu_rank.argtypes = [vp, u64p, u8p, C.c_size_t, u64p]
+    L.fmsi_gpu_update_range.argtypes = [vp, u64p, u64p, u8p, C.c_size_t]
+    L.fmsi_gpu_extend_range_with_klcp.argtypes = [vp, u64p, u64p, C.c_size_t]
+    L.fmsi_gpu_get_range_with_pattern.argtypes = [vp, u64p, C.c_int, C.c_size_t, C.c_int, u64p, u64p]
+    L.fmsi_gpu_infer_presence.argtypes = [vp, u64p, u64p, C.c_size_t, C.c_int, i8p]
+    L.fmsi_gpu_kmer_order_if_present.argtypes = [vp, u64p, u64p, C.c_size_t, i64p]
+    L.fmsi_gpu_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    L.fmsi_gpu_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp,
+                                        C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("fmsi_gpu_abi_version", "fmsi_gpu_device_count"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise FmsiGpuError(rc, lib().fmsi_gpu_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().fmsi_gpu_launch_count())
+
+
+def device_count() -> int:
+    return int(lib().fmsi_gpu_device_count())
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a: np.ndarray, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def result_dtype_shape(output: int, strands: int, n: int):
+    if output == OUT_PRESENCE:
+        return np.uint8, (n,)
+    return np.int64, ((n, 2) if strands == STRANDS_BOTH else (n,))
+
+
+class Index:
+    """Handle to a GPU-resident FMS-index (the reference's `fms_index`, src/fms_index.h:52-66)."""
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+        info = IndexInfo()
+        _check(lib().fmsi_gpu_index_get_info(self._h, C.byref(info)))
+        self.info = info
+        self.n = int(info.n_bwt)
+        self.k = int(info.k)
+        self.has_klcp = bool(info.has_klcp)
+        self.counts = [int(c) for c in info.counts]
+        self.dollar_position = int(info.dollar_position)
+        self.prefix_t = int(info.prefix_t)
+        self.wide = bool(info.wide)
+        self.hbm_bytes = int(info.hbm_bytes)
+        self.mask_ones = int(info.mask_ones)
+
+    # ---- construction -------------------------------------------------------------------------
+    @staticmethod
+    def load(prefix: str, use_klcp: bool = True, device: int = 0, prefix_t: int = -1, sb_shift_log2: int = 0) -> "Index":
+        """load_index(fn, use_klcp) — reference src/fms_index.h:502."""
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2)
+        h = C.c_void_p()
+        _check(lib().fmsi_gpu_index_load(os.fsencode(prefix), int(use_klcp), device, C.byref(opts), C.byref(h)))
+        return Index(h)
+
+    @staticmethod
+    def from_bits(ac_gt, ac, gt, mask, counts, dollar_position, klcp=None, k=31, device=0, prefix_t=-1,
+                  sb_shift_log2=0) -> "Index":
+        """In-memory fixture, the form of tests/fms_index_test.h:10-69."""
+        arrs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (ac_gt, ac, gt, mask)]
+        kl = np.ascontiguousarray(klcp if klcp is not None else [], dtype=np.uint8)
+        cnt = _u64(counts)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2)
+        h = C.c_void_p()
+        _check(lib().fmsi_gpu_index_from_bits(
+            _ptr(arrs[0], C.c_uint8), arrs[0].size, _ptr(arrs[1], C.c_uint8), arrs[1].size,
+            _ptr(arrs[2], C.c_uint8), arrs[2].size, _ptr(arrs[3], C.c_uint8), arrs[3].size,
+            _ptr(cnt, C.c_uint64), int(dollar_position), _ptr(kl, C.c_uint8), kl.size, int(k), device,
+            C.byref(opts), C.byref(h)))
+        return Index(h)
+
+    def close(self) -> None:
+        if self._h:
+            lib().fmsi_gpu_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- building blocks (reference names) ----------------------------------------------------
+    def rank(self, i, c) -> np.ndarray:
+        i = _u64(np.atleast_1d(i))
+        c = np.ascontiguousarray(np.atleast_1d(c), dtype=np.uint8)
+        out = np.empty(i.size, dtype=np.uint64)
+        _check(lib().fmsi_gpu_rank(self._h, _ptr(i, C.c_uint64), _ptr(c, C.c_uint8), i.size, _ptr(out, C.c_uint64)))
+        return out
+
+    def update_range(self, i, j, c):
+        i = _u64(np.atleast_1d(i)).copy()
+        j = _u64(np.atleast_1d(j)).copy()
+        c = np.ascontiguousarray(np.atleast_1d(c), dtype=np.uint8)
+        _check(lib().fmsi_gpu_update_range(self._h, _ptr(i, C.c_uint64), _ptr(j, C.c_uint64), _ptr(c, C.c_uint8), i.size))
+        return i, j
+
+    def extend_range_with_klcp(self, i, j):
+        i = _u64(np.atleast_1d(i)).copy()
+        j = _u64(np.atleast_1d(j)).copy()
+        _check(lib().fmsi_gpu_extend_range_with_klcp(self._h, _ptr(i, C.c_uint64), _ptr(j, C.c_uint64), i.size))
+        return i, j
+
+    def get_range_with_pattern(self, kmers, k: int, use_table: bool = True):
+        kmers = _u64(np.atleast_1d(kmers))
+        i = np.empty(kmers.size, dtype=np.uint64)
+        j = np.empty(kmers.size, dtype=np.uint64)
+        _check(lib().fmsi_gpu_get_range_with_pattern(self._h, _ptr(kmers, C.c_uint64), k, kmers.size, int(use_table),
+                                                    _ptr(i, C.c_uint64), _ptr(j, C.c_uint64)))
+        return i, j
+
+    def infer_presence(self, sa_start, sa_end, maximized_ones: bool) -> np.ndarray:
+        i = _u64(np.atleast_1d(sa_start))
+        j = _u64(np.atleast_1d(sa_end))
+        out = np.empty(i.size, dtype=np.int8)
+        _check(lib().fmsi_gpu_infer_presence(self._h, _ptr(i, C.c_uint64), _ptr(j, C.c_uint64), i.size,
+                                            int(maximized_ones), _ptr(out, C.c_int8)))
+        return out
+
+    def kmer_order_if_present(self, sa_start, sa_end) -> np.ndarray:
+        i = _u64(np.atleast_1d(sa_start))
+        j = _u64(np.atleast_1d(sa_end))
+        out = np.empty(i.size, dtype=np.int64)
+        _check(lib().fmsi_gpu_kmer_order_if_present(self._h, _ptr(i, C.c_uint64), _ptr(j, C.c_uint64), i.size, _ptr(out, C.c_int64)))
+        return out
+
+    # ---- hot path -----------------------------------------------------------------------------
+    def query_kmers(self, kmers, k: int | None = None, mode: int = MODE_OR, output: int = OUT_PRESENCE,
+                    strands: int = STRANDS_LAZY) -> np.ndarray:
+        """query_kmers_single over packed k-mers held in host memory (numpy)."""
+        kmers = _u64(kmers)
+        k = self.k if k is None else k
+        dt, shape = result_dtype_shape(output, strands, kmers.size)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_query_kmers(self._h, mode, output, strands, kmers.ctypes.data, kmers.size, k,
+                                         out.ctypes.data, MEM_HOST, None))
+        return out
+
+    def query_kmers_ptr(self, kmers_ptr: int, n: int, out_ptr: int, k: int | None = None, mode: int = MODE_OR,
+                        output: int = OUT_PRESENCE, strands: int = STRANDS_LAZY, mem: int = MEM_DEVICE,
+                        stream: int = 0) -> None:
+        """Raw-pointer form (device tensors' data_ptr() or pinned host buffers)."""
+        k = self.k if k is None else k
+        _check(lib().fmsi_gpu_query_kmers(self._h, mode, output, strands, kmers_ptr, n, k, out_ptr, mem, stream or None))
+
+    def query_chunks(self, bases: bytes | np.ndarray, chunk_off, chunk_len, k: int | None = None, mode: int = MODE_OR,
+                     output: int = OUT_PRESENCE, strands: int = STRANDS_LAZY, streaming: bool = False) -> np.ndarray:
+        """query_kmers<mode>() over chunks of ACGT text in host memory; results concatenated chunk by chunk."""
+        k = self.k if k is None else k
+        b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.ascontiguousarray(bases, dtype=np.uint8)
+        off = _u64(chunk_off)
+        ln = np.ascontiguousarray(chunk_len, dtype=np.uint32)
+        cnt = ln.astype(np.int64) - k + 1
+        if (cnt < 1).any():
+            raise ValueError("every chunk must hold at least one k-mer")
+        res_off = np.zeros(off.size, dtype=np.uint64)
+        if off.size:
+            res_off[1:] = np.cumsum(cnt)[:-1].astype(np.uint64)
+        n_res = int(cnt.sum())
+        dt, shape = result_dtype_shape(output, strands, n_res)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_query_chunks(self._h, mode, output, strands, int(streaming), b.ctypes.data, b.size,
+                                          off.ctypes.data, ln.ctypes.data, res_off.ctypes.data, off.size, n_res, k,
+                                          out.ctypes.data, MEM_HOST, None))
+        return out
+
+
+def load_index(prefix: str, use_klcp: bool = True, device: int = 0, **kw) -> Index:
+    return Index.load(prefix, use_klcp, device, **kw)

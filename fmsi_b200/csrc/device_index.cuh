@@ -1,0 +1,81 @@
+// device_index.cuh — device-side view of the FMS-index and the rank / LF-mapping primitives.
+// Everything here is integer work on 32-byte sectors; one LF probe = one 256-bit load.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "index_layout.hpp"
+
+namespace fmsi {
+
+typedef uint64_t u64;
+typedef unsigned int u32;
+
+struct DevIndex {
+    const RankBlock *rank;
+    const AuxBlock *aux;
+    const void *table;    // 4^t entries {i, j}: u32 pairs (narrow) or u64 pairs (wide)
+    const u64 *sb_base;   // [n_superblocks][4]
+    u64 n;                // N = BWT length
+    u64 dollar;
+    u32 t;                // suffix-table depth (0 = no table)
+    u32 sb_shift;
+    u32 k;
+    u32 has_klcp;
+};
+
+template <bool WIDE> struct PosT { typedef u32 type; };
+template <> struct PosT<true> { typedef u64 type; };
+
+// One sector, bypassing L1 allocation (no reuse inside an SM for random probes).
+__device__ __forceinline__ void ld_sector(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+}
+// One sector through L1 (streaming path: consecutive probes revisit the same block).
+__device__ __forceinline__ void ld_sector_l1(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+}
+
+__device__ __forceinline__ u64 low_mask(u32 nbits) {  // nbits in [0, 63]
+    return (1ull << nbits) - 1ull;
+}
+
+// LF(i, c) = counts[c] + rank(i, c) from the sector of block i>>6 (reference rank(),
+// src/fms_index.h:68-86, and the `count + rank` of update_range, :100-102).
+// w0 = cnt[0] | cnt[1] << 32, w1 = cnt[2] | cnt[3] << 32.
+template <bool WIDE>
+__device__ __forceinline__ typename PosT<WIDE>::type lf_map(const DevIndex &d, u64 w0, u64 w1, u64 lo, u64 hi,
+                                                            typename PosT<WIDE>::type i, u32 c) {
+    typedef typename PosT<WIDE>::type pos_t;
+    const u64 w = (c & 2) ? w1 : w0;
+    const u32 cnt = (c & 1) ? (u32)(w >> 32) : (u32)w;
+    const u64 x = (c & 1) ? lo : ~lo;
+    const u64 y = (c & 2) ? hi : ~hi;
+    const u64 m = x & y & low_mask((u32)i & 63u);
+    pos_t r = (pos_t)cnt + (pos_t)__popcll(m);
+    if (WIDE) r += (pos_t)d.sb_base[(((u64)i >> 6) >> d.sb_shift) * 4 + c];
+    // '$' is stored as A: ranks of A past the dollar slot are one too high (fms_index.h:81).
+    r -= (pos_t)((c == 0) & ((u64)i > d.dollar));
+    return r;
+}
+
+// 2-bit reverse complement of a packed k-mer (first base in the highest used bits).
+__device__ __forceinline__ u64 revcomp_packed(u64 x, u32 k) {
+    x = __brevll(~x);
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    return x >> (64 - 2 * k);
+}
+
+// mask rank1 / bit helpers on an aux sector (klcp, mask, mask_cum, spare)
+__device__ __forceinline__ u64 mask_rank_excl(u64 mask, u64 cum, u32 off) {  // ones in [64b, 64b+off)
+    return cum + (u64)__popcll(mask & low_mask(off));
+}
+__device__ __forceinline__ u64 mask_rank_incl(u64 mask, u64 cum, u32 off) {  // ones in [64b, 64b+off]
+    return cum + (u64)__popcll(mask & ((2ull << off) - 1ull));
+}
+
+}  // namespace fmsi

@@ -1,0 +1,569 @@
+// fmsi_gpu.cu — C-ABI of libfmsi_gpu.so (see include/fmsi_gpu.h). Host-side plumbing only:
+// index upload, suffix-table construction, staging/pipelining of host buffers and kernel dispatch.
+#include "../../include/fmsi_gpu.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_index.cuh"
+#include "index_layout.hpp"
+#include "query_kernels.cuh"
+#include "stream_kernels.cuh"
+
+using namespace fmsi;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(FMSI_GPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+constexpr int kSlots = 2;
+constexpr size_t kBatchKmers = 16u << 20;  // k-mers per pipelined host batch
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr;
+    size_t in_cap = 0, out_cap = 0, aux_cap = 0;
+    unsigned long long *d_cursor = nullptr;
+};
+
+}  // namespace
+
+struct fmsi_gpu_index {
+    int device = 0;
+    int sm_count = 0;
+    HostIndex meta;  // vectors released after upload
+    DevIndex dev{};
+    void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr;
+    uint64_t hbm_bytes = 0;
+    bool wide = false;
+    Slot slots[kSlots];
+    unsigned long long *d_cursor_user = nullptr;  // cursor for MEM_DEVICE launches
+};
+
+namespace {
+
+int ensure(void **p, size_t *cap, size_t need) {
+    if (*cap >= need) return FMSI_GPU_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 256;
+    CU(cudaMalloc(p, want));
+    *cap = want;
+    return FMSI_GPU_OK;
+}
+
+template <typename Kernel>
+int persistent_grid(const fmsi_gpu_index *idx, Kernel kern, int block) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return idx->sm_count * per_sm;
+}
+
+u32 pick_chunk(size_t n, int grid, int block) {
+    const size_t warps = (size_t)grid * (block / 32);
+    size_t c = n / (warps * 8 + 1);
+    c = (c / 32) * 32;
+    if (c < 32) c = 32;
+    if (c > 2048) c = 2048;
+    return (u32)c;
+}
+
+template <int MODE, int OUT, int STRANDS, bool WIDE>
+int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
+                 unsigned long long *cursor, cudaStream_t st) {
+    auto kern = query_kmers_kernel<MODE, OUT, STRANDS, WIDE>;
+    const int grid = persistent_grid(idx, kern, kQueryBlock);
+    const u32 chunk = pick_chunk(n, grid, kQueryBlock);
+    CU(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, cursor, chunk);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return FMSI_GPU_OK;
+}
+
+template <int MODE, int OUT, int STRANDS>
+int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
+                   unsigned long long *cursor, cudaStream_t st) {
+    if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, cursor, st);
+    return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, cursor, st);
+}
+
+int dispatch_query(const fmsi_gpu_index *idx, const DevIndex &d, int mode, int output, int strands,
+                   const u64 *kmers, size_t n, void *out, unsigned long long *cursor, cudaStream_t st) {
+    if (output == FMSI_GPU_OUT_ORDERS) {
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
+        return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+    }
+    if (mode == FMSI_GPU_MODE_ALL) {
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
+        return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+    }
+    if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
+    return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+}
+
+size_t result_bytes(int output, int strands) {
+    if (output == FMSI_GPU_OUT_PRESENCE) return 1;
+    return strands == FMSI_GPU_STRANDS_BOTH ? 16 : 8;
+}
+
+// DevIndex for a query with k-mer length k (the table only helps when t <= k).
+DevIndex dev_for_k(const fmsi_gpu_index *idx, int k) {
+    DevIndex d = idx->dev;
+    d.k = (u32)k;
+    if (d.t > (u32)k) d.t = 0;
+    return d;
+}
+
+template <bool WIDE>
+int build_table(fmsi_gpu_index *idx, u32 t) {
+    typedef TableEntry<WIDE> E;
+    if (t == 0) return FMSI_GPU_OK;
+    const u64 total = 1ull << (2 * t);
+    E *full = nullptr, *quarter = nullptr;
+    CU(cudaMalloc(&full, total * sizeof(E)));
+    if (t > 1) CU(cudaMalloc(&quarter, (total / 4) * sizeof(E)));
+    DevIndex d = idx->dev;
+    for (u32 s = 1; s <= t; ++s) {
+        E *cur = ((t - s) % 2 == 0) ? full : quarter;
+        const E *prev = ((t - s) % 2 == 0) ? quarter : full;
+        const u64 cnt = 1ull << (2 * s);
+        const int block = 256;
+        const u64 grid = (cnt + block - 1) / block;
+        table_level_kernel<WIDE><<<(unsigned)grid, block>>>(d, prev, cur, s);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(1);
+    }
+    CU(cudaDeviceSynchronize());
+    if (quarter) cudaFree(quarter);
+    idx->d_table = full;
+    idx->dev.table = full;
+    idx->dev.t = t;
+    idx->hbm_bytes += total * sizeof(E);
+    return FMSI_GPU_OK;
+}
+
+int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FMSI_GPU_ERR_CUDA, "no CUDA device available (libfmsi_gpu has no CPU fallback)");
+    if (idx->device < 0 || idx->device >= ndev) return fail(FMSI_GPU_ERR_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(idx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, idx->device));
+    idx->sm_count = prop.multiProcessorCount;
+    HostIndex &h = idx->meta;
+    idx->wide = h.wide();
+    const size_t rb = h.rank.size() * sizeof(RankBlock), ab = h.aux.size() * sizeof(AuxBlock);
+    CU(cudaMalloc(&idx->d_rank, rb));
+    CU(cudaMalloc(&idx->d_aux, ab));
+    CU(cudaMalloc(&idx->d_sb, h.sb_base.size() * 8));
+    CU(cudaMalloc(&idx->d_counts, 4 * 8));
+    CU(cudaMemcpy(idx->d_rank, h.rank.data(), rb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_aux, h.aux.data(), ab, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_sb, h.sb_base.data(), h.sb_base.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice));
+    idx->hbm_bytes = rb + ab + h.sb_base.size() * 8 + 32;
+    std::vector<RankBlock>().swap(h.rank);
+    std::vector<AuxBlock>().swap(h.aux);
+
+    DevIndex &d = idx->dev;
+    d.rank = reinterpret_cast<const RankBlock *>(idx->d_rank);
+    d.aux = reinterpret_cast<const AuxBlock *>(idx->d_aux);
+    d.table = nullptr;
+    d.sb_base = reinterpret_cast<const u64 *>(idx->d_sb);
+    d.n = h.n;
+    d.dollar = h.dollar;
+    d.t = 0;
+    d.sb_shift = h.sb_shift >= 63 ? 63 : h.sb_shift;
+    d.k = (u32)h.k;
+    d.has_klcp = h.has_klcp;
+
+    // Suffix-table depth: auto = largest t with 4^t <= N (table no larger than ~2x the rank
+    // array), capped by k, by 16 and by a quarter of the free device memory.
+    int t = opts ? opts->prefix_t : -1;
+    if (const char *e = std::getenv("FMSI_GPU_PREFIX_T")) t = std::atoi(e);
+    if (t < 0) {
+        t = 0;
+        while (t < 16 && (1ull << (2 * (t + 1))) <= h.n) ++t;
+    }
+    if (t > h.k) t = h.k;
+    if (t > 16) t = 16;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t esz = idx->wide ? 16 : 8;
+    while (t > 0 && ((1ull << (2 * t)) * esz * 5 / 4) > free_b / 4) --t;
+    int rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
+    if (rc) return rc;
+
+    for (int s = 0; s < kSlots; ++s) {
+        CU(cudaStreamCreateWithFlags(&idx->slots[s].stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&idx->slots[s].done, cudaEventDisableTiming));
+        CU(cudaMalloc(&idx->slots[s].d_cursor, sizeof(unsigned long long)));
+    }
+    CU(cudaMalloc(&idx->d_cursor_user, sizeof(unsigned long long)));
+    return FMSI_GPU_OK;
+}
+
+BitVec bits_to_vec(const uint8_t *bits, size_t n) {
+    BitVec b;
+    b.resize_bits(n);
+    for (size_t p = 0; p < n; ++p)
+        if (bits[p]) b.set(p);
+    return b;
+}
+
+// RAII device scratch for the probe entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        CU(cudaMalloc(&p, bytes ? bytes : 8));
+        return FMSI_GPU_OK;
+    }
+    int put(const void *src, size_t bytes) {
+        int rc = alloc(bytes);
+        if (rc) return rc;
+        CU(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        return FMSI_GPU_OK;
+    }
+    int get(void *dst, size_t bytes) {
+        CU(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost));
+        return FMSI_GPU_OK;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+inline unsigned blocks_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+extern "C" {
+
+const char *fmsi_gpu_last_error(void) { return g_err.c_str(); }
+int fmsi_gpu_abi_version(void) { return FMSI_GPU_ABI_VERSION; }
+int fmsi_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+uint64_t fmsi_gpu_launch_count(void) { return g_launches.load(); }
+
+int fmsi_gpu_index_load(const char *prefix, int use_klcp, int device, const fmsi_gpu_options *opts,
+                        fmsi_gpu_index **out) {
+    if (!prefix || !out) return fail(FMSI_GPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
+    idx->device = device;
+    try {
+        IndexFiles f = read_index_files(prefix, use_klcp != 0);
+        if (f.mask.nbits == 0) return fail(FMSI_GPU_ERR_IO, "index not correctly loaded (empty mask)");
+        idx->meta = build_host_index(f.ac_gt, f.ac, f.gt, f.mask, f.klcp_present ? &f.klcp : nullptr, f.counts,
+                                     f.dollar, f.k, opts ? (unsigned)opts->sb_shift_log2 : 0u);
+    } catch (const std::exception &e) {
+        return fail(FMSI_GPU_ERR_IO, e.what());
+    }
+    int rc = upload(idx.get(), opts);
+    if (rc) {
+        fmsi_gpu_index_free(idx.release());
+        return rc;
+    }
+    *out = idx.release();
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t *ac, size_t n_ac,
+                             const uint8_t *gt, size_t n_gt, const uint8_t *mask, size_t n_mask,
+                             const uint64_t counts[4], uint64_t dollar_position, const uint8_t *klcp,
+                             size_t n_klcp, int k, int device, const fmsi_gpu_options *opts,
+                             fmsi_gpu_index **out) {
+    if (!ac_gt || !ac || !gt || !mask || !counts || !out) return fail(FMSI_GPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
+    idx->device = device;
+    try {
+        BitVec b_acgt = bits_to_vec(ac_gt, n_ac_gt), b_ac = bits_to_vec(ac, n_ac), b_gt = bits_to_vec(gt, n_gt),
+               b_mask = bits_to_vec(mask, n_mask), b_klcp;
+        if (klcp && n_klcp) b_klcp = bits_to_vec(klcp, n_klcp);
+        idx->meta = build_host_index(b_acgt, b_ac, b_gt, b_mask, (klcp && n_klcp) ? &b_klcp : nullptr, counts,
+                                     dollar_position, k, opts ? (unsigned)opts->sb_shift_log2 : 0u);
+    } catch (const std::exception &e) {
+        return fail(FMSI_GPU_ERR_IO, e.what());
+    }
+    int rc = upload(idx.get(), opts);
+    if (rc) {
+        fmsi_gpu_index_free(idx.release());
+        return rc;
+    }
+    *out = idx.release();
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
+    if (!idx) return FMSI_GPU_OK;
+    cudaSetDevice(idx->device);
+    for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, (void *)idx->d_cursor_user})
+        if (p) cudaFree(p);
+    for (auto &s : idx->slots) {
+        for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.d_cursor})
+            if (p) cudaFree(p);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete idx;
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info) {
+    if (!idx || !info) return fail(FMSI_GPU_ERR_ARG, "null argument");
+    std::memset(info, 0, sizeof(*info));
+    info->n_bwt = idx->meta.n;
+    for (int c = 0; c < 4; ++c) info->counts[c] = idx->meta.counts[c];
+    info->dollar_position = idx->meta.dollar;
+    info->mask_ones = idx->meta.mask_ones;
+    info->hbm_bytes = idx->hbm_bytes;
+    info->k = idx->meta.k;
+    info->has_klcp = idx->meta.has_klcp;
+    info->prefix_t = (int32_t)idx->dev.t;
+    info->wide = idx->wide;
+    info->device = idx->device;
+    return FMSI_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------- probes
+#define PROBE_PROLOGUE()                                                  \
+    if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");                \
+    if (n == 0) return FMSI_GPU_OK;                                       \
+    CU(cudaSetDevice(idx->device))
+
+int fmsi_gpu_rank(fmsi_gpu_index *idx, const uint64_t *i, const uint8_t *c, size_t n, uint64_t *out) {
+    PROBE_PROLOGUE();
+    for (size_t q = 0; q < n; ++q)
+        if (i[q] > idx->meta.n || c[q] > 3) return fail(FMSI_GPU_ERR_ARG, "rank argument out of range");
+    DevBuf di, dc, dout;
+    int rc;
+    if ((rc = di.put(i, n * 8)) || (rc = dc.put(c, n)) || (rc = dout.alloc(n * 8))) return rc;
+    if (idx->wide)
+        probe_rank_kernel<true><<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dc.as<unsigned char>(), n, (const u64 *)idx->d_counts, dout.as<u64>());
+    else
+        probe_rank_kernel<false><<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dc.as<unsigned char>(), n, (const u64 *)idx->d_counts, dout.as<u64>());
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return dout.get(out, n * 8);
+}
+
+int fmsi_gpu_update_range(fmsi_gpu_index *idx, uint64_t *i, uint64_t *j, const uint8_t *c, size_t n) {
+    PROBE_PROLOGUE();
+    for (size_t q = 0; q < n; ++q)
+        if (i[q] > idx->meta.n || j[q] > idx->meta.n || c[q] > 3) return fail(FMSI_GPU_ERR_ARG, "update_range argument out of range");
+    DevBuf di, dj, dc;
+    int rc;
+    if ((rc = di.put(i, n * 8)) || (rc = dj.put(j, n * 8)) || (rc = dc.put(c, n))) return rc;
+    if (idx->wide) probe_update_range_kernel<true><<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dj.as<u64>(), dc.as<unsigned char>(), n);
+    else probe_update_range_kernel<false><<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dj.as<u64>(), dc.as<unsigned char>(), n);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    if ((rc = di.get(i, n * 8)) || (rc = dj.get(j, n * 8))) return rc;
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_extend_range_with_klcp(fmsi_gpu_index *idx, uint64_t *i, uint64_t *j, size_t n) {
+    PROBE_PROLOGUE();
+    if (!idx->meta.has_klcp) return fail(FMSI_GPU_ERR_KLCP, "index loaded without kLCP");
+    for (size_t q = 0; q < n; ++q)
+        if (i[q] == 0 || i[q] >= j[q] || j[q] > idx->meta.n) return fail(FMSI_GPU_ERR_ARG, "extend_range_with_klcp needs 1 <= i < j <= N");
+    DevBuf di, dj;
+    int rc;
+    if ((rc = di.put(i, n * 8)) || (rc = dj.put(j, n * 8))) return rc;
+    probe_extend_kernel<<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dj.as<u64>(), n);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    if ((rc = di.get(i, n * 8)) || (rc = dj.get(j, n * 8))) return rc;
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_get_range_with_pattern(fmsi_gpu_index *idx, const uint64_t *kmers, int k, size_t n,
+                                    int use_table, uint64_t *sa_start, uint64_t *sa_end) {
+    PROBE_PROLOGUE();
+    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
+    DevBuf dk, di, dj;
+    int rc;
+    if ((rc = dk.put(kmers, n * 8)) || (rc = di.alloc(n * 8)) || (rc = dj.alloc(n * 8))) return rc;
+    if (idx->wide) probe_get_range_kernel<true><<<blocks_for(n), 256>>>(idx->dev, dk.as<u64>(), (u32)k, n, use_table, di.as<u64>(), dj.as<u64>());
+    else probe_get_range_kernel<false><<<blocks_for(n), 256>>>(idx->dev, dk.as<u64>(), (u32)k, n, use_table, di.as<u64>(), dj.as<u64>());
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    if ((rc = di.get(sa_start, n * 8)) || (rc = dj.get(sa_end, n * 8))) return rc;
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_infer_presence(fmsi_gpu_index *idx, const uint64_t *sa_start, const uint64_t *sa_end,
+                            size_t n, int maximized_ones, int8_t *out) {
+    PROBE_PROLOGUE();
+    for (size_t q = 0; q < n; ++q)
+        if (sa_start[q] > sa_end[q] || sa_end[q] > idx->meta.n) return fail(FMSI_GPU_ERR_ARG, "interval out of range");
+    DevBuf di, dj, dout;
+    int rc;
+    if ((rc = di.put(sa_start, n * 8)) || (rc = dj.put(sa_end, n * 8)) || (rc = dout.alloc(n))) return rc;
+    probe_presence_kernel<<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dj.as<u64>(), n, maximized_ones, dout.as<signed char>());
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return dout.get(out, n);
+}
+
+int fmsi_gpu_kmer_order_if_present(fmsi_gpu_index *idx, const uint64_t *sa_start,
+                                   const uint64_t *sa_end, size_t n, int64_t *out) {
+    PROBE_PROLOGUE();
+    for (size_t q = 0; q < n; ++q)
+        if (sa_start[q] > sa_end[q] || sa_end[q] > idx->meta.n) return fail(FMSI_GPU_ERR_ARG, "interval out of range");
+    DevBuf di, dj, dout;
+    int rc;
+    if ((rc = di.put(sa_start, n * 8)) || (rc = dj.put(sa_end, n * 8)) || (rc = dout.alloc(n * 8))) return rc;
+    probe_order_kernel<<<blocks_for(n), 256>>>(idx->dev, di.as<u64>(), dj.as<u64>(), n, dout.as<long long>());
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return dout.get(out, n * 8);
+}
+
+// ---------------------------------------------------------------------------------- hot path
+int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
+                         const uint64_t *kmers, size_t n, int k, void *results, int mem, void *stream) {
+    if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
+    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32] for packed k-mers");
+    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    if (n == 0) return FMSI_GPU_OK;
+    if (!kmers || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    CU(cudaSetDevice(idx->device));
+    const DevIndex d = dev_for_k(idx, k);
+    const size_t rbytes = result_bytes(output, strands);
+
+    if (mem == FMSI_GPU_MEM_DEVICE) {
+        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->d_cursor_user, (cudaStream_t)stream);
+    }
+    if (mem != FMSI_GPU_MEM_HOST) return fail(FMSI_GPU_ERR_ARG, "bad mem");
+
+    // Host buffers: double-buffered batches so H2D, kernel and D2H of neighbouring batches overlap.
+    size_t done = 0;
+    int b = 0;
+    while (done < n) {
+        Slot &s = idx->slots[b % kSlots];
+        const size_t m = std::min(kBatchKmers, n - done);
+        CU(cudaEventSynchronize(s.done));
+        int rc;
+        if ((rc = ensure(&s.d_in, &s.in_cap, m * 8)) || (rc = ensure(&s.d_out, &s.out_cap, m * rbytes))) return rc;
+        CU(cudaMemcpyAsync(s.d_in, kmers + done, m * 8, cudaMemcpyHostToDevice, s.stream));
+        if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.d_cursor, s.stream))) return rc;
+        CU(cudaMemcpyAsync((char *)results + done * rbytes, s.d_out, m * rbytes, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        done += m;
+        ++b;
+    }
+    for (auto &s : idx->slots) CU(cudaStreamSynchronize(s.stream));
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
+                          const char *bases, size_t n_bases, const uint64_t *chunk_off,
+                          const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
+                          size_t n_results, int k, void *results, int mem, void *stream) {
+    if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
+    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
+    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    if (streaming && !idx->meta.has_klcp) return fail(FMSI_GPU_ERR_KLCP, "kLCP array was not loaded for the given index");
+    if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
+    if (!bases || !chunk_off || !chunk_len || !res_off || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    CU(cudaSetDevice(idx->device));
+    const DevIndex d = dev_for_k(idx, k);
+    const size_t rbytes = result_bytes(output, strands);
+    const bool on_host = mem == FMSI_GPU_MEM_HOST;
+    if (!on_host && mem != FMSI_GPU_MEM_DEVICE) return fail(FMSI_GPU_ERR_ARG, "bad mem");
+
+    Slot &s = idx->slots[0];
+    cudaStream_t st = on_host ? s.stream : (cudaStream_t)stream;
+    const char *d_bases = bases;
+    const u64 *d_off = chunk_off, *d_res = res_off;
+    const u32 *d_len = chunk_len;
+    void *d_results = results;
+    int rc;
+    // scratch: [packed bases | (host mode) bases, offsets, lens, res_off | packed k-mers (non-streaming)]
+    const size_t n_words = (n_bases + 31) / 32 + 4;
+    size_t aux_need = n_words * 8;
+    const size_t kmers_off = aux_need;
+    if (!streaming) aux_need += n_results * 8;
+    if (on_host) {
+        CU(cudaEventSynchronize(s.done));
+        if (streaming) {
+            // host-side validation of the per-chunk k-mer bound
+            for (size_t c = 0; c < n_chunks; ++c)
+                if (chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS)
+                    return fail(FMSI_GPU_ERR_ARG, "streaming chunks must hold between 1 and FMSI_GPU_MAX_STREAM_KMERS k-mers");
+        }
+        const size_t in_need = ((n_bases + 7) & ~size_t(7)) + n_chunks * (8 + 8 + 4) + 64;
+        if ((rc = ensure(&s.d_in, &s.in_cap, in_need)) || (rc = ensure(&s.d_out, &s.out_cap, n_results * rbytes))) return rc;
+        char *p = (char *)s.d_in;
+        CU(cudaMemcpyAsync(p, bases, n_bases, cudaMemcpyHostToDevice, st));
+        d_bases = p;
+        p += (n_bases + 7) & ~size_t(7);
+        CU(cudaMemcpyAsync(p, chunk_off, n_chunks * 8, cudaMemcpyHostToDevice, st));
+        d_off = (const u64 *)p;
+        p += n_chunks * 8;
+        CU(cudaMemcpyAsync(p, res_off, n_chunks * 8, cudaMemcpyHostToDevice, st));
+        d_res = (const u64 *)p;
+        p += n_chunks * 8;
+        CU(cudaMemcpyAsync(p, chunk_len, n_chunks * 4, cudaMemcpyHostToDevice, st));
+        d_len = (const u32 *)p;
+        d_results = s.d_out;
+    }
+    if ((rc = ensure(&s.d_aux, &s.aux_cap, aux_need))) return rc;
+    u64 *d_packed = (u64 *)s.d_aux;
+    pack_bases_kernel<<<blocks_for(n_words), 256, 0, st>>>(d_bases, (u64)n_bases, d_packed, (u64)n_words);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+
+    if (!streaming) {
+        u64 *d_kmers = (u64 *)((char *)s.d_aux + kmers_off);
+        extract_kmers_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(1);
+        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.d_cursor : idx->d_cursor_user, st))) return rc;
+    } else {
+        if ((rc = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off, d_len, d_res, n_chunks, d_results,
+                                  on_host ? s.d_cursor : idx->d_cursor_user, st)))
+            return fail(FMSI_GPU_ERR_CUDA, std::string("streaming kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+        g_launches.fetch_add(1);
+    }
+    if (on_host) {
+        CU(cudaMemcpyAsync(results, d_results, n_results * rbytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(s.done, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return FMSI_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// sdsl_io.hpp — reader/writer for the sdsl-lite 2.1.0 on-disk forms FMSI's index files use,
+// written from the format description, without linking sdsl.
+//
+//   .ac_gt / .ac / .gt / .klcp : int_vector<1>   = u64 bit_len, ceil(bit_len/64) LE u64 words
+//                                (reference: sdsl int_vector.hpp:593-610 header, :1563-1595 data)
+//   .mask                      : rrr_vector<63>  = u64 size, bt (int_vector<0>: u64 bit_len, u8 width,
+//                                words), btnr (int_vector<1>), btnrp, rank (int_vector<0>), invert
+//                                (int_vector<1>)   (reference: sdsl rrr_vector.hpp:350-373)
+//   .misc                      : text: dollar_position, counts[0..3], k  (fms_index.h:493-499)
+//
+// The RRR<63> block code (class = popcount, offset = rank of the 63-bit word inside its class in
+// the combinatorial number system) is decoded ONCE at load into plain bits; the GPU never sees RRR.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace fmsi {
+
+struct BitVec {
+    uint64_t nbits = 0;
+    std::vector<uint64_t> w;  // ceil(nbits/64)+1 words, zero padded
+    bool get(uint64_t p) const { return (w[p >> 6] >> (p & 63)) & 1; }
+    void set(uint64_t p) { w[p >> 6] |= 1ull << (p & 63); }
+    void resize_bits(uint64_t n) {
+        nbits = n;
+        w.assign(((n + 63) >> 6) + 1, 0);
+    }
+    // len <= 64 bits starting at bit pos, least significant first
+    uint64_t get_int(uint64_t pos, unsigned len) const {
+        if (len == 0) return 0;
+        uint64_t wi = pos >> 6;
+        unsigned off = pos & 63;
+        uint64_t x = w[wi] >> off;
+        if (off + len > 64) x |= w[wi + 1] << (64 - off);
+        if (len < 64) x &= (1ull << len) - 1;
+        return x;
+    }
+    void set_int(uint64_t pos, uint64_t x, unsigned len) {
+        for (unsigned t = 0; t < len; ++t)
+            if ((x >> t) & 1) set(pos + t);
+    }
+};
+
+struct IntVec {
+    BitVec bits;
+    unsigned width = 0;
+    uint64_t n = 0;
+    uint64_t get(uint64_t i) const { return bits.get_int(i * width, width); }
+    void alloc(uint64_t n_, unsigned width_) {
+        n = n_;
+        width = width_;
+        bits.resize_bits(n_ * width_);
+    }
+    void set(uint64_t i, uint64_t x) { bits.set_int(i * width, x, width); }
+};
+
+class ByteReader {
+  public:
+    explicit ByteReader(const std::string &path) {
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open " + path);
+        std::fseek(f, 0, SEEK_END);
+        long sz = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        buf_.resize((size_t)sz);
+        if (sz > 0 && std::fread(buf_.data(), 1, (size_t)sz, f) != (size_t)sz) {
+            std::fclose(f);
+            throw std::runtime_error("short read on " + path);
+        }
+        std::fclose(f);
+        path_ = path;
+    }
+    uint64_t u64() {
+        need(8);
+        uint64_t v;
+        std::memcpy(&v, buf_.data() + pos_, 8);
+        pos_ += 8;
+        return v;
+    }
+    unsigned u8() {
+        need(1);
+        return buf_[pos_++];
+    }
+    void words(uint64_t *dst, uint64_t n) {
+        need(n * 8);
+        std::memcpy(dst, buf_.data() + pos_, n * 8);
+        pos_ += n * 8;
+    }
+    bool at_end() const { return pos_ == buf_.size(); }
+    void read_bitvec(BitVec &b) {
+        uint64_t nbits = u64();
+        b.resize_bits(nbits);
+        words(b.w.data(), (nbits + 63) >> 6);
+    }
+    void read_intvec(IntVec &v) {
+        uint64_t nbits = u64();
+        unsigned width = u8();
+        if (width == 0 || width > 64) throw std::runtime_error("bad int_vector width in " + path_);
+        v.width = width;
+        v.n = nbits / width;
+        v.bits.resize_bits(nbits);
+        words(v.bits.w.data(), (nbits + 63) >> 6);
+    }
+
+  private:
+    void need(uint64_t n) {
+        if (pos_ + n > buf_.size()) throw std::runtime_error("truncated file " + path_);
+    }
+    std::vector<uint8_t> buf_;
+    size_t pos_ = 0;
+    std::string path_;
+};
+
+// ---- RRR<63>, samples every 32 blocks -----------------------------------------------------------
+constexpr unsigned kRrrBlock = 63;
+constexpr unsigned kRrrSample = 32;
+
+struct Binomials {
+    uint64_t c[65][65];
+    unsigned space[64];  // bits of the offset field for a class (0 for the two uniform classes)
+    Binomials() {
+        for (int n = 0; n <= 64; ++n)
+            for (int k = 0; k <= 64; ++k) c[n][k] = 0;
+        for (int n = 0; n <= 64; ++n) {
+            c[n][0] = 1;
+            for (int k = 1; k <= n; ++k) c[n][k] = c[n - 1][k - 1] + (k <= n - 1 ? c[n - 1][k] : 0);
+        }
+        for (unsigned k = 0; k <= kRrrBlock; ++k) {
+            uint64_t v = c[kRrrBlock][k];
+            space[k] = (v == 1) ? 0 : (64 - (unsigned)__builtin_clzll(v));
+        }
+    }
+    static const Binomials &get() {
+        static Binomials b;
+        return b;
+    }
+};
+
+// Expand one block: `ones` set bits, `nr` = index inside the class. Bit t of the result is
+// position t of the block. (Follows the coder described by sdsl rrr_helper.hpp:304-320 / :374-407.)
+inline uint64_t rrr_unrank(unsigned ones, uint64_t nr) {
+    if (ones == 0) return 0;
+    if (ones == kRrrBlock) return (1ull << kRrrBlock) - 1;
+    const Binomials &B = Binomials::get();
+    uint64_t word = 0;
+    unsigned left = kRrrBlock;
+    for (unsigned pos = 0; pos < kRrrBlock && ones > 0; ++pos, --left) {
+        uint64_t below = B.c[left - 1][ones];  // words of this class whose bit `pos` is 0
+        if (nr >= below) {
+            word |= 1ull << pos;
+            nr -= below;
+            --ones;
+        }
+    }
+    return word;
+}
+inline uint64_t rrr_rank_of_word(uint64_t word) {
+    const Binomials &B = Binomials::get();
+    unsigned ones = (unsigned)__builtin_popcountll(word);
+    if (ones == 0 || ones == kRrrBlock) return 0;
+    uint64_t nr = 0;
+    unsigned left = kRrrBlock;
+    for (unsigned pos = 0; pos < kRrrBlock && ones > 0; ++pos, --left) {
+        if ((word >> pos) & 1) {
+            nr += B.c[left - 1][ones];
+            --ones;
+        }
+    }
+    return nr;
+}
+
+struct RrrFile {
+    uint64_t size = 0;
+    IntVec bt;
+    BitVec btnr;
+    IntVec btnrp;
+    IntVec rank;
+    BitVec invert;
+};
+
+inline RrrFile read_rrr(const std::string &path) {
+    ByteReader r(path);
+    RrrFile f;
+    f.size = r.u64();
+    r.read_intvec(f.bt);
+    r.read_bitvec(f.btnr);
+    r.read_intvec(f.btnrp);
+    r.read_intvec(f.rank);
+    r.read_bitvec(f.invert);
+    if (!r.at_end()) throw std::runtime_error("trailing bytes in " + path);
+    return f;
+}
+
+// Decode the whole vector into plain bits. Also verifies the stored samples (btnrp, rank) and the
+// total, so a corrupt .mask is rejected at load instead of producing wrong answers.
+inline BitVec rrr_decode_all(const RrrFile &f) {
+    const Binomials &B = Binomials::get();
+    BitVec out;
+    out.resize_bits(f.size);
+    uint64_t nblocks = (f.size + kRrrBlock) / kRrrBlock;
+    if (f.bt.n < nblocks) throw std::runtime_error("rrr: bt array too short");
+    uint64_t off = 0, ones_total = 0;
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        uint64_t sb = b / kRrrSample;
+        if (b % kRrrSample == 0) {
+            if (sb >= f.btnrp.n || f.btnrp.get(sb) != off) throw std::runtime_error("rrr: btnrp sample mismatch");
+            if (sb >= f.rank.n || f.rank.get(sb) != ones_total) throw std::runtime_error("rrr: rank sample mismatch");
+        }
+        uint64_t pos0 = b * kRrrBlock;
+        if (pos0 >= f.size) break;  // trailing dummy block when size % 63 == 0
+        unsigned stored = (unsigned)f.bt.get(b);
+        unsigned ones = f.invert.get(sb) ? kRrrBlock - stored : stored;
+        unsigned len = B.space[stored];
+        uint64_t nr = f.btnr.get_int(off, len);
+        off += len;
+        uint64_t word = rrr_unrank(ones, nr);
+        unsigned valid = (unsigned)std::min<uint64_t>(kRrrBlock, f.size - pos0);
+        if (valid < kRrrBlock && (word >> valid)) throw std::runtime_error("rrr: padding bits set");
+        ones_total += (unsigned)__builtin_popcountll(word);
+        for (unsigned t = 0; t < valid; ++t)
+            if ((word >> t) & 1) out.set(pos0 + t);
+    }
+    if (f.rank.n == 0 || f.rank.get(f.rank.n - 1) != ones_total) throw std::runtime_error("rrr: total mismatch");
+    return out;
+}
+
+}  // namespace fmsi

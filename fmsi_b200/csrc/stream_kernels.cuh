@@ -1,0 +1,371 @@
+// stream_kernels.cuh — chunk helpers and the kLCP streaming kernel.
+//
+// stream_kernel restates query_kmers_streaming (reference src/fms_index.h:181-254) with one LANE per
+// chunk of <= 64 k-mers: pass 0 walks the chunk right to left on the forward strand, pass 1 walks
+// the reverse-complement strand over the positions pass 0 left undecided (all positions for
+// STRANDS_BOTH). While the interval of the neighbouring k-mer is non-empty the next k-mer costs
+//     MX   : one aux sector (two if [i, j) straddles a block) — the mask probe of the current k-mer
+//            AND the kLCP extension (extend_range_with_klcp, :106-109) for the next one come from
+//            the same sectors, because mask and kLCP bits of a 64-position block share a sector;
+//     STEP : one LF-step (update_range, :98-103);
+// after a miss the search restarts from the suffix table like a single query. Lanes are refilled
+// with the next chunk as soon as they finish, exactly as in query_kmers_kernel. The chunk's bases
+// (<= 95) live in three registers, so no base is re-read from memory.
+//
+// The engine may chunk differently from ms_query (main.cpp:329-331): per-k-mer strand results do
+// not depend on chunk boundaries; the boundaries only feed the strand predictor, which the host
+// replays on its own (predictor.hpp).
+#pragma once
+#include "query_kernels.cuh"
+
+namespace fmsi {
+
+constexpr int kStreamBlock = 256;
+constexpr u32 kMaxStreamKmers = 64;
+
+// ASCII ACGTacgt -> 2-bit code (A=0 C=1 G=2 T=3): bits 1-2 of the character are 00,01,11,10.
+__device__ __forceinline__ u32 base_code(unsigned char ch) {
+    const u32 x = (ch >> 1) & 3u;
+    return x ^ (x >> 1);
+}
+
+// Packed text: base b sits at bits [62 - 2(b & 31), 63 - 2(b & 31)] of word b >> 5, so that a window
+// read is already in k-mer order (first base highest).
+__global__ void pack_bases_kernel(const char *__restrict__ bases, const u64 n_bases, u64 *__restrict__ packed,
+                                  const u64 n_words) {
+    const u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    u64 v = 0;
+    const u64 b0 = w * 32;
+#pragma unroll 8
+    for (u32 t = 0; t < 32; ++t) {
+        const u64 b = b0 + t;
+        const u32 code = (b < n_bases) ? base_code((unsigned char)bases[b]) : 0u;
+        v = (v << 2) | code;
+    }
+    packed[w] = v;
+}
+
+// len (<= 32) bases starting at base s, as a packed k-mer.
+__device__ __forceinline__ u64 window(const u64 *__restrict__ packed, u64 s, u32 len) {
+    const u64 w0 = __ldg(packed + (s >> 5)), w1 = __ldg(packed + (s >> 5) + 1);
+    const u32 sh = 2u * ((u32)s & 31u);
+    const u64 v = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+    return v >> (64 - 2 * len);
+}
+
+// Non-streaming chunks: one thread per result slot materialises its k-mer; the single-query kernel
+// then runs over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
+__global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
+                                     const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks,
+                                     const u64 n_results, const u32 k, u64 *__restrict__ kmers) {
+    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r >= n_results) return;
+    u64 lo = 0, hi = n_chunks;  // last chunk with roff <= r
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (roff[mid] <= r) lo = mid;
+        else hi = mid;
+    }
+    const u64 pos = r - roff[lo];
+    u64 km = 0;
+    if (roff[lo] <= r && clen[lo] >= k && pos + k <= clen[lo]) km = window(packed, coff[lo] + pos, k);
+    kmers[r] = km;
+}
+
+enum { SP_TABLE = 0, SP_STEP = 1, SP_MX = 2 };
+
+__device__ __forceinline__ u64 sel3(u32 w, u64 w0, u64 w1, u64 w2) { return w == 0 ? w0 : (w == 1 ? w1 : w2); }
+
+template <int MODE, int OUT, int STRANDS, bool WIDE>
+__global__ void __launch_bounds__(kStreamBlock)
+stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__restrict__ coff,
+              const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks, void *out,
+              unsigned long long *__restrict__ cursor, const u32 grab) {
+    typedef typename PosT<WIDE>::type pos_t;
+    const unsigned FULL = 0xffffffffu;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const u32 t = d.t, k = d.k;
+    const u64 tmask = t ? ((t >= 32) ? ~0ull : ((1ull << (2 * t)) - 1ull)) : 0ull;
+    const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
+
+    bool active = false;
+    u32 phase = SP_TABLE, pass = 0, p = 0, nk = 0, steps = 0;
+    u64 ro = 0, decided = 0, pat = 0, w0 = 0, w1 = 0, w2 = 0;
+    pos_t i = 0, j = 0;
+    u64 cnext = 0, cend = 0;
+    bool exhausted = false;
+
+    // k-mer at chunk position q from the register-resident bases
+    auto kmer_at = [&](u32 q) -> u64 {
+        const u32 wi = q >> 5, sh = 2u * (q & 31u);
+        const u64 a = sel3(wi, w0, w1, w2), b = sel3(wi + 1, w0, w1, w2);
+        const u64 v = sh ? ((a << sh) | (b >> (64 - sh))) : a;
+        return v >> (64 - 2 * k);
+    };
+    auto base_at = [&](u32 q) -> u32 {
+        return (u32)(sel3(q >> 5, w0, w1, w2) >> (62 - 2 * (q & 31u))) & 3u;
+    };
+    auto begin_fresh = [&](u32 q) {
+        const u64 km = kmer_at(q);
+        pat = pass ? revcomp_packed(km, k) : km;
+        if (t) {
+            phase = SP_TABLE;
+        } else {
+            phase = SP_STEP;
+            i = 0;
+            j = (pos_t)d.n;
+            steps = k;
+        }
+    };
+
+    for (;;) {
+        // ---------------------------------------------------------------- refill idle lanes
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (need && !exhausted) {
+            if (cnext >= cend) {
+                unsigned long long c0 = 0;
+                if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)grab);
+                c0 = __shfl_sync(FULL, c0, 0);
+                if (c0 >= n_chunks) exhausted = true;
+                else {
+                    cnext = c0;
+                    cend = (c0 + grab < n_chunks) ? c0 + grab : n_chunks;
+                }
+            }
+            if (!exhausted) {
+                const u64 my = cnext + __popc(need & lt_mask);
+                const bool take = !active && my < cend;
+                const u64 left = cend - cnext;
+                const u32 want = __popc(need);
+                cnext += (want < left) ? want : left;
+                if (take) {
+                    const u64 cs = coff[my];
+                    const u32 len = clen[my];
+                    ro = roff[my];
+                    nk = len - k + 1;
+                    if (len >= k && nk <= kMaxStreamKmers) {
+                        // bases cs .. cs+95 as three aligned-to-chunk words
+                        const u64 *pw = packed + (cs >> 5);
+                        const u64 q0 = __ldg(pw), q1 = __ldg(pw + 1), q2 = __ldg(pw + 2);
+                        const u32 sh = 2u * ((u32)cs & 31u);
+                        if (sh) {
+                            const u64 q3 = __ldg(pw + 3);
+                            w0 = (q0 << sh) | (q1 >> (64 - sh));
+                            w1 = (q1 << sh) | (q2 >> (64 - sh));
+                            w2 = (q2 << sh) | (q3 >> (64 - sh));
+                        } else {
+                            w0 = q0;
+                            w1 = q1;
+                            w2 = q2;
+                        }
+                        active = true;
+                        pass = 0;
+                        decided = 0;
+                        p = nk - 1;
+                        begin_fresh(p);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---------------------------------------------------------------- loads
+        const bool isT = active && phase == SP_TABLE;
+        const bool isS = active && phase == SP_STEP;
+        const bool isM = active && phase == SP_MX;
+        // Will the next k-mer of this pass continue from this interval?
+        bool will_cont = false;
+        if (isM) {
+            if (pass == 0) will_cont = p > 0;
+            else will_cont = (p + 1 < nk) && (STRANDS == K_STRANDS_BOTH || !((decided >> (p + 1)) & 1ull));
+        }
+        const u64 bi = (u64)i >> 6;
+        const u64 bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+        const bool two = (isS || (isM && (need_j || will_cont))) && (bj != bi);
+        u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        pos_t ti = 0, tj = 0;
+        if (isT) ld_table<WIDE>(d.table, pat & tmask, ti, tj);
+        if (isS || isM) {
+            const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
+            ld_sector_l1(pa, a0, a1, a2, a3);
+            if (two) {
+                const void *pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
+                ld_sector_l1(pb, b0, b1, b2, b3);
+            }
+        }
+
+        // ---------------------------------------------------------------- consume
+        bool finished = false;  // the k-mer at position p got its value for this pass
+        bool nonempty = false;
+        long long res = -1;
+        if (isT) {
+            i = ti;
+            j = tj;
+            pat >>= 2 * t;
+            steps = k - t;
+            if (i == j) finished = true;
+            else phase = steps ? SP_STEP : SP_MX;
+        } else if (isS) {
+            const u32 c = (u32)pat & 3u;
+            pat >>= 2;
+            if (!two) {
+                b0 = a0; b1 = a1; b2 = a2; b3 = a3;
+            }
+            const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
+            const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
+            i = ni;
+            j = nj;
+            --steps;
+            if (i == j) finished = true;
+            else if (steps == 0) phase = SP_MX;
+        } else if (isM) {
+            if (!two) {
+                b0 = a0; b1 = a1; b2 = a2;
+            }
+            res = strand_result<MODE, OUT>((u64)i, (u64)j, a1, a2, b1, b2);
+            finished = true;
+            nonempty = true;
+        }
+
+        if (finished) {
+            // ---- record (fms_index.h:200-207 / :224-233)
+            const u64 slot = ro + p;
+            if (pass == 0) {
+                bool dec;
+                if (OUT == K_OUT_ORDERS) dec = res >= 0;
+                else if (MODE == K_MODE_ALL) dec = res != -1;
+                else dec = res == 1;
+                if (dec) decided |= 1ull << p;
+                if (OUT == K_OUT_PRESENCE) {
+                    reinterpret_cast<unsigned char *>(out)[slot] =
+                        (STRANDS == K_STRANDS_BOTH) ? (unsigned char)(res + 1) : (unsigned char)(res == 1);
+                } else if (STRANDS == K_STRANDS_BOTH) {
+                    reinterpret_cast<long long *>(out)[2 * slot] = res;
+                } else {
+                    reinterpret_cast<long long *>(out)[slot] = res;
+                }
+            } else {
+                if (OUT == K_OUT_PRESENCE) {
+                    unsigned char *o = reinterpret_cast<unsigned char *>(out) + slot;
+                    if (STRANDS == K_STRANDS_BOTH) *o = (unsigned char)(*o | ((res + 1) << 2));
+                    else *o = (unsigned char)(res == 1);
+                } else if (STRANDS == K_STRANDS_BOTH) {
+                    reinterpret_cast<long long *>(out)[2 * slot + 1] = res;
+                } else {
+                    reinterpret_cast<long long *>(out)[slot] = res;
+                }
+            }
+            // ---- next position of this pass, or next pass, or chunk done
+            bool have_next = false, adjacent = false;
+            u32 q = 0;
+            if (pass == 0) {
+                if (p > 0) {
+                    q = p - 1;
+                    have_next = adjacent = true;
+                } else {
+                    pass = 1;
+                    const u64 und = (STRANDS == K_STRANDS_BOTH) ? ~0ull : ~decided;
+                    const u64 cand = und & ((nk >= 64) ? ~0ull : ((1ull << nk) - 1ull));
+                    if (cand) {
+                        q = (u32)__ffsll((long long)cand) - 1;
+                        have_next = true;
+                    }
+                }
+            } else {
+                const u64 und = (STRANDS == K_STRANDS_BOTH) ? ~0ull : ~decided;
+                u64 cand = und & ((nk >= 64) ? ~0ull : ((1ull << nk) - 1ull));
+                cand &= ~((2ull << p) - 1ull);  // positions > p
+                if (cand) {
+                    q = (u32)__ffsll((long long)cand) - 1;
+                    have_next = true;
+                    adjacent = q == p + 1;
+                }
+            }
+            if (!have_next) {
+                active = false;
+            } else if (nonempty && adjacent) {
+                // ---- extend_range_with_klcp from the sectors already in registers, then one step
+                u64 ei = (u64)i, ej = (u64)j;
+                bool slow = false;
+                {
+                    const u64 pj = ej - 1;  // block bj: klcp word b0 (== a0 when !two)
+                    const u64 z = ~b0 & ~low_mask((u32)pj & 63u);
+                    if (z) ej = (pj & ~63ull) + (u64)(__ffsll((long long)z) - 1) + 1;
+                    else slow = true;
+                }
+                {
+                    const u64 pi = ei - 1;
+                    if ((pi >> 6) == bi) {
+                        const u64 z = ~a0 & ((2ull << (pi & 63)) - 1ull);
+                        if (z) ei = (pi & ~63ull) + (u64)(63 - __clzll((long long)z)) + 1;
+                        else slow = true;
+                    } else {
+                        slow = true;
+                    }
+                }
+                if (slow) {  // run of ones crosses a block boundary: rare, plain loop
+                    ei = (u64)i;
+                    ej = (u64)j;
+                    dev_extend_klcp(d, ei, ej);
+                }
+                i = (pos_t)ei;
+                j = (pos_t)ej;
+                // pass 0 prepends base q; pass 1 prepends the complement of base q+k-1
+                pat = pass == 0 ? base_at(q) : (3u - base_at(q + k - 1));
+                steps = 1;
+                phase = SP_STEP;
+                p = q;
+            } else {
+                p = q;
+                begin_fresh(q);
+            }
+        }
+    }
+}
+
+template <int MODE, int OUT, int STRANDS, bool WIDE>
+int launch_stream(int sm_count, const DevIndex &d, const u64 *packed, const u64 *coff, const u32 *clen, const u64 *roff,
+                  size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st) {
+    auto kern = stream_kernel<MODE, OUT, STRANDS, WIDE>;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = sm_count * per_sm;
+    const size_t warps = (size_t)grid * (kStreamBlock / 32);
+    size_t grab = n_chunks / (warps * 8 + 1);
+    if (grab < 32) grab = 32;
+    if (grab > 512) grab = 512;
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kStreamBlock, 0, st>>>(d, packed, coff, clen, roff, (u64)n_chunks, out, cursor, (u32)grab);
+    return (int)cudaGetLastError();
+}
+
+template <int MODE, int OUT, int STRANDS>
+int launch_stream_w(bool wide, int sm_count, const DevIndex &d, const u64 *packed, const u64 *coff, const u32 *clen,
+                    const u64 *roff, size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st) {
+    if (wide) return launch_stream<MODE, OUT, STRANDS, true>(sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+    return launch_stream<MODE, OUT, STRANDS, false>(sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+}
+
+// returns a cudaError_t as int (0 = ok)
+inline int dispatch_stream(bool wide, int sm_count, const DevIndex &d, int mode, int output, int strands,
+                           const u64 *packed, const u64 *coff, const u32 *clen, const u64 *roff, size_t n_chunks,
+                           void *out, unsigned long long *cursor, cudaStream_t st) {
+    if (output == K_OUT_ORDERS) {
+        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+        return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+    }
+    if (mode == K_MODE_ALL) {
+        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+        return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+    }
+    if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+    return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+}
+
+}  // namespace fmsi

@@ -1,0 +1,147 @@
+/* fmsi_gpu.h — C-ABI of libfmsi_gpu.so: the B200 (sm_100a) drop-in for FMSI's query path.
+ *
+ * The reference (OndrejSladky/fmsi v0.4.0) has no FFI; its query path is reached through the
+ * function-level seam `load_index()` + `query_kmers<mode>()` called from `ms_query`
+ * (reference src/main.cpp:302, :344-350). Every entry point below names the reference function
+ * it replaces (paths relative to the reference root). INTEGRATION.md shows the binding a
+ * maintainer adds to the reference's main.cpp.
+ *
+ * Conventions
+ *  - plain C types only; all functions return FMSI_GPU_OK (0) or a negative error code, and
+ *    fmsi_gpu_last_error() returns a thread-local message for the last failure;
+ *  - k-mers are packed 2 bits per base, A=0 C=1 G=2 T=3 (reference src/kmers.h:3-20), first base
+ *    in the highest used bits: kmer = sum base[t] << 2*(k-1-t), k <= 32;
+ *  - SA intervals are half-open [i, j) over [0, N], N = n+1 = sa_transformed_mask.size();
+ *  - `mem` says where the query/result buffers live: FMSI_GPU_MEM_HOST (the library stages them
+ *    through its own pinned/device buffers and returns when results are in host memory) or
+ *    FMSI_GPU_MEM_DEVICE (device pointers; the call enqueues on `stream` and does not synchronise);
+ *  - there is NO CPU fallback: every call fails with FMSI_GPU_ERR_CUDA when no usable device exists.
+ */
+#ifndef FMSI_GPU_H
+#define FMSI_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMSI_GPU_ABI_VERSION 1
+
+enum {
+    FMSI_GPU_OK = 0,
+    FMSI_GPU_ERR_ARG = -1,     /* bad argument */
+    FMSI_GPU_ERR_IO = -2,      /* index files missing / malformed ("index not correctly loaded") */
+    FMSI_GPU_ERR_CUDA = -3,    /* CUDA runtime failure or no device */
+    FMSI_GPU_ERR_KLCP = -4,    /* streaming requested but the index has no kLCP array */
+    FMSI_GPU_ERR_K = -5,       /* k does not match the index / k unsupported */
+    FMSI_GPU_ERR_NOMEM = -6
+};
+
+/* query_mode, reference src/fms_index.h:256-260 (`general` / -f functions are out of scope). */
+enum { FMSI_GPU_MODE_OR = 0, FMSI_GPU_MODE_ALL = 1 };
+/* output_orders of query_kmers(): presence bits (`fmsi query`) or mask-rank ids (`fmsi lookup`). */
+enum { FMSI_GPU_OUT_PRESENCE = 0, FMSI_GPU_OUT_ORDERS = 1 };
+/* Strand policy.
+ *  LAZY: forward strand first, reverse complement only if undecided — the reference's evaluation
+ *        order with a neutral strand predictor (src/fms_index.h:268-299 with should_swap == false).
+ *  BOTH: always evaluate both strands and return both values, so the host can replay the
+ *        reference's stateful strand_predictor (src/fms_index.h:18-49) exactly, whatever it says. */
+enum { FMSI_GPU_STRANDS_LAZY = 0, FMSI_GPU_STRANDS_BOTH = 1 };
+enum { FMSI_GPU_MEM_HOST = 0, FMSI_GPU_MEM_DEVICE = 1 };
+
+typedef struct fmsi_gpu_index fmsi_gpu_index;
+
+typedef struct {
+    int32_t prefix_t;      /* depth of the k-mer suffix lookup table; -1 = auto, 0 = none */
+    int32_t sb_shift_log2; /* test hook: superblock size (log2 blocks); 0 = auto */
+    int64_t reserved[6];
+} fmsi_gpu_options;
+
+typedef struct {
+    uint64_t n_bwt;      /* N */
+    uint64_t counts[4];  /* C-array of the reference's .misc */
+    uint64_t dollar_position;
+    uint64_t mask_ones;  /* number of represented occurrences = size of the lookup id space */
+    uint64_t hbm_bytes;  /* device memory held by this index */
+    int32_t k;
+    int32_t has_klcp;
+    int32_t prefix_t;
+    int32_t wide;        /* 1 when N >= 2^32 (64-bit positions on device) */
+    int32_t device;
+    int32_t reserved[7];
+} fmsi_gpu_index_info;
+
+const char *fmsi_gpu_last_error(void);
+int fmsi_gpu_abi_version(void);
+int fmsi_gpu_device_count(void);
+
+/* load_index(fn, use_klcp) — reference src/fms_index.h:502-526. Reads
+ * <prefix>.fmsi.{ac_gt,ac,gt,mask,klcp,misc}, converts them to the blocked GPU layout and uploads
+ * it to `device`. opts may be NULL. */
+int fmsi_gpu_index_load(const char *prefix, int use_klcp, int device, const fmsi_gpu_options *opts,
+                        fmsi_gpu_index **out);
+/* In-memory construction from raw bit arrays (one byte per bit) — the form of the hand-built
+ * fixtures in the reference's unit tests (tests/fms_index_test.h:10-69). klcp may be NULL. */
+int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t *ac, size_t n_ac,
+                             const uint8_t *gt, size_t n_gt, const uint8_t *mask, size_t n_mask,
+                             const uint64_t counts[4], uint64_t dollar_position, const uint8_t *klcp,
+                             size_t n_klcp, int k, int device, const fmsi_gpu_options *opts,
+                             fmsi_gpu_index **out);
+int fmsi_gpu_index_free(fmsi_gpu_index *idx);
+int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info);
+
+/* ---- building blocks, one device thread per element; host arrays in and out ---------------- */
+/* rank(index, i, c) — reference src/fms_index.h:68-86. */
+int fmsi_gpu_rank(fmsi_gpu_index *idx, const uint64_t *i, const uint8_t *c, size_t n, uint64_t *out);
+/* update_range(index, i, j, c) — src/fms_index.h:98-103. In place. */
+int fmsi_gpu_update_range(fmsi_gpu_index *idx, uint64_t *i, uint64_t *j, const uint8_t *c, size_t n);
+/* extend_range_with_klcp(index, i, j) — src/fms_index.h:106-109. In place. */
+int fmsi_gpu_extend_range_with_klcp(fmsi_gpu_index *idx, uint64_t *i, uint64_t *j, size_t n);
+/* get_range_with_pattern(index, sa_start, sa_end, pattern, k) — src/fms_index.h:117-124; patterns
+ * are packed k-mers, any 1 <= k <= 32. use_table: 0 = plain k LF-steps, 1 = through the suffix
+ * table (an empty interval may then be reported as any i == j). */
+int fmsi_gpu_get_range_with_pattern(fmsi_gpu_index *idx, const uint64_t *kmers, int k, size_t n,
+                                    int use_table, uint64_t *sa_start, uint64_t *sa_end);
+/* infer_presence<maximized_ones>(index, sa_start, sa_end) — src/fms_index.h:126-144: -1/0/1. */
+int fmsi_gpu_infer_presence(fmsi_gpu_index *idx, const uint64_t *sa_start, const uint64_t *sa_end,
+                            size_t n, int maximized_ones, int8_t *out);
+/* kmer_order_if_present(index, sa_start, sa_end) — src/fms_index.h:150-156. */
+int fmsi_gpu_kmer_order_if_present(fmsi_gpu_index *idx, const uint64_t *sa_start,
+                                   const uint64_t *sa_end, size_t n, int64_t *out);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* query_kmers_single<mode>() over n independent packed k-mers — reference src/fms_index.h:263-331
+ * (one k-mer per element instead of one chunk per call).
+ * results layout:
+ *   PRESENCE, LAZY : uint8[n]     1 iff the reference prints '1'
+ *   PRESENCE, BOTH : uint8[n]     (f+1) | (r+1) << 2, f/r = single_query_or<> on the k-mer / its RC
+ *   ORDERS,   LAZY : int64[n]     the id the reference prints (-1 absent)
+ *   ORDERS,   BOTH : int64[2n]    {f, r} = single_query_order on the k-mer / its RC
+ * k must equal the index's k. */
+int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
+                         const uint64_t *kmers, size_t n, int k, void *results, int mem,
+                         void *stream);
+
+/* query_kmers<mode>() over chunks of ACGT text — reference src/fms_index.h:333-342, i.e.
+ * query_kmers_streaming (:181-254) when `streaming` != 0 (needs kLCP) else query_kmers_single.
+ * bases: ASCII ACGTacgt only (the caller splits records at other characters like
+ * ms_query, src/main.cpp:337-370); chunk c is bases[chunk_off[c] .. chunk_off[c]+chunk_len[c]),
+ * chunk_len[c] >= k, and yields chunk_len[c]-k+1 results starting at result index res_off[c].
+ * With streaming != 0 a chunk holds at most FMSI_GPU_MAX_STREAM_KMERS k-mers.
+ * results layout as for fmsi_gpu_query_kmers with n = total number of k-mers. */
+#define FMSI_GPU_MAX_STREAM_KMERS 64
+int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
+                          const char *bases, size_t n_bases, const uint64_t *chunk_off,
+                          const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
+                          size_t n_results, int k, void *results, int mem, void *stream);
+
+/* Number of kernel launches issued by this library on behalf of the calling process so far
+ * (bench.py reports it as gpu_launches). */
+uint64_t fmsi_gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
