@@ -52,7 +52,7 @@ struct HostIndex {
     std::vector<uint64_t> sb_base;  // [n_superblocks][4]
     std::vector<RankBlock> rank;
     std::vector<AuxBlock> aux;
-    bool wide() const { return sb_base.size() > 4; }
+    bool wide() const { return sb_shift < 63; }
 };
 
 // Deposit the low popcount(sel) bits of `src` into the set positions of `sel` (software PDEP).

@@ -1,0 +1,302 @@
+"""GPU parity tests: every call goes through the C-ABI of libfmsi_gpu.so (ctypes) and is compared
+bit for bit with the oracle on the same inputs, with the reference's unit goldens, and with the
+reference binary's committed outputs. Integer work: the tolerance is zero."""
+import json
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle_ffi import FIXTURES, MODE_ALL, MODE_OR, REF_EXE, OracleIndex
+
+import fmsi_b200 as fg
+from fmsi_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("oracle_built")]
+
+L = "ACGT"
+
+
+def pack(s: str) -> int:
+    v = 0
+    for ch in s:
+        v = (v << 2) | L.index(ch.upper())
+    return v
+
+
+def gpu_fixture(n, **kw):
+    f = FIXTURES[n]
+    return fg.Index.from_bits(f["ac_gt"], f["ac"], f["gt"], f["mask"], f["counts"], f["dollar"], f["klcp"], k=3, **kw)
+
+
+def test_library_is_native_and_device_present():
+    assert os.path.exists(fg.lib_path())
+    assert fg.device_count() >= 1
+    assert fg.lib().fmsi_gpu_abi_version() == 1
+
+
+# ---- the reference's unit goldens against the device building blocks ------------------------------
+@pytest.mark.parametrize("t", [0, 1, -1])
+def test_unit_goldens_on_device(t):
+    idx = gpu_fixture(1, prefix_t=t)
+    cases = [(4, 3, 1), (1, 3, 0), (1, 2, 1), (5, 0, 1), (7, 1, 1), (7, 2, 2), (8, 2, 3), (0, 2, 0)]  # RANK :71-94
+    got = idx.rank([c[0] for c in cases], [c[1] for c in cases])
+    assert got.tolist() == [c[2] for c in cases]
+    ur = [(0, 8, 0, 1, 3), (0, 5, 0, 1, 2), (4, 5, 0, 1, 2), (5, 6, 0, 2, 3), (0, 8, 1, 3, 4), (0, 8, 2, 4, 7), (0, 8, 3, 7, 8), (0, 2, 0, 1, 1)]
+    gi, gj = idx.update_range([c[0] for c in ur], [c[1] for c in ur], [c[2] for c in ur])  # UPDATE_RANGE :116-142
+    assert gi.tolist() == [c[3] for c in ur] and gj.tolist() == [c[4] for c in ur]
+    idx2 = gpu_fixture(2, prefix_t=t)
+    assert idx2.rank([4, 5, 6], [0, 0, 0]).tolist() == [2, 3, 3]  # RANK2 :96-114
+
+    idx3 = gpu_fixture(3, prefix_t=t)
+    ex = [(4, 6, 4, 7), (4, 5, 4, 7), (5, 6, 4, 7), (2, 3, 1, 3), (1, 2, 1, 3), (3, 4, 3, 4)]  # EXTEND_RANGE_WITH_KLCP :144-167
+    gi, gj = idx3.extend_range_with_klcp([c[0] for c in ex], [c[1] for c in ex])
+    assert gi.tolist() == [c[2] for c in ex] and gj.tolist() == [c[3] for c in ex]
+    for pat, wi, wj in [("ACA", 1, 3), ("CAC", 4, 6), ("CAT", 6, 7), ("AAA", 1, 1), ("TAC", 8, 8), ("A", 1, 4), ("CA", 4, 7), ("T", 7, 8)]:
+        for use_table in (False, True):  # GET_RANGE_WITH_PATTERN :169-196
+            gi, gj = idx3.get_range_with_pattern([pack(pat)], len(pat), use_table)
+            if wi == wj:
+                assert gi[0] == gj[0]  # empty (through the table any i == j stands for empty)
+                if not use_table:
+                    assert (gi[0], gj[0]) == (wi, wj)
+            else:
+                assert (gi[0], gj[0]) == (wi, wj)
+    ko = [(1, 2, 0), (2, 3, -1), (1, 1, -1), (3, 4, -1), (4, 6, 1), (5, 6, 2), (1, 6, 0)]  # KMER_ORDER_IF_PRESENT :198-220
+    assert idx3.kmer_order_if_present([c[0] for c in ko], [c[1] for c in ko]).tolist() == [c[2] for c in ko]
+
+
+def test_streaming_and_query_goldens_on_device():
+    idx3 = gpu_fixture(3)
+    # QUERY_KMERS_STREAMING :223-249 and _ORDERS :251-276 (results here do not depend on the predictor)
+    for q, mo, want in [("CACATACA", False, "111001"), ("TGTATGTG", False, "100111"), ("CACATTGT", False, "111001"), ("CACATACA", True, "111001")]:
+        got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, mode=fg.MODE_ALL if mo else fg.MODE_OR, streaming=True)
+        assert "".join(map(str, got.tolist())) == want
+        got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, mode=fg.MODE_ALL if mo else fg.MODE_OR, streaming=False)
+        assert "".join(map(str, got.tolist())) == want
+    for q, want in [("CACATACA", [1, 0, 3, -1, -1, 0]), ("TGTATGTG", [0, -1, -1, 3, 0, 1]), ("CACATTGT", [1, 0, 3, -1, -1, 0])]:
+        for streaming in (True, False):
+            got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, output=fg.OUT_ORDERS, streaming=streaming)
+            assert got.tolist() == want
+    idx1 = gpu_fixture(1)
+    # QUERY_ORDERS :278-306 / QUERY :308-332 (k varies per case)
+    for q, k, want in [("A", 1, [3]), ("AG", 2, [-1]), ("CA", 2, [0]), ("AC", 2, [2]), ("TA", 2, [3]), ("GGTA", 4, [1]), ("ATGG", 4, [-1]),
+                       ("GA", 2, [-1]), ("GGG", 3, [-1]), ("CC", 2, [1]), ("CCAG", 2, [1, 0, -1])]:
+        assert idx1.query_chunks(q.encode(), [0], [len(q)], k=k, output=fg.OUT_ORDERS).tolist() == want
+    for q, want in [("A", 1), ("AG", 0), ("CA", 1), ("GGTA", 1), ("ATGG", 0), ("GA", 0), ("GGG", 0), ("CC", 1)]:
+        assert idx1.query_kmers([pack(q)], k=len(q)).tolist() == [want]
+    idx2 = gpu_fixture(2)
+    for q, want in [("AAGA", 1), ("AAGAA", 0), ("GGTTAAGA", 1), ("GTTAAGA", 1)]:  # QUERY2 :334-354
+        assert idx2.query_kmers([pack(q)], k=len(q)).tolist() == [want]
+
+
+# ---- golden indexes: device vs oracle on seeded random inputs -----------------------------------
+def _random_kmers(rng, ms_codes, k, n):
+    """Half from the superstring (random strand), half random; plus a few edge k-mers."""
+    pos = rng.integers(0, len(ms_codes) - k + 1, size=n // 2)
+    win = ms_codes[pos[:, None] + np.arange(k)[None, :]]
+    flip = rng.integers(0, 2, size=len(win)).astype(bool)
+    win[flip] = 3 - win[flip][:, ::-1]
+    rnd = rng.integers(0, 4, size=(n - len(win), k), dtype=np.uint8)
+    rows = np.concatenate([win, rnd, np.zeros((1, k), np.uint8), np.full((1, k), 3, np.uint8)])
+    return synth.pack_rows(rows.astype(np.uint8))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide"])
+def test_device_matches_oracle(case, variant):
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    k = meta["k"]
+    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}}[variant]
+    if variant != "auto" and case not in ("syn_k31_max", "syn_k9_min", "syn_k5_min", "quirks_k3", "data_k13", "syn_k32"):
+        pytest.skip("variants run on a subset")
+    prefix = os.path.join(d, "ms.fa")
+    gi = fg.Index.load(prefix, use_klcp=meta["klcp"], **kw)
+    oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
+    assert gi.n == oi.n and gi.k == k and gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
+    assert gi.wide == (variant == "wide")
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    N = gi.n
+    # rank / update_range
+    ii = np.concatenate([rng.integers(0, N + 1, size=300), [0, N, oi.dollar(), oi.dollar() + 1, min(N, 64), min(N, 63)]]).astype(np.uint64)
+    cc = rng.integers(0, 4, size=len(ii)).astype(np.uint8)
+    assert gi.rank(ii, cc).tolist() == [oi.rank(i, c) for i, c in zip(ii, cc)]
+    a = rng.integers(0, N + 1, size=300)
+    b = rng.integers(0, N + 1, size=300)
+    lo, hi = np.minimum(a, b).astype(np.uint64), np.maximum(a, b).astype(np.uint64)
+    c3 = rng.integers(0, 4, size=300).astype(np.uint8)
+    g_lo, g_hi = gi.update_range(lo, hi, c3)
+    want = [oi.update_range(x, y, c) for x, y, c in zip(lo, hi, c3)]
+    assert list(zip(g_lo.tolist(), g_hi.tolist())) == want
+    # mask: infer_presence<>, kmer_order_if_present on random and tiny intervals
+    tiny = np.minimum(lo + rng.integers(0, 3, size=300).astype(np.uint64), N)
+    for s, e in ((lo, hi), (lo, tiny)):
+        for mo in (False, True):
+            assert gi.infer_presence(s, e, mo).tolist() == [oi.infer_presence(x, y, mo) for x, y in zip(s, e)]
+        assert gi.kmer_order_if_present(s, e).tolist() == [oi.kmer_order_if_present(x, y) for x, y in zip(s, e)]
+    # k-mers
+    ms = open(prefix, "rb").read().split(b"\n")[1]
+    ms_codes = synth.ascii_to_codes(ms)
+    kmers = _random_kmers(rng, ms_codes, k, 600)
+    strs = ["".join(L[(int(v) >> (2 * (k - 1 - t))) & 3] for t in range(k)) for v in kmers]
+    for use_table in (False, True):
+        s, e = gi.get_range_with_pattern(kmers, k, use_table)
+        for q, st in enumerate(strs):
+            ws, we = oi.get_range_with_pattern(st)
+            if ws == we:
+                assert s[q] == e[q]
+            else:
+                assert (s[q], e[q]) == (ws, we)
+    # kLCP extension on real intervals
+    if meta["klcp"]:
+        s, e = gi.get_range_with_pattern(kmers, k, False)
+        ne = s < e
+        if ne.any():
+            xs, xe = gi.extend_range_with_klcp(s[ne], e[ne])
+            assert list(zip(xs.tolist(), xe.tolist())) == [oi.extend_range_with_klcp(x, y) for x, y in zip(s[ne], e[ne])]
+    # the hot path, all modes, LAZY (neutral predictor) and BOTH (per-strand values)
+    for mode, out, omode, oord in ((fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False),
+                                   (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
+        got = gi.query_kmers(kmers, k, mode, out, fg.STRANDS_LAZY)
+        assert got.astype(np.int64).tolist() == oi.query_packed(kmers, k, omode, oord).tolist()
+        both = gi.query_kmers(kmers, k, mode, out, fg.STRANDS_BOTH)
+        want = [oi.kmer_both_strands(st, omode, oord) for st in strs]
+        if out == fg.OUT_PRESENCE:
+            assert [((int(v) & 3) - 1, ((int(v) >> 2) & 3) - 1) for v in both] == want
+        else:
+            assert [tuple(r) for r in both.tolist()] == want
+    gi.close()
+    oi.close()
+
+
+def _chunks_of(seq_codes_list, k, max_kmers):
+    """Concatenate sequences into one base buffer and cut each into chunks of <= max_kmers k-mers
+    overlapping by k-1 (the shape ms_query produces)."""
+    bases, offs, lens = bytearray(), [], []
+    for codes in seq_codes_list:
+        start = len(bases)
+        bases += synth.codes_to_ascii(codes)
+        n = len(codes)
+        p = 0
+        while n - p >= k:
+            ln = min(n - p, max_kmers + k - 1)
+            offs.append(start + p)
+            lens.append(ln)
+            p += ln - k + 1
+    return bytes(bases), np.array(offs, np.uint64), np.array(lens, np.uint32)
+
+
+@pytest.mark.parametrize("case", ["syn_k31_max", "syn_k31_min", "syn_k9_max", "syn_k9_min", "syn_k5_min", "data_k13", "data_k31", "syn_k32", "quirks_k3_nonmax"])
+def test_chunks_streaming_and_single_match_oracle(case):
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    k = meta["k"]
+    prefix = os.path.join(d, "ms.fa")
+    gi = fg.Index.load(prefix, use_klcp=True)
+    oi = OracleIndex.load(prefix, use_klcp=True)
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    rng = np.random.default_rng(7)
+    seqs = []
+    for r in range(60):  # reads from the superstring with substitutions, random strand, assorted lengths
+        ln = int(rng.integers(k, min(len(ms_codes), 260)))
+        p = int(rng.integers(0, len(ms_codes) - ln + 1))
+        s = ms_codes[p:p + ln].copy()
+        sub = rng.random(ln) < 0.03
+        s[sub] = (s[sub] + rng.integers(1, 4, size=int(sub.sum()))) & 3
+        if r % 2:
+            s = synth.revcomp_codes(s)
+        seqs.append(s.astype(np.uint8))
+    seqs.append(rng.integers(0, 4, size=200).astype(np.uint8))
+    seqs.append(ms_codes[:k].copy())
+    for max_kmers in (64, 25, 1):
+        bases, offs, lens = _chunks_of(seqs, k, max_kmers)
+        kmers = np.concatenate([synth.pack_kmers(synth.ascii_to_codes(bases[o:o + l]), k) for o, l in zip(offs.tolist(), lens.tolist())])
+        strs = ["".join(L[(int(v) >> (2 * (k - 1 - t))) & 3] for t in range(k)) for v in kmers]
+        for mode, out, omode, oord in ((fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False),
+                                       (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
+            want = oi.query_packed(kmers, k, omode, oord).tolist()
+            for streaming in (False, True):
+                got = gi.query_chunks(bases, offs, lens, k, mode, out, fg.STRANDS_LAZY, streaming)
+                assert got.astype(np.int64).tolist() == want, (case, max_kmers, mode, out, streaming)
+            wb = [oi.kmer_both_strands(st, omode, oord) for st in strs]
+            for streaming in (False, True):
+                both = gi.query_chunks(bases, offs, lens, k, mode, out, fg.STRANDS_BOTH, streaming)
+                if out == fg.OUT_PRESENCE:
+                    assert [((int(v) & 3) - 1, ((int(v) >> 2) & 3) - 1) for v in both] == wb, (case, max_kmers, mode, streaming)
+                else:
+                    assert [tuple(r) for r in both.tolist()] == wb, (case, max_kmers, streaming)
+    gi.close()
+    oi.close()
+
+
+def test_error_behaviour():
+    with pytest.raises(fg.FmsiGpuError) as e:
+        fg.Index.load("/nonexistent/prefix")
+    assert e.value.code == -2  # "index not correctly loaded"
+    d = os.path.join(GOLDEN, "syn_k31_noklcp")
+    gi = fg.Index.load(os.path.join(d, "ms.fa"), use_klcp=True)  # no .klcp file on disk
+    assert not gi.has_klcp
+    with pytest.raises(fg.FmsiGpuError) as e:
+        gi.query_chunks(b"A" * 40, [0], [40], streaming=True)
+    assert e.value.code == -4  # kLCP mismatch (reference main.cpp:309-312)
+    with pytest.raises(fg.FmsiGpuError):
+        gi.query_kmers([0], k=33)
+    assert gi.query_kmers(np.zeros(0, np.uint64)).size == 0  # empty batch
+    gi.close()
+
+
+# ---- mid-size index built on the box with the reference binary -------------------------------------
+@pytest.fixture(scope="module")
+def midsize(tmp_path_factory):
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/fmsi not shipped")
+    d = tmp_path_factory.mktemp("mid")
+    g = synth.random_codes(1_000_000, 2024)
+    ms = synth.contig_superstring(g, 31, 200, 2025, "max")
+    fa = str(d / "ms.fa")
+    synth.write_fasta_single(fa, "ms", ms)
+    subprocess.run([REF_EXE, "index", "-k", "31", fa], check=True, capture_output=True)
+    return g, fa
+
+
+def test_midsize_parity_and_properties(midsize):
+    g, fa = midsize
+    k = 31
+    gi = fg.Index.load(fa, use_klcp=True)
+    oi = OracleIndex.load(fa, use_klcp=True)
+    rows = synth.kmer_queries(g, k, 200_000, 5)
+    kmers = synth.pack_rows(rows)
+    for mode, out, omode, oord in ((fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False), (fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False),
+                                   (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
+        got = gi.query_kmers(kmers, k, mode, out)
+        assert np.array_equal(got.astype(np.int64), oi.query_packed(kmers, k, omode, oord))
+    # size-independent properties at a larger batch (2M k-mers): strand symmetry, idempotence,
+    # every genome k-mer present, lookup ids form an injection into [0, mask_ones)
+    big = synth.pack_rows(synth.kmer_queries(g, k, 2_000_000, 6))
+    r1 = gi.query_kmers(big, k, fg.MODE_ALL)
+    r2 = gi.query_kmers(synth.revcomp_packed(big, k), k, fg.MODE_ALL)
+    assert np.array_equal(r1, r2) and np.array_equal(r1, gi.query_kmers(big, k, fg.MODE_ALL))
+    assert np.array_equal(r1, gi.query_kmers(big, k, fg.MODE_OR))  # max-ones mask: -O == or
+    gk = synth.pack_kmers(g[:300_000], k)
+    assert gi.query_kmers(gk, k, fg.MODE_ALL).all()
+    ids = gi.query_kmers(gk, k, output=fg.OUT_ORDERS)
+    assert (ids >= 0).all() and ids.max() < gi.mask_ones
+    canon = synth.canonical_packed(gk, k)
+    _, first = np.unique(canon, return_index=True)
+    assert len(np.unique(ids[first])) == len(first)  # distinct canonical k-mers -> distinct ids
+    # streaming reads == single queries
+    reads = synth.read_queries(g, 150, 3000, 8)
+    bases, offs, lens = _chunks_of(list(reads), k, 64)
+    a = gi.query_chunks(bases, offs, lens, k, fg.MODE_ALL, streaming=True)
+    b = gi.query_chunks(bases, offs, lens, k, fg.MODE_ALL, streaming=False)
+    assert np.array_equal(a, b)
+    la = gi.query_chunks(bases, offs, lens, k, output=fg.OUT_ORDERS, streaming=True)
+    lb = gi.query_chunks(bases, offs, lens, k, output=fg.OUT_ORDERS, streaming=False)
+    assert np.array_equal(la, lb)
+    allk = np.concatenate([synth.pack_kmers(synth.ascii_to_codes(bases[o:o + l]), k) for o, l in zip(offs.tolist()[:400], lens.tolist()[:400])])
+    assert np.array_equal(a[:len(allk)].astype(np.int64), oi.query_packed(allk, k, MODE_ALL, False))
+    gi.close()
+    oi.close()
