@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py — 31-mer queries/s of the FMS-index query path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (`fmsi query -O` semantics: fmsi_gpu_query_kmers, mode ALL,
+strands LAZY) over one batch of synthetic packed 31-mers, 50 % present. `value` is measured with
+the batch resident in HBM (CUDA events on the launching stream); `e2e` is the same metric through
+the C-ABI with pinned HOST buffers, host<->device copies inside the timed region. With N > 1
+(torchrun) every rank owns one GPU, a full replica of the index and its own batch (weak scaling, no
+data-path collective); the time is the max over ranks.
+
+`--impl reference` times the unmodified reference CPU binary (oracle/_ref/fmsi, one process per
+host core over FASTA shards of a bounded sample) on the same index and query distribution.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from fmsi_b200 import synth  # noqa: E402
+
+DATA = os.path.join(ROOT, "data")
+REF_FMSI = os.path.join(ROOT, "oracle", "_ref", "fmsi")
+REF_KMERCAMEL = os.path.join(ROOT, "oracle", "_ref", "kmercamel")
+METRIC = "31-mer queries/sec"
+UNIT = "kmers/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: E. coli-sized synthetic, k=31, masked superstring via bundled
+    # kmercamel + `fmsi index`; single 31-mer `fmsi query -O`, 50 % present.
+    "ecoli": dict(genome_len=5_000_000, k=31, seed=1, superstring="kmercamel", batch=1 << 26,
+                  desc="5 Mbp random genome, kmercamel -c + optimize -a ones, fmsi index -k 31; single 31-mers, 50% present"),
+    # small variant for quick checks
+    "tiny": dict(genome_len=200_000, k=31, seed=3, superstring="contigs", batch=1 << 22,
+                 desc="200 kbp random genome (debug)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, capture_output=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError(f"{cmd} failed: {r.stderr.decode(errors='replace')[-2000:]}")
+    return r
+
+
+# ------------------------------------------------------------------------------------------------
+def prepare_index(name: str) -> dict:
+    """Genome -> masked superstring -> reference `fmsi index`; cached under data/<name>/."""
+    w = WORKLOADS[name]
+    d = os.path.join(DATA, name)
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, "ms.fa")
+    k = w["k"]
+    genome = synth.random_codes(w["genome_len"], w["seed"])
+    if not os.path.exists(prefix + ".fmsi.misc"):
+        if not os.path.exists(REF_FMSI):
+            raise RuntimeError("oracle/_ref/fmsi is needed to build the benchmark index (index construction is the "
+                               "reference's, unchanged); run __graft_entry__.build() where /root/reference exists")
+        t0 = time.time()
+        how = w["superstring"]
+        if how == "kmercamel" and os.path.exists(REF_KMERCAMEL):
+            gfa = os.path.join(d, "genome.fa")
+            synth.write_fasta_single(gfa, "genome", synth.codes_to_ascii(genome))
+            run([REF_KMERCAMEL, "-c", "-k", str(k), "-p", gfa, "-o", os.path.join(d, "ms.raw.fa")])
+            run([REF_KMERCAMEL, "optimize", "-c", "-a", "ones", "-k", str(k), "-p", os.path.join(d, "ms.raw.fa"), "-o", prefix])
+            os.remove(gfa)
+            os.remove(os.path.join(d, "ms.raw.fa"))
+            how = "kmercamel"
+        else:
+            synth.write_fasta_single(prefix, "ms", synth.contig_superstring(genome, k, 64, w["seed"] + 100, "max"))
+            how = "contigs"
+        run([REF_FMSI, "index", "-k", str(k), prefix])
+        with open(os.path.join(d, "how.txt"), "w") as f:
+            f.write(how)
+        log(f"[bench] built index {name} ({how}) in {time.time() - t0:.1f}s")
+    how = open(os.path.join(d, "how.txt")).read().strip() if os.path.exists(os.path.join(d, "how.txt")) else "?"
+    return dict(prefix=prefix, k=k, genome=genome, how=how, **{kk: w[kk] for kk in ("batch", "desc", "genome_len")})
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-lms", "100", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_cpu_rate(wl: dict, per_proc: int, seed: int, procs: int | None = None) -> dict:
+    """The reference's own CPU query path: P independent `fmsi query -O` processes over FASTA shards
+    (the reference has no threads). Wall time from first start to last exit; index load included
+    (a few ms at this size) and reported."""
+    if not os.path.exists(REF_FMSI):
+        raise RuntimeError("oracle/_ref/fmsi missing")
+    P = procs or os.cpu_count() or 1
+    k = wl["k"]
+    gk = synth.pack_kmers(wl["genome"], k)
+    tmp = tempfile.mkdtemp(prefix="fmsi_ref_")
+    try:
+        files = []
+        for p in range(P):
+            q = synth.packed_kmer_queries(gk, k, per_proc, seed + p)
+            fn = os.path.join(tmp, f"q{p}.fa")
+            with open(fn, "wb") as f:
+                f.write(synth.packed_to_fasta(q, k))
+            files.append(fn)
+        one = os.path.join(tmp, "one.fa")
+        with open(one, "wb") as f:
+            f.write(b">q\n" + b"A" * k + b"\n")
+        t0 = time.perf_counter()
+        run([REF_FMSI, "query", "-O", "-q", one, wl["prefix"]])
+        load_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([REF_FMSI, "query", "-O", "-q", fn, wl["prefix"]], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fn in files]
+        for p_ in ps:
+            if p_.wait() != 0:
+                raise RuntimeError("reference fmsi query failed")
+        wall = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    total = P * per_proc
+    return dict(value=total / wall, unit=UNIT, cores=P, kind="reference", wall_s=round(wall, 3), index_load_s=round(load_s, 3),
+                sample=f"{P} concurrent `fmsi query -O` processes x {per_proc} single 31-mer FASTA records (50% present), "
+                       f"same index; wall {wall:.2f}s incl. per-process index load {load_s:.3f}s")
+
+
+def algorithmic_bytes_per_kmer(wl: dict, sample: int, seed: int) -> dict:
+    """32 B x (rank sectors + mask sectors) per k-mer, counted by the instrumented
+    oracle on a sample of the same query distribution (forward strand first, neutral predictor),
+    + 8 B packed query in + 1 B result out. Part of the cpu_baseline leg: the oracle is only a counter here."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_ffi import MODE_ALL, OracleIndex
+    oi = OracleIndex.load(wl["prefix"], use_klcp=False)
+    gk = synth.pack_kmers(wl["genome"], wl["k"])
+    q = synth.packed_kmer_queries(gk, wl["k"], sample, seed)
+    oi.counters_reset()
+    oi.query_packed(q, wl["k"], MODE_ALL, False)
+    c = oi.counters()
+    oi.close()
+    n = c["kmers"]
+    per = dict(lf_steps=c["lf_steps"] / n, rank_sectors=c["rank_sectors"] / n, mask_sectors=c["mask_sectors"] / n)
+    per["bytes"] = 32.0 * (per["rank_sectors"] + per["mask_sectors"]) + 8 + 1
+    return per
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FMSI_BENCH_WORKLOAD", "ecoli"))
+    ap.add_argument("--batch", type=int, default=0, help="k-mers per step per GPU (default: workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="k-mers per reference CPU process")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: W < 3 violates the timing rules; using W = 3")
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = prepare_index(args.workload)
+        vals = []
+        for s in range(args.warmup + args.steps):
+            r = reference_cpu_rate(wl, args.cpu_sample, seed=5000 + 100 * s)
+            if s >= args.warmup:
+                vals.append(r)
+        wall = sum(v["wall_s"] for v in vals)
+        total = sum(v["cores"] * args.cpu_sample for v in vals)
+        value = total / wall
+        cb = dict(vals[-1])
+        cb["value"] = value
+        line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=1000.0 * wall / len(vals), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
+                    data="synthetic", config=dict(workload=args.workload, desc=wl["desc"], k=wl["k"], superstring=wl["how"],
+                                                  kmers_per_step=cb["cores"] * args.cpu_sample, mode="query -O"),
+                    cpu_baseline=cb, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import fmsi_b200 as fg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    # rank 0 prepares the cached index first so that ranks do not race on the files
+    if world > 1:
+        if rank == 0:
+            wl = prepare_index(args.workload)
+        dist.barrier()
+        if rank != 0:
+            wl = prepare_index(args.workload)
+    else:
+        wl = prepare_index(args.workload)
+    k = wl["k"]
+    batch = args.batch or wl["batch"]
+
+    t0 = time.time()
+    gi = fg.Index.load(wl["prefix"], use_klcp=False, device=local_rank)
+    load_s = time.time() - t0
+    gk = synth.pack_kmers(wl["genome"], k)
+    nbuf = 2  # alternate between distinct batches; each is larger than L2
+    host_batches = [synth.packed_kmer_queries(gk, k, batch, seed=1000 + 17 * rank + b) for b in range(nbuf)]
+    pinned_in = [torch.from_numpy(h.view(np.int64)).pin_memory() for h in host_batches]
+    pinned_out = torch.empty(batch, dtype=torch.uint8).pin_memory()
+    d_in = [p.to(dev, non_blocking=False) for p in pinned_in]
+    d_out = torch.empty(batch, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device(s):
+        gi.query_kmers_ptr(d_in[s % nbuf].data_ptr(), batch, d_out.data_ptr(), k, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY,
+                           fg.MEM_DEVICE, stream.cuda_stream)
+
+    def step_host(s):
+        gi.query_kmers_ptr(pinned_in[s % nbuf].data_ptr(), batch, pinned_out.data_ptr(), k, fg.MODE_ALL, fg.OUT_PRESENCE,
+                           fg.STRANDS_LAZY, fg.MEM_HOST, 0)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-resident timing -----------------------------------------------------------------
+    for s in range(args.warmup):
+        step_device(s)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = fg.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        step_device(s)
+    e1.record(stream)
+    sync_all()
+    launches = fg.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_per_step = ms_total / args.steps
+    value = world * batch / (ms_per_step / 1e3)
+
+    # sanity: the timed kernel did the work (present fraction ~ 50 %) and both paths agree
+    frac_present = float(d_out.float().mean().item())
+
+    # ---- end-to-end through the C-ABI with host buffers --------------------------------------
+    for s in range(2):
+        step_host(s)
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(s)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * batch * args.steps / e2e_s
+    step_device(args.steps - 1)
+    torch.cuda.synchronize(dev)
+    same = bool(torch.equal(d_out.cpu(), pinned_out))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline + CPU baseline (rank 0) -----------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    alg = algorithmic_bytes_per_kmer(wl, 200_000, seed=77)
+    launch_ms = ms_per_step  # one query_kmers_kernel launch per step (+ an 8-byte memset)
+    achieved = alg["bytes"] * batch / (launch_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(args.workload)
+        if tj and tj.get("batch"):
+            traffic = tj["dram_bytes_per_launch"] * (batch / tj["batch"])
+    roofline = dict(bound="hbm", achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=traffic,
+                    kernel="query_kmers_kernel<ALL,PRESENCE,LAZY>", launch_ms=round(launch_ms, 4), peak_source=peak_src,
+                    algorithmic=dict(bytes_per_kmer=round(alg["bytes"], 1), lf_steps_per_kmer=round(alg["lf_steps"], 2),
+                                     rank_sectors_per_kmer=round(alg["rank_sectors"], 2), mask_sectors_per_kmer=round(alg["mask_sectors"], 2)),
+                    note="algorithmic bytes = reference algorithm's dependent sector probes (SURVEY 8d); index is L2-resident for "
+                         "ecoli-sized workloads, so HBM is not the binding limit there")
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = reference_cpu_rate(wl, args.cpu_sample, seed=9000)
+        except Exception as ex:  # keep the bench line even if the reference binary did not travel
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="reference", sample=f"unavailable: {ex}")
+
+    info = gi.info
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64", data="synthetic",
+                config=dict(workload=args.workload, desc=wl["desc"], k=k, superstring=wl["how"], kmers_per_step_per_gpu=batch,
+                            mode="query -O (MODE_ALL, STRANDS_LAZY)", parallelism=f"replicas x{world}, queries sharded, no collective",
+                            l2="inputs larger than L2: 2 alternating batches of %d MiB" % (batch * 8 >> 20), n_bwt=int(info.n_bwt),
+                            prefix_t=int(info.prefix_t), index_hbm_bytes=int(info.hbm_bytes), index_load_s=round(load_s, 3),
+                            frac_present=round(frac_present, 4), e2e_equals_device=same),
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=batch * 8, d2h_bytes_per_step=batch * 1),
+                gpu_launches=int(launches), clocks=clocks)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

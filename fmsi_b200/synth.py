@@ -174,3 +174,31 @@ def read_queries(codes: np.ndarray, read_len: int, n_reads: int, seed: int, sub_
 def ensure_dir(path: str) -> str:
     os.makedirs(path, exist_ok=True)
     return path
+
+
+def packed_kmer_queries(genome_kmers: np.ndarray, k: int, n_queries: int, seed: int, frac_present: float = 0.5) -> np.ndarray:
+    """Packed form of kmer_queries() for large batches: genome_kmers = pack_kmers(genome, k).
+    Present k-mers are drawn from uniform genome positions with a random strand, absent ones are
+    i.i.d. uniform k-mers; the two kinds are interleaved at random."""
+    rng = np.random.default_rng(seed)
+    present = rng.random(n_queries) < frac_present
+    pos = rng.integers(0, len(genome_kmers), size=n_queries)
+    km = genome_kmers[pos]
+    flip = rng.integers(0, 2, size=n_queries).astype(bool)
+    km = np.where(flip, revcomp_packed(km, k), km)
+    hi = np.uint64((1 << (2 * k)) - 1)
+    rnd = rng.integers(0, np.iinfo(np.uint64).max, size=n_queries, dtype=np.uint64, endpoint=True) & hi
+    return np.where(present, km, rnd).astype(np.uint64)
+
+
+def packed_to_fasta(kmers: np.ndarray, k: int) -> bytes:
+    """Fixed-width FASTA: one record `>q\\nSEQ\\n` per packed k-mer (vectorised)."""
+    n = len(kmers)
+    rec = np.empty((n, k + 4), dtype=np.uint8)
+    rec[:, 0] = ord(">")
+    rec[:, 1] = ord("q")
+    rec[:, 2] = ord("\n")
+    for t in range(k):
+        rec[:, 3 + t] = ACGT[((kmers >> np.uint64(2 * (k - 1 - t))) & np.uint64(3)).astype(np.uint8)]
+    rec[:, k + 3] = ord("\n")
+    return rec.tobytes()
