@@ -1,0 +1,526 @@
+// fmsi_cli.cpp — `fmsi query` / `fmsi lookup` front end over libfmsi_gpu.so.
+//
+// Drop-in for the query path of the reference CLI (reference src/main.cpp: ms_query :238-375,
+// usage texts :102-130, dispatch :668-699): same flags, same index files, byte-identical stdout.
+// Everything else the reference CLI does (index, export, merge, set operations, -f functions other
+// than or/all) is out of scope for the GPU engine and is forwarded to the unchanged reference
+// binary when $FMSI_REFERENCE_BIN points at one.
+//
+// Flow per batch of records:  kseq-compatible reader -> valid ACGT runs -> GPU chunks
+//   -> fmsi_gpu_query_chunks (both strands) -> strand-predictor replay (predictor.hpp, exact
+//   reference semantics whatever the index/mask) -> text formatter.
+// $FMSI_GPU_STRANDS=lazy skips the replay (forward strand first, reverse complement only if
+// undecided): identical output whenever the strand predictor cannot change results (or-mode
+// always; -O on max-ones masks; lookup when no k-mer is ON on both strands), and much cheaper for -S.
+#include <fmsi_gpu.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "predictor.hpp"
+
+namespace {
+
+const char *kVersion = "0.4.0-b200";
+
+int usage() {
+    std::cerr << std::endl;
+    std::cerr << "Program: FMSI - a tool for space-efficient k-mer set indexing via masked superstrings." << std::endl;
+    std::cerr << "         (B200 GPU query engine; drop-in for `query` and `lookup`)" << std::endl;
+    std::cerr << "Version: " << kVersion << std::endl << std::endl;
+    std::cerr << "Usage:   fmsi <command> [options]" << std::endl << std::endl;
+    std::cerr << "Command (GPU):" << std::endl;
+    std::cerr << "    query   - Queries k-mers against an index." << std::endl;
+    std::cerr << "    lookup  - Return unique hashes of present k-mers." << std::endl << std::endl;
+    std::cerr << "Command (forwarded to the reference binary named by $FMSI_REFERENCE_BIN):" << std::endl;
+    std::cerr << "    index export union inter diff symdiff merge compact clean" << std::endl << std::endl;
+    return 1;
+}
+
+void usage_functions() {
+    std::cerr << "  -f FUNCTION - Demasking function to determine k-mer presence; recognized functions:" << std::endl;
+    std::cerr << "    or      - represented when at least 1 ON occurrence [default]" << std::endl;
+    std::cerr << "    all     - all occurrence are either ON or OFF (equivalent to -O flag for queries)" << std::endl;
+    std::cerr << "    and     - represented when no OFF occurrence" << std::endl;
+    std::cerr << "    xor     - represented when an odd number of ON occurrences" << std::endl;
+    std::cerr << "    INT-INT - represented when in the bounds" << std::endl;
+}
+
+int usage_query() {
+    std::cerr << std::endl;
+    std::cerr << "Usage:   fmsi query [options] <index-prefix>" << std::endl << std::endl;
+    std::cerr << "Options (stable):" << std::endl;
+    std::cerr << "  -q FILE - Path to FASTA/FASTQ with queries [default: stdin]" << std::endl;
+    std::cerr << "  -k INT  - Size of k-mers [default: infer automatically from index]" << std::endl;
+    std::cerr << "  -S      - Use kLCP array for streamed queries (increses memory consumption)" << std::endl;
+    std::cerr << "  -O      - FMSI uses properties of max-one masked superstrings to speed up queries" << std::endl;
+    std::cerr << "            Use only if a masked superstring with maximum number of ones is indexed." << std::endl;
+    std::cerr << "Parameters (experimental, using f-MS framework):" << std::endl;
+    usage_functions();
+    std::cerr << std::endl;
+    return 1;
+}
+
+int usage_lookup() {
+    std::cerr << std::endl;
+    std::cerr << "Usage:   fmsi lookup [options] <index-prefix>" << std::endl << std::endl;
+    std::cerr << "Options (stable):" << std::endl;
+    std::cerr << "  -q FILE - Path to FASTA/FASTQ with queries [default: stdin]" << std::endl;
+    std::cerr << "  -k INT  - Size of k-mers [default: infer automatically from index]" << std::endl;
+    std::cerr << "  -S      - Use kLCP array for streamed queries (increses memory consumption)" << std::endl;
+    std::cerr << std::endl;
+    return 1;
+}
+
+int usage_query(bool lookup) { return lookup ? usage_lookup() : usage_query(); }
+
+// -f names the reference accepts (src/functions.h:23-57); only or/all run on the GPU.
+bool known_function(const std::string &name) {
+    if (name == "or" || name == "and" || name == "xor" || name == "all") return true;
+    for (size_t i = 1; i + 1 < name.size(); ++i) {
+        if (name[i] == '-') {
+            bool valid = true;
+            for (size_t j = 0; j < name.size(); ++j)
+                if (j != i && (name[j] < '0' || name[j] > '9')) valid = false;
+            if (valid) return true;
+            break;
+        }
+    }
+    return false;
+}
+
+int forward_to_reference(int argc, char *argv[]) {
+    const char *ref = std::getenv("FMSI_REFERENCE_BIN");
+    if (!ref || !*ref) {
+        std::cerr << "ERROR: `" << (argc > 1 ? argv[1] : "") << "` is not part of the GPU query engine. "
+                  << "Set FMSI_REFERENCE_BIN to the reference fmsi binary to forward it." << std::endl;
+        return 1;
+    }
+    std::vector<char *> av(argv, argv + argc);
+    av[0] = const_cast<char *>(ref);
+    av.push_back(nullptr);
+    execv(ref, av.data());
+    std::cerr << "ERROR: cannot execute " << ref << std::endl;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Record reader with the semantics of the reference's kseq (src/kseq.h:173-226) over zlib
+// (plain or gzip, file or stdin — parser.h:14-27).
+class RecordReader {
+  public:
+    explicit RecordReader(const std::string &path) {
+        FILE *in = path == "-" ? stdin : std::fopen(path.c_str(), "r");
+        if (!in) throw std::invalid_argument("couldn't open file " + path);  // uncaught in the reference too
+        fp_ = gzdopen(fileno(in), "r");
+        gzbuffer(fp_, 1 << 20);
+        buf_.resize(1 << 22);
+    }
+    ~RecordReader() {
+        if (fp_) gzclose(fp_);
+    }
+    // Returns sequence length (>= 0), or a negative code: -1 EOF, -2 truncated quality.
+    int64_t next(std::string &name, std::string &seq) {
+        int c;
+        if (last_char_ == 0) {
+            while ((c = getc()) >= 0 && c != '>' && c != '@') {}
+            if (c < 0) return c;
+            last_char_ = c;
+        }
+        seq.clear();
+        qual_len_ = 0;
+        int64_t r = getuntil(kSpace, name, &c, false);
+        if (r < 0) return r;
+        if (c != '\n') getuntil(kLine, scratch_, nullptr, false);  // comment
+        while ((c = getc()) >= 0 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n') continue;
+            seq.push_back((char)c);
+            getuntil(kLine, seq, nullptr, true);
+        }
+        if (c == '>' || c == '@') last_char_ = c;
+        if (c != '+') return (int64_t)seq.size();
+        while ((c = getc()) >= 0 && c != '\n') {}
+        if (c == -1) return -2;
+        scratch_.clear();
+        while (getuntil(kLine, scratch_, nullptr, true) >= 0 && scratch_.size() < seq.size()) {}
+        last_char_ = 0;
+        if (seq.size() != scratch_.size()) return -2;
+        return (int64_t)seq.size();
+    }
+
+  private:
+    enum { kSpace = 0, kLine = 2 };
+    bool fill() {
+        if (eof_) return false;
+        int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+        begin_ = 0;
+        end_ = n > 0 ? (size_t)n : 0;
+        if (n <= 0) eof_ = true;
+        return n > 0;
+    }
+    int getc() {
+        if (begin_ >= end_ && !fill()) return -1;
+        return (unsigned char)buf_[begin_++];
+    }
+    int64_t getuntil(int delimiter, std::string &str, int *dret, bool append) {
+        bool gotany = false;
+        if (dret) *dret = 0;
+        if (!append) str.clear();
+        for (;;) {
+            if (begin_ >= end_ && !fill()) break;
+            size_t i;
+            if (delimiter == kLine) {
+                const char *sep = (const char *)memchr(buf_.data() + begin_, '\n', end_ - begin_);
+                i = sep ? (size_t)(sep - buf_.data()) : end_;
+            } else {
+                for (i = begin_; i < end_; ++i)
+                    if (isspace((unsigned char)buf_[i])) break;
+            }
+            gotany = true;
+            str.append(buf_.data() + begin_, i - begin_);
+            begin_ = i + 1;
+            if (i < end_) {
+                if (dret) *dret = (unsigned char)buf_[i];
+                break;
+            }
+        }
+        if (!gotany && eof_) return -1;
+        if (delimiter == kLine && str.size() > 1 && str.back() == '\r') str.pop_back();
+        return (int64_t)str.size();
+    }
+    gzFile fp_ = nullptr;
+    std::vector<char> buf_;
+    size_t begin_ = 0, end_ = 0;
+    bool eof_ = false;
+    int last_char_ = 0;
+    size_t qual_len_ = 0;
+    std::string scratch_;
+};
+
+inline bool is_acgt(unsigned char ch) {  // nucleotideToInt[ch] != 4, src/kmers.h:3-20
+    switch (ch) {
+    case 'A': case 'C': case 'G': case 'T': case 'a': case 'c': case 'g': case 't': return true;
+    default: return false;
+    }
+}
+
+struct Op {  // one stretch of a record's output
+    uint64_t count;
+    bool kmers;  // true: `count` consecutive k-mer results; false: `count` invalid-position fillers
+};
+struct Record {
+    std::string name;
+    size_t op_begin, op_end;
+};
+
+struct Batch {
+    std::vector<Record> records;
+    std::vector<Op> ops;
+    std::string bases;                  // valid runs (>= k) back to back
+    std::vector<uint64_t> chunk_off;    // GPU chunks
+    std::vector<uint32_t> chunk_len;
+    std::vector<uint64_t> res_off;
+    std::vector<uint32_t> ref_chunks;   // k-mers per REFERENCE chunk, in order (predictor granularity)
+    uint64_t n_results = 0;
+    void clear() {
+        records.clear();
+        ops.clear();
+        bases.clear();
+        chunk_off.clear();
+        chunk_len.clear();
+        res_off.clear();
+        ref_chunks.clear();
+        n_results = 0;
+    }
+};
+
+// ms_query's record loop (main.cpp:328-373) turned into a layout: which k-mers exist, where the
+// reference cuts its chunks, and how many filler results each invalid character produces.
+void layout_record(Batch &b, const std::string &name, const std::string &s, int k, bool streaming) {
+    Record rec;
+    rec.name = name;
+    rec.op_begin = b.ops.size();
+    int64_t sequence_length = (int64_t)s.size();
+    int64_t max_chunk = 400;
+    max_chunk = k + std::max((int64_t)10, std::min(max_chunk, 2 * (int64_t)std::sqrt((double)sequence_length)));
+    const char *sequence = s.data();
+    const uint32_t gpu_max = streaming ? (uint32_t)(FMSI_GPU_MAX_STREAM_KMERS + k - 1) : 0xFFFFFF00u;
+    while (sequence_length > 0) {
+        int64_t current_length = 0;
+        while (current_length < sequence_length && is_acgt((unsigned char)sequence[current_length])) ++current_length;
+        if (current_length >= k) {
+            const uint64_t run_kmers = (uint64_t)(current_length - k + 1);
+            const uint64_t base0 = b.bases.size();
+            b.bases.append(sequence, (size_t)current_length);
+            for (uint64_t p = 0; p < run_kmers;) {  // GPU chunks, overlapping by k-1
+                const uint64_t left = (uint64_t)current_length - p;
+                const uint32_t len = (uint32_t)std::min<uint64_t>(left, gpu_max);
+                b.chunk_off.push_back(base0 + p);
+                b.chunk_len.push_back(len);
+                b.res_off.push_back(b.n_results + p);
+                p += len - k + 1;
+            }
+            int64_t cur = current_length;  // reference chunks (main.cpp:340-354)
+            while (cur >= k) {
+                const int64_t chunk_length = std::min(cur, max_chunk);
+                b.ref_chunks.push_back((uint32_t)(chunk_length - k + 1));
+                cur -= chunk_length - k + 1;
+            }
+            b.ops.push_back({run_kmers, true});
+            b.n_results += run_kmers;
+            sequence += run_kmers;
+            sequence_length -= (int64_t)run_kmers;
+            current_length -= (int64_t)run_kmers;
+        }
+        // current_length < k characters of the run remain, then the invalid character (main.cpp:355-370)
+        sequence_length -= current_length + 1;
+        sequence += current_length + 1;
+        if (sequence_length >= 0) b.ops.push_back({(uint64_t)std::min<int64_t>(k, current_length + 1), false});
+    }
+    rec.op_end = b.ops.size();
+    b.records.push_back(std::move(rec));
+}
+
+struct Engine {
+    fmsi_gpu_index *idx = nullptr;
+    int k = 0;
+    bool streaming = false, orders = false, lazy = false;
+    fmsi::QueryMode mode = fmsi::QueryMode::Or;
+    fmsi::StrandPredictor predictor;
+    std::vector<uint8_t> raw8;
+    std::vector<int64_t> raw64, fin64;
+    std::vector<uint8_t> fin8;
+    std::string out;
+
+    void check(int rc) {
+        if (rc != FMSI_GPU_OK) {
+            std::cerr << "ERROR: GPU query failed: " << fmsi_gpu_last_error() << std::endl;
+            std::exit(1);
+        }
+    }
+
+    void run(Batch &b) {
+        const uint64_t n = b.n_results;
+        const int gmode = mode == fmsi::QueryMode::All ? FMSI_GPU_MODE_ALL : FMSI_GPU_MODE_OR;
+        const int gout = orders ? FMSI_GPU_OUT_ORDERS : FMSI_GPU_OUT_PRESENCE;
+        const int gstr = lazy ? FMSI_GPU_STRANDS_LAZY : FMSI_GPU_STRANDS_BOTH;
+        void *raw = nullptr;
+        if (orders) {
+            raw64.resize(n * (lazy ? 1 : 2));
+            raw = raw64.data();
+        } else {
+            raw8.resize(n);
+            raw = raw8.data();
+        }
+        if (n)
+            check(fmsi_gpu_query_chunks(idx, gmode, gout, gstr, streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
+                                        b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, k, raw, FMSI_GPU_MEM_HOST, nullptr));
+        // ---- final values in query order
+        const uint8_t *p8 = nullptr;
+        const int64_t *p64 = nullptr;
+        if (lazy) {
+            p8 = raw8.data();
+            p64 = raw64.data();
+        } else {
+            if (orders) fin64.resize(n);
+            else fin8.resize(n);
+            auto f_of = [&](uint64_t q) -> int64_t { return orders ? raw64[2 * q] : (int64_t)(raw8[q] & 3) - 1; };
+            auto r_of = [&](uint64_t q) -> int64_t { return orders ? raw64[2 * q + 1] : (int64_t)((raw8[q] >> 2) & 3) - 1; };
+            uint64_t q0 = 0;
+            for (uint32_t m : b.ref_chunks) {
+                if (streaming) {
+                    fmsi::replay_streaming_chunk(
+                        predictor, mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
+                        [&](size_t q, int64_t v) {
+                            if (orders) fin64[q0 + q] = v;
+                            else fin8[q0 + q] = v == 1;
+                        });
+                } else {
+                    for (uint32_t q = 0; q < m; ++q) {
+                        const int64_t v = fmsi::replay_single(predictor, mode, orders, f_of(q0 + q), r_of(q0 + q));
+                        if (orders) fin64[q0 + q] = v;
+                        else fin8[q0 + q] = v == 1;
+                    }
+                }
+                q0 += m;
+            }
+            p8 = fin8.data();
+            p64 = fin64.data();
+        }
+        // ---- text (main.cpp:333, :341-342, :358-372 and fms_index.h:242-253 / :301-309)
+        out.clear();
+        uint64_t q = 0;
+        char num[24];
+        for (const Record &rec : b.records) {
+            out.append(rec.name.c_str());  // C-string semantics of `cout << seq->name.s`
+            out.push_back('\t');
+            bool comma = false;
+            for (size_t o = rec.op_begin; o < rec.op_end; ++o) {
+                const Op &op = b.ops[o];
+                if (!orders) {
+                    if (op.kmers) {
+                        const size_t at = out.size();
+                        out.resize(at + op.count);
+                        for (uint64_t t = 0; t < op.count; ++t) out[at + t] = (char)('0' + p8[q + t]);
+                        q += op.count;
+                    } else {
+                        out.append(op.count, '0');
+                    }
+                } else {
+                    for (uint64_t t = 0; t < op.count; ++t) {
+                        if (comma) out.push_back(',');
+                        comma = true;
+                        if (op.kmers) {
+                            const int len = std::snprintf(num, sizeof num, "%lld", (long long)p64[q + t]);
+                            out.append(num, (size_t)len);
+                        } else {
+                            out.append("-1");
+                        }
+                    }
+                    if (op.kmers) q += op.count;
+                }
+            }
+            out.push_back('\n');
+        }
+        if (!out.empty()) std::fwrite(out.data(), 1, out.size(), stdout);
+    }
+};
+
+int ms_query(int argc, char *argv[], bool output_orders) {
+    bool usage = false;
+    int c;
+    int k = 0;
+    std::string fn;
+    if (argc > 1 && std::string(argv[argc - 1]) != "-h") {  // prefix must be last (main.cpp:244-247)
+        fn = argv[argc - 1];
+        argc--;
+    }
+    std::string query_fn = "-";
+    std::string f_name = "or";
+    bool has_klcp = false;
+    while ((c = getopt(argc, argv, "f:hq:k:OS")) >= 0) {
+        switch (c) {
+        case 'f':
+            if (!known_function(optarg)) {
+                std::cerr << "ERROR: Function '" << optarg << "' not recognized." << std::endl;
+                return usage_query();
+            }
+            f_name = optarg;
+            break;
+        case 'h': usage = true; break;
+        case 'q': query_fn = optarg; break;
+        case 'k': k = atoi(optarg); break;
+        case 'O':
+            if (f_name != "or") std::cerr << "WARNING: Parameter -O is ignored when parameter -f is specified." << std::endl;
+            else f_name = "all";
+            break;
+        case 'S': has_klcp = true; break;
+        default: return usage_query(output_orders);
+        }
+    }
+    if (usage) {
+        usage_query(output_orders);
+        return 0;
+    } else if (fn.empty()) {
+        std::cerr << "ERROR: Path to the fasta file is a required argument." << std::endl;
+        return usage_query(output_orders);
+    }
+    if (output_orders && f_name == "all") {
+        std::cerr << "WARNING: The current version of FMSI has speed benefits only if output as (minimum) perfect hash function is not used. Additionally, if you desire minimum perfect hash function, please minimize the number of ones in the mask." << std::endl;
+    } else if (f_name != "or" && output_orders) {
+        std::cerr << "ERROR: FMSI as Minimum Perfect Hash Function is not allowed with f-masked superstrings in the current version." << std::endl;
+        return usage_query(output_orders);
+    }
+    if (f_name != "or" && f_name != "all") return -2;  // general f-MS mode: caller forwards to the reference
+
+    int device = 0;
+    if (const char *e = std::getenv("FMSI_GPU_DEVICE")) device = atoi(e);
+    fmsi_gpu_index *idx = nullptr;
+    int rc = fmsi_gpu_index_load(fn.c_str(), has_klcp ? 1 : 0, device, nullptr, &idx);
+    if (rc == FMSI_GPU_ERR_IO) {
+        std::cerr << "ERROR: index not correctly loaded. Ensure that you correctly call `fmsi index` before." << std::endl;
+        return usage_query(output_orders);
+    } else if (rc != FMSI_GPU_OK) {
+        std::cerr << "ERROR: " << fmsi_gpu_last_error() << std::endl;
+        return 1;
+    }
+    fmsi_gpu_index_info info;
+    fmsi_gpu_index_get_info(idx, &info);
+    if (has_klcp != (info.has_klcp != 0)) {
+        std::cerr << "ERROR: kLCP array was not constructed for the given index. Either construct it again without the `-s` flag or use `query -s` which slows down streaming queries." << std::endl;
+        return usage_query(output_orders);
+    }
+    const int index_k = info.k;
+    if (k != 0 && k != index_k) {
+        std::cerr << "ERROR: Mismatch. Provided k (" << k << ") does not match the k of the index (" << index_k << ")." << std::endl;
+        return usage_query(output_orders);
+    }
+    if (k == 0) k = index_k;
+    if (k < 1 || k > 32) {
+        std::cerr << "ERROR: the GPU query engine supports k <= 32 (index has k = " << k << ")." << std::endl;
+        return 1;
+    }
+
+    Engine eng;
+    eng.idx = idx;
+    eng.k = k;
+    eng.streaming = has_klcp;
+    eng.orders = output_orders;
+    eng.mode = f_name == "all" ? fmsi::QueryMode::All : fmsi::QueryMode::Or;
+    if (const char *e = std::getenv("FMSI_GPU_STRANDS")) eng.lazy = std::string(e) == "lazy";
+
+    RecordReader reader(query_fn);
+    Batch batch;
+    std::string name, seq;
+    size_t batch_bases = 64u << 20;
+    if (const char *e = std::getenv("FMSI_GPU_BATCH_BASES")) batch_bases = (size_t)atoll(e);
+    size_t pending = 0;
+    while (reader.next(name, seq) >= 0) {
+        layout_record(batch, name, seq, k, eng.streaming);
+        pending += seq.size() + 1;
+        if (pending >= batch_bases) {
+            eng.run(batch);
+            batch.clear();
+            pending = 0;
+        }
+    }
+    if (!batch.records.empty()) eng.run(batch);
+    std::fflush(stdout);
+    fmsi_gpu_index_free(idx);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    if (argc < 2) return usage();
+    const std::string op = argv[1];
+    int ret;
+    if (op == "query" || op == "lookup") {
+        ret = ms_query(argc - 1, argv + 1, op == "lookup");
+        if (ret == -2) return forward_to_reference(argc, argv);
+        return ret;
+    }
+    if (op == "-v") {
+        std::cout << kVersion << std::endl;
+        return 0;
+    }
+    if (op == "-h") {
+        usage();
+        return 0;
+    }
+    if (op == "index" || op == "clean" || op == "merge" || op == "normalize" || op == "compact" || op == "export" || op == "union" ||
+        op == "inter" || op == "diff" || op == "symdiff")
+        return forward_to_reference(argc, argv);
+    return usage();
+}

@@ -1,0 +1,83 @@
+"""The `fmsi` front end (fmsi_b200/bin/fmsi) must print exactly what the reference prints:
+byte-for-byte comparison with the reference binary's committed outputs under tests/golden/,
+for every command/flag combination, including the cases whose output depends on the reference's
+stateful strand predictor."""
+import gzip
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "fmsi_b200", "bin", "fmsi")
+ARGS = {"query": ["query"], "query_O": ["query", "-O"], "query_S": ["query", "-S"], "query_OS": ["query", "-O", "-S"],
+        "lookup": ["lookup"], "lookup_S": ["lookup", "-S"]}
+# cases where no k-mer is decided differently by strand order (max-ones masks, k=31 random genomes)
+LAZY_EXACT = {"syn_k31_max": list(ARGS), "data_k31": list(ARGS), "syn_k31_noklcp": ["query", "query_O", "lookup"],
+              "syn_k31_min": ["query", "query_S"], "syn_k9_min": ["query", "query_S"], "syn_k5_min": ["query", "query_S"]}
+
+
+def run_cli(args, env=None, stdin=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([CLI] + args, capture_output=True, env=e, input=stdin)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_cli_matches_reference_outputs(case):
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    for cmd in meta["cmds"]:
+        r = run_cli(ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")])
+        assert r.returncode == 0, r.stderr.decode()
+        want = open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read()
+        assert r.stdout == want, f"{case}/{cmd}"
+
+
+@pytest.mark.parametrize("case", sorted(LAZY_EXACT))
+def test_cli_lazy_mode_where_order_independent(case):
+    d = os.path.join(GOLDEN, case)
+    for cmd in LAZY_EXACT[case]:
+        r = run_cli(ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")], env={"FMSI_GPU_STRANDS": "lazy"})
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}"
+
+
+def test_cli_small_batches_stdin_gzip_and_k_flag(tmp_path):
+    d = os.path.join(GOLDEN, "syn_k9_max")
+    want = open(os.path.join(d, "exp_lookup_S.txt"), "rb").read()
+    q = open(os.path.join(d, "q.fa"), "rb").read()
+    # tiny batches: predictor state must carry across GPU batches
+    r = run_cli(["lookup", "-S", "-k", "9", "-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")], env={"FMSI_GPU_BATCH_BASES": "500"})
+    assert r.returncode == 0 and r.stdout == want
+    # stdin (default and "-"), gzip input
+    r = run_cli(["lookup", "-S", os.path.join(d, "ms.fa")], stdin=q)
+    assert r.stdout == want
+    gz = tmp_path / "q.fa.gz"
+    gz.write_bytes(gzip.compress(q))
+    r = run_cli(["lookup", "-S", "-q", str(gz), os.path.join(d, "ms.fa")])
+    assert r.stdout == want
+
+
+def test_cli_errors_match_reference_behaviour():
+    d = os.path.join(GOLDEN, "syn_k31_noklcp")
+    r = run_cli(["query", "-S", "-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")])
+    assert r.returncode == 1 and b"kLCP array was not constructed" in r.stderr and r.stdout == b""
+    r = run_cli(["query", "-k", "30", "-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")])
+    assert r.returncode == 1 and b"Mismatch. Provided k (30) does not match the k of the index (31)." in r.stderr
+    r = run_cli(["query", "-q", os.path.join(d, "q.fa"), "/nonexistent/prefix"])
+    assert r.returncode == 1 and b"index not correctly loaded" in r.stderr
+    r = run_cli(["query", "-f", "bogus", os.path.join(d, "ms.fa")])
+    assert r.returncode == 1 and b"Function 'bogus' not recognized." in r.stderr
+    r = run_cli(["lookup", "-f", "xor", os.path.join(d, "ms.fa")])
+    assert r.returncode == 1 and b"Minimum Perfect Hash Function is not allowed" in r.stderr
+    r = run_cli(["query", "-h"])
+    assert r.returncode == 0 and b"Usage:   fmsi query" in r.stderr
+    r = run_cli(["query"])
+    assert r.returncode == 1 and b"Path to the fasta file is a required argument" in r.stderr
+    r = run_cli(["query", "-q", "/nonexistent/q.fa", os.path.join(d, "ms.fa")])
+    assert r.returncode != 0  # the reference aborts on an uncaught std::invalid_argument
