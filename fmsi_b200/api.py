@@ -21,7 +21,7 @@ MAX_STREAM_KMERS = 64
 # every symbol include/fmsi_gpu.h declares (tests check the .so exports exactly these)
 EXPORTED_SYMBOLS = [
     "fmsi_gpu_last_error", "fmsi_gpu_abi_version", "fmsi_gpu_device_count", "fmsi_gpu_index_load",
-    "fmsi_gpu_index_from_bits", "fmsi_gpu_index_free", "fmsi_gpu_index_get_info", "fmsi_gpu_rank",
+    "fmsi_gpu_index_from_bits", "fmsi_gpu_index_build", "fmsi_gpu_index_save", "fmsi_gpu_index_free", "fmsi_gpu_index_get_info", "fmsi_gpu_rank",
     "fmsi_gpu_update_range", "fmsi_gpu_extend_range_with_klcp", "fmsi_gpu_get_range_with_pattern",
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
     "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count",
@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     L.fmsi_gpu_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
     L.fmsi_gpu_index_from_bits.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t, u64p,
                                            C.c_uint64, u8p, C.c_size_t, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.fmsi_gpu_index_build.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.fmsi_gpu_index_save.argtypes = [vp, C.c_char_p]
     L.fmsi_gpu_index_free.argtypes = [vp]
     L.fmsi_gpu_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.fmsi_gpu_rank.argtypes = [vp, u64p, u8p, C.c_size_t, u64p]
@@ -159,6 +161,25 @@ class Index:
             _ptr(cnt, C.c_uint64), int(dollar_position), _ptr(kl, C.c_uint8), kl.size, int(k), device,
             C.byref(opts), C.byref(h)))
         return Index(h)
+
+    @staticmethod
+    def build(ms, k: int, with_klcp: bool = True, device: int = 0, prefix_t: int = -1, n: int | None = None,
+              mem: int = MEM_HOST) -> "Index":
+        """construct(ms, k, use_klcp) on the GPU (reference src/fms_index.h:397). ms: mask-cased ASCII
+        bytes (host) or a raw device pointer (int) with n and mem=MEM_DEVICE."""
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=0)
+        h = C.c_void_p()
+        if isinstance(ms, int):
+            ptr, length = ms, int(n)
+        else:
+            buf = np.frombuffer(ms, dtype=np.uint8)
+            ptr, length = buf.ctypes.data, buf.size
+        _check(lib().fmsi_gpu_index_build(ptr, length, int(k), int(with_klcp), mem, device, C.byref(opts), C.byref(h)))
+        return Index(h)
+
+    def save(self, prefix: str) -> None:
+        """dump_index(index, fn) (reference src/fms_index.h:484): reference-format .fmsi.* files."""
+        _check(lib().fmsi_gpu_index_save(self._h, os.fsencode(prefix)))
 
     def close(self) -> None:
         if self._h:

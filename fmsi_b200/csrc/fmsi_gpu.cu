@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "device_index.cuh"
+#include "index_build.cuh"
 #include "index_layout.hpp"
 #include "query_kernels.cuh"
 #include "stream_kernels.cuh"
@@ -57,6 +58,8 @@ struct fmsi_gpu_index {
     bool wide = false;
     Slot slots[kSlots];
     unsigned long long *d_cursor_user = nullptr;  // cursor for MEM_DEVICE launches
+    // host copies of the BWT/mask/kLCP planes, kept only for indexes made by fmsi_gpu_index_build
+    std::vector<uint64_t> plane_lo, plane_hi, plane_mask, plane_klcp;
 };
 
 namespace {
@@ -163,7 +166,7 @@ int build_table(fmsi_gpu_index *idx, u32 t) {
     return FMSI_GPU_OK;
 }
 
-int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+int select_device(fmsi_gpu_index *idx) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(FMSI_GPU_ERR_CUDA, "no CUDA device available (libfmsi_gpu has no CPU fallback)");
@@ -172,21 +175,12 @@ int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, idx->device));
     idx->sm_count = prop.multiProcessorCount;
-    HostIndex &h = idx->meta;
-    idx->wide = h.wide();
-    const size_t rb = h.rank.size() * sizeof(RankBlock), ab = h.aux.size() * sizeof(AuxBlock);
-    CU(cudaMalloc(&idx->d_rank, rb));
-    CU(cudaMalloc(&idx->d_aux, ab));
-    CU(cudaMalloc(&idx->d_sb, h.sb_base.size() * 8));
-    CU(cudaMalloc(&idx->d_counts, 4 * 8));
-    CU(cudaMemcpy(idx->d_rank, h.rank.data(), rb, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(idx->d_aux, h.aux.data(), ab, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(idx->d_sb, h.sb_base.data(), h.sb_base.size() * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice));
-    idx->hbm_bytes = rb + ab + h.sb_base.size() * 8 + 32;
-    std::vector<RankBlock>().swap(h.rank);
-    std::vector<AuxBlock>().swap(h.aux);
+    return FMSI_GPU_OK;
+}
 
+// Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table, streams, cursors.
+int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+    HostIndex &h = idx->meta;
     DevIndex &d = idx->dev;
     d.rank = reinterpret_cast<const RankBlock *>(idx->d_rank);
     d.aux = reinterpret_cast<const AuxBlock *>(idx->d_aux);
@@ -223,6 +217,26 @@ int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     }
     CU(cudaMalloc(&idx->d_cursor_user, sizeof(unsigned long long)));
     return FMSI_GPU_OK;
+}
+
+int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+    int rc = select_device(idx);
+    if (rc) return rc;
+    HostIndex &h = idx->meta;
+    idx->wide = h.wide();
+    const size_t rb = h.rank.size() * sizeof(RankBlock), ab = h.aux.size() * sizeof(AuxBlock);
+    CU(cudaMalloc(&idx->d_rank, rb));
+    CU(cudaMalloc(&idx->d_aux, ab));
+    CU(cudaMalloc(&idx->d_sb, h.sb_base.size() * 8));
+    CU(cudaMalloc(&idx->d_counts, 4 * 8));
+    CU(cudaMemcpy(idx->d_rank, h.rank.data(), rb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_aux, h.aux.data(), ab, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_sb, h.sb_base.data(), h.sb_base.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice));
+    idx->hbm_bytes = rb + ab + h.sb_base.size() * 8 + 32;
+    std::vector<RankBlock>().swap(h.rank);
+    std::vector<AuxBlock>().swap(h.aux);
+    return finish_device_setup(idx, opts);
 }
 
 BitVec bits_to_vec(const uint8_t *bits, size_t n) {
@@ -318,6 +332,136 @@ int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t
         return rc;
     }
     *out = idx.release();
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_index_build(const char *ms, size_t n, int k, int with_klcp, int mem, int device,
+                         const fmsi_gpu_options *opts, fmsi_gpu_index **out) {
+    if (!ms || !out) return fail(FMSI_GPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (mem != FMSI_GPU_MEM_HOST && mem != FMSI_GPU_MEM_DEVICE) return fail(FMSI_GPU_ERR_ARG, "bad mem");
+    std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
+    idx->device = device;
+    int rc = select_device(idx.get());
+    if (rc) return rc;
+    uint64_t launches = 0;
+    try {
+        DevArr<char> staged;
+        const char *d_ms = ms;
+        if (mem == FMSI_GPU_MEM_HOST) {
+            staged.alloc(n);
+            BCU(cudaMemcpy(staged.p, ms, n, cudaMemcpyHostToDevice));
+            d_ms = staged.p;
+        }
+        BuiltIndex b;
+        build_index_on_device(d_ms, n, k, with_klcp != 0, true, b, &launches);
+        g_launches.fetch_add(launches);
+        HostIndex &h = idx->meta;
+        h.n = b.n_bwt;
+        h.k = k;
+        h.has_klcp = with_klcp != 0;
+        for (int c = 0; c < 4; ++c) h.counts[c] = b.counts[c];
+        h.dollar = b.dollar;
+        h.mask_ones = b.mask_ones;
+        h.sb_shift = 63;
+        h.sb_base.assign(4, 0);
+        idx->wide = false;
+        idx->d_rank = b.rank.p;
+        idx->d_aux = b.aux.p;
+        idx->hbm_bytes = (b.rank.n + b.aux.n) * 32 + 64;
+        b.rank.p = nullptr;
+        b.aux.p = nullptr;
+        idx->plane_lo.swap(b.lo);
+        idx->plane_hi.swap(b.hi);
+        idx->plane_mask.swap(b.mask);
+        idx->plane_klcp.swap(b.klcp);
+    } catch (const std::exception &e) {
+        fmsi_gpu_index_free(idx.release());
+        return fail(FMSI_GPU_ERR_CUDA, std::string("index build: ") + e.what());
+    }
+    HostIndex &h = idx->meta;
+    auto cu_fail = [&](const char *what) {
+        fmsi_gpu_index_free(idx.release());
+        return fail(FMSI_GPU_ERR_CUDA, what);
+    };
+    if (cudaMalloc(&idx->d_sb, 32) != cudaSuccess || cudaMalloc(&idx->d_counts, 32) != cudaSuccess) return cu_fail("cudaMalloc");
+    if (cudaMemcpy(idx->d_sb, h.sb_base.data(), 32, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice) != cudaSuccess)
+        return cu_fail("cudaMemcpy");
+    rc = finish_device_setup(idx.get(), opts);
+    if (rc) {
+        fmsi_gpu_index_free(idx.release());
+        return rc;
+    }
+    *out = idx.release();
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_index_save(const fmsi_gpu_index *idx, const char *prefix) {
+    if (!idx || !prefix) return fail(FMSI_GPU_ERR_ARG, "null argument");
+    if (idx->plane_hi.empty()) return fail(FMSI_GPU_ERR_ARG, "fmsi_gpu_index_save: index was not made by fmsi_gpu_index_build");
+    try {
+        const HostIndex &h = idx->meta;
+        const uint64_t N = h.n, nw = (N + 63) >> 6;
+        const std::string base = std::string(prefix) + ".fmsi";
+        BitVec ac_gt, ac, gt, mask, klcp;
+        ac_gt.resize_bits(N);
+        mask.resize_bits(N);
+        std::memcpy(ac_gt.w.data(), idx->plane_hi.data(), nw * 8);
+        std::memcpy(mask.w.data(), idx->plane_mask.data(), nw * 8);
+        // counts = {1, #A+1, #A+#C+1, ...} -> |ac| = counts[2], |gt| = N - counts[2] (fms_index.h:434-451)
+        ac.resize_bits(h.counts[2]);
+        gt.resize_bits(N - h.counts[2]);
+        uint64_t ap = 0, gp = 0;
+        for (uint64_t b = 0; b < nw; ++b) {
+            const unsigned valid = (unsigned)std::min<uint64_t>(64, N - b * 64);
+            const uint64_t vmask = valid == 64 ? ~0ull : ((1ull << valid) - 1);
+            const uint64_t hi = idx->plane_hi[b] & vmask, lo = idx->plane_lo[b];
+            uint64_t sel = ~hi & vmask;
+            while (sel) {  // A/C/$ slots in order
+                const unsigned t = (unsigned)__builtin_ctzll(sel);
+                if ((lo >> t) & 1) ac.set(ap);
+                ++ap;
+                sel &= sel - 1;
+            }
+            sel = hi;
+            while (sel) {
+                const unsigned t = (unsigned)__builtin_ctzll(sel);
+                if ((lo >> t) & 1) gt.set(gp);
+                ++gp;
+                sel &= sel - 1;
+            }
+        }
+        if (ap != ac.nbits || gp != gt.nbits) throw std::runtime_error("plane sizes inconsistent with counts");
+        {
+            ByteWriter w(base + ".ac_gt");
+            w.bitvec(ac_gt);
+        }
+        {
+            ByteWriter w(base + ".ac");
+            w.bitvec(ac);
+        }
+        {
+            ByteWriter w(base + ".gt");
+            w.bitvec(gt);
+        }
+        write_rrr(base + ".mask", rrr_encode(mask));
+        if (h.has_klcp) {
+            klcp.resize_bits(N);
+            std::memcpy(klcp.w.data(), idx->plane_klcp.data(), nw * 8);
+            ByteWriter w(base + ".klcp");
+            w.bitvec(klcp);
+        } else {
+            std::remove((base + ".klcp").c_str());
+        }
+        FILE *f = std::fopen((base + ".misc").c_str(), "w");
+        if (!f) throw std::runtime_error("cannot create " + base + ".misc");
+        std::fprintf(f, "%llu\n%llu\n%llu\n%llu\n%llu\n%d\n", (unsigned long long)h.dollar, (unsigned long long)h.counts[0],
+                     (unsigned long long)h.counts[1], (unsigned long long)h.counts[2], (unsigned long long)h.counts[3], h.k);
+        std::fclose(f);
+    } catch (const std::exception &e) {
+        return fail(FMSI_GPU_ERR_IO, e.what());
+    }
     return FMSI_GPU_OK;
 }
 

@@ -11,6 +11,7 @@
 // The RRR<63> block code (class = popcount, offset = rank of the 63-bit word inside its class in
 // the combinatorial number system) is decoded ONCE at load into plain bits; the GPU never sees RRR.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -206,12 +207,12 @@ inline BitVec rrr_decode_all(const RrrFile &f) {
     uint64_t off = 0, ones_total = 0;
     for (uint64_t b = 0; b < nblocks; ++b) {
         uint64_t sb = b / kRrrSample;
+        uint64_t pos0 = b * kRrrBlock;
+        if (pos0 >= f.size) break;  // trailing dummy block when size % 63 == 0 (sdsl writes no sample for it)
         if (b % kRrrSample == 0) {
             if (sb >= f.btnrp.n || f.btnrp.get(sb) != off) throw std::runtime_error("rrr: btnrp sample mismatch");
             if (sb >= f.rank.n || f.rank.get(sb) != ones_total) throw std::runtime_error("rrr: rank sample mismatch");
         }
-        uint64_t pos0 = b * kRrrBlock;
-        if (pos0 >= f.size) break;  // trailing dummy block when size % 63 == 0
         unsigned stored = (unsigned)f.bt.get(b);
         unsigned ones = f.invert.get(sb) ? kRrrBlock - stored : stored;
         unsigned len = B.space[stored];
@@ -226,6 +227,103 @@ inline BitVec rrr_decode_all(const RrrFile &f) {
     }
     if (f.rank.n == 0 || f.rank.get(f.rank.n - 1) != ones_total) throw std::runtime_error("rrr: total mismatch");
     return out;
+}
+
+
+// ---- writers ----------------------------------------------------------------------------------
+class ByteWriter {
+  public:
+    explicit ByteWriter(const std::string &path) : path_(path) {
+        f_ = std::fopen(path.c_str(), "wb");
+        if (!f_) throw std::runtime_error("cannot create " + path);
+    }
+    ~ByteWriter() {
+        if (f_) std::fclose(f_);
+    }
+    void bytes(const void *p, size_t n) {
+        if (n && std::fwrite(p, 1, n, f_) != n) throw std::runtime_error("short write on " + path_);
+    }
+    void u64(uint64_t v) { bytes(&v, 8); }
+    void u8(uint8_t v) { bytes(&v, 1); }
+    void bitvec(const BitVec &b) {
+        u64(b.nbits);
+        bytes(b.w.data(), ((b.nbits + 63) >> 6) * 8);
+    }
+    void intvec(const IntVec &v) {
+        u64(v.bits.nbits);
+        u8((uint8_t)v.width);
+        bytes(v.bits.w.data(), ((v.bits.nbits + 63) >> 6) * 8);
+    }
+
+  private:
+    FILE *f_ = nullptr;
+    std::string path_;
+};
+
+inline unsigned bit_length_or_one(uint64_t x) { return x ? 64 - (unsigned)__builtin_clzll(x) : 1; }  // sdsl bits::hi(x) + 1
+
+// Encode a plain bit vector as sdsl's rrr_vector<63> would (constructor, sdsl rrr_vector.hpp:150-250):
+// 63-bit blocks stored as (class, offset in class); every 32 blocks one sample of the offset-stream
+// position and of the running rank; a full superblock in which more than half of the blocks have
+// more than 31 ones is stored complemented (classes only) and flagged in `invert`.
+inline RrrFile rrr_encode(const BitVec &bv) {
+    const Binomials &B = Binomials::get();
+    RrrFile f;
+    f.size = bv.nbits;
+    const uint64_t nblocks = (bv.nbits + kRrrBlock) / kRrrBlock;  // incl. a dummy block when size % 63 == 0
+    const uint64_t nsuper = (nblocks + kRrrSample - 1) / kRrrSample;
+    std::vector<uint8_t> cls(nblocks, 0);
+    std::vector<uint64_t> word(nblocks, 0);
+    uint64_t total_ones = 0, stream_bits = 0;
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        const uint64_t pos = b * kRrrBlock;
+        if (pos >= bv.nbits) break;
+        const unsigned len = (unsigned)std::min<uint64_t>(kRrrBlock, bv.nbits - pos);
+        word[b] = bv.get_int(pos, len);
+        cls[b] = (uint8_t)__builtin_popcountll(word[b]);
+        total_ones += cls[b];
+        stream_bits += B.space[cls[b]];
+    }
+    f.bt.alloc(nblocks, 6);
+    f.btnr.resize_bits(std::max<uint64_t>(stream_bits, 64));
+    f.btnrp.alloc(nsuper, bit_length_or_one(stream_bits));
+    f.rank.alloc(nsuper + ((bv.nbits % ((uint64_t)kRrrSample * kRrrBlock)) > 0 ? 1 : 0), bit_length_or_one(total_ones));
+    f.invert.resize_bits(nsuper);
+    uint64_t off = 0, ones = 0;
+    for (uint64_t sb = 0; sb < nsuper; ++sb) {
+        const uint64_t b0 = sb * kRrrSample, b1 = std::min<uint64_t>(b0 + kRrrSample, nblocks);
+        if (b0 * kRrrBlock >= bv.nbits) break;  // superblock made only of the dummy block: no sample written
+        f.btnrp.set(sb, off);
+        f.rank.set(sb, ones);
+        bool inv = false;
+        if (b0 + kRrrSample <= nblocks) {  // only complete superblocks may be complemented
+            unsigned heavy = 0;
+            for (uint64_t b = b0; b < b1; ++b) heavy += cls[b] > kRrrBlock / 2;
+            inv = heavy > kRrrSample / 2;
+        }
+        if (inv) f.invert.set(sb);
+        for (uint64_t b = b0; b < b1; ++b) {
+            const unsigned stored = inv ? kRrrBlock - cls[b] : cls[b];
+            f.bt.set(b, stored);
+            if (b * kRrrBlock >= bv.nbits) continue;  // dummy block: class only
+            const unsigned len = B.space[stored];
+            if (len) f.btnr.set_int(off, rrr_rank_of_word(word[b]), len);
+            off += len;
+            ones += cls[b];
+        }
+    }
+    f.rank.set(f.rank.n - 1, total_ones);
+    return f;
+}
+
+inline void write_rrr(const std::string &path, const RrrFile &f) {
+    ByteWriter w(path);
+    w.u64(f.size);
+    w.intvec(f.bt);
+    w.bitvec(f.btnr);
+    w.intvec(f.btnrp);
+    w.intvec(f.rank);
+    w.bitvec(f.invert);
 }
 
 }  // namespace fmsi

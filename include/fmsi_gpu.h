@@ -89,6 +89,16 @@ int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t
                              const uint64_t counts[4], uint64_t dollar_position, const uint8_t *klcp,
                              size_t n_klcp, int k, int device, const fmsi_gpu_options *opts,
                              fmsi_gpu_index **out);
+/* construct<T>(ms, k, use_klcp) — reference src/fms_index.h:397-460 (+ construct_klcp :357-385),
+ * on the GPU: suffix-sorts the mask-cased superstring `ms` (ACGTacgt, upper case = ON, n characters,
+ * host or device memory per `mem`), and builds the device-resident index directly. The suffix
+ * array is unique, so the result equals the reference's `fmsi index` output (fmsi_gpu_index_save
+ * writes byte-identical files). Limits: n + 1 < 2^32, k <= 32. */
+int fmsi_gpu_index_build(const char *ms, size_t n, int k, int with_klcp, int mem, int device,
+                         const fmsi_gpu_options *opts, fmsi_gpu_index **out);
+/* dump_index(index, fn) — reference src/fms_index.h:484-500: writes <prefix>.fmsi.{ac_gt,ac,gt,mask,
+ * klcp,misc} in the reference's (sdsl) formats. Only for indexes made by fmsi_gpu_index_build. */
+int fmsi_gpu_index_save(const fmsi_gpu_index *idx, const char *prefix);
 int fmsi_gpu_index_free(fmsi_gpu_index *idx);
 int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info);
 

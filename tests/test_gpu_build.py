@@ -1,0 +1,90 @@
+"""GPU index construction (fmsi_gpu_index_build / _save) must reproduce the reference's
+`fmsi index` output byte for byte: the suffix array is unique, so ac_gt/ac/gt/klcp/mask/misc are."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle_ffi import REF_EXE
+
+import fmsi_b200 as fg
+from fmsi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+EXTS = ["ac_gt", "ac", "gt", "mask", "klcp", "misc"]
+
+
+def compare_files(got_prefix, want_prefix, klcp=True):
+    for ext in EXTS:
+        if ext == "klcp" and not klcp:
+            assert not os.path.exists(f"{got_prefix}.fmsi.klcp")
+            continue
+        a = open(f"{got_prefix}.fmsi.{ext}", "rb").read()
+        b = open(f"{want_prefix}.fmsi.{ext}", "rb").read()
+        assert a == b, f"{ext} differs ({len(a)} vs {len(b)} bytes)"
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_build_reproduces_reference_index_files(case, tmp_path):
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    ms = open(os.path.join(d, "ms.fa"), "rb").read().split(b"\n")[1]
+    idx = fg.Index.build(ms, meta["k"], with_klcp=meta["klcp"])
+    out = str(tmp_path / "ms.fa")
+    idx.save(out)
+    compare_files(out, os.path.join(d, "ms.fa"), klcp=meta["klcp"])
+    # and the built index answers queries like the loaded one
+    ref = fg.Index.load(os.path.join(d, "ms.fa"), use_klcp=meta["klcp"])
+    codes = synth.ascii_to_codes(ms)
+    if len(codes) >= meta["k"]:
+        kmers = synth.pack_kmers(codes, meta["k"])[:5000]
+        rnd = np.random.default_rng(1).integers(0, 1 << (2 * meta["k"]) - 1, size=2000, dtype=np.uint64)
+        q = np.concatenate([kmers, rnd])
+        for out_kind in (fg.OUT_PRESENCE, fg.OUT_ORDERS):
+            assert np.array_equal(idx.query_kmers(q, meta["k"], fg.MODE_OR, out_kind), ref.query_kmers(q, meta["k"], fg.MODE_OR, out_kind))
+    idx.close()
+    ref.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/fmsi not shipped")
+@pytest.mark.parametrize("name", ["polyA", "tandem", "repeats", "random300k", "two_letters"])
+def test_build_on_repetitive_inputs(name, tmp_path):
+    rng = np.random.default_rng(5)
+    if name == "polyA":
+        ms, k = b"A" * 700 + b"a" * 4, 5
+    elif name == "tandem":
+        ms, k = (b"ACGTTGCA" * 300) + b"acgt", 5
+    elif name == "repeats":
+        unit = synth.codes_to_ascii(rng.integers(0, 4, size=900, dtype=np.uint8))
+        parts = []
+        for r in range(12):
+            u = bytearray(unit)
+            for _ in range(3):
+                u[int(rng.integers(0, len(u)))] = b"ACGT"[int(rng.integers(0, 4))]
+            parts.append(bytes(u))
+        s = b"".join(parts)
+        ms, k = s[:-30] + s[-30:].lower(), 31
+    elif name == "random300k":
+        g = synth.random_codes(300_000, 77)
+        ms, k = synth.contig_superstring(g, 23, 50, 78, "max"), 23
+    else:
+        s = synth.codes_to_ascii(rng.integers(0, 2, size=5000, dtype=np.uint8) * 3)  # only A and T
+        ms, k = s[:-8] + s[-8:].lower(), 9
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta_single(fa, "ms", ms)
+    subprocess.run([REF_EXE, "index", "-k", str(k), fa], check=True, capture_output=True)
+    idx = fg.Index.build(ms, k, with_klcp=True)
+    out = str(tmp_path / "gpu.fa")
+    idx.save(out)
+    compare_files(out, fa)
+    idx.close()
+
+
+def test_build_rejects_bad_input():
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Index.build(b"ACGTNACGT", 3)
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Index.build(b"ACGTACGT", 33)
