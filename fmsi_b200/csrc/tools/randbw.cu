@@ -80,6 +80,11 @@ int main(int argc, char** argv) {
     int nsm = p.multiProcessorCount;
     printf("# %s, %d SMs, L2 %.0f MB\n", p.name, nsm, p.l2CacheSize / 1048576.0);
     uint64_t big = (argc > 1 ? strtoull(argv[1], 0, 10) : 4096ull) << 20;
+    // argv[2]: cudaLimitMaxL2FetchGranularity in bytes (32/64/128; 0 = leave the driver default)
+    size_t gran = argc > 2 ? strtoull(argv[2], 0, 10) : 0, got = 0;
+    if (gran) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran));
+    CK(cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity));
+    printf("# cudaLimitMaxL2FetchGranularity = %zu (requested %zu)\n", got, gran);
     uint8_t* buf; CK(cudaMalloc(&buf, big));
     CK(cudaMemset(buf, 0x5a, big));
     uint64_t* sink; CK(cudaMalloc(&sink, 8));
