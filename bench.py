@@ -499,7 +499,7 @@ def main():
                 config=dict(workload=args.workload, desc=wl["desc"], k=k, superstring=wl["how"], kmers_per_step_per_gpu=batch,
                             mode="query -O (MODE_ALL, STRANDS_LAZY)", parallelism=f"replicas x{world}, queries sharded, no collective",
                             l2="inputs larger than L2: 2 alternating batches of %d MiB" % (batch * 8 >> 20), n_bwt=int(info.n_bwt),
-                            prefix_t=int(info.prefix_t), index_hbm_bytes=int(info.hbm_bytes), index_setup_s=round(load_s, 2),
+                            prefix_t=int(info.prefix_t), dictionary_tier=bool(info.dict), index_hbm_bytes=int(info.hbm_bytes), index_setup_s=round(load_s, 2),
                             frac_present=round(frac_present, 4), e2e_equals_device=same, parity_vs_oracle_sample=parity),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=batch * 8, d2h_bytes_per_step=batch * 1),

@@ -14,11 +14,13 @@ typedef unsigned int u32;
 struct DevIndex {
     const RankBlock *rank;
     const AuxBlock *aux;
-    const void *table;    // 4^t entries {i, j}: u32 pairs (narrow) or u64 pairs (wide)
+    const void *table;    // 4^t entries, 1 << tshift bytes apart, each starting with {i, j}: u32 pairs
+                          // (narrow; 32-byte dictionary buckets when tshift == 5) or u64 pairs (wide)
     const u64 *sb_base;   // [n_superblocks][4]
     u64 n;                // N = BWT length
     u64 dollar;
     u32 t;                // suffix-table depth (0 = no table)
+    u32 tshift;           // log2 of the table entry stride in bytes
     u32 sb_shift;
     u32 k;
     u32 has_klcp;

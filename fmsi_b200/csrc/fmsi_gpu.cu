@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "device_index.cuh"
+#include "dict.cuh"
 #include "index_build.cuh"
 #include "index_layout.hpp"
 #include "query_kernels.cuh"
@@ -38,12 +39,20 @@ int fail(int code, const std::string &msg) {
 constexpr int kSlots = 2;
 constexpr size_t kBatchKmers = 16u << 20;  // k-mers per pipelined host batch
 
+// Per-launch device scratch: ctr[0] = work cursor, ctr[1] = overflow count of the dictionary kernel,
+// ctr[2] = work cursor of the fixup launch; ovf = overflow list (one u32 per query of the launch).
+struct LaunchScratch {
+    unsigned long long *ctr = nullptr;
+    void *ovf = nullptr;
+    size_t ovf_cap = 0;
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     void *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr;
     size_t in_cap = 0, out_cap = 0, aux_cap = 0;
-    unsigned long long *d_cursor = nullptr;
+    LaunchScratch ls;
 };
 
 }  // namespace
@@ -53,11 +62,12 @@ struct fmsi_gpu_index {
     int sm_count = 0;
     HostIndex meta;  // vectors released after upload
     DevIndex dev{};
-    void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr;
+    void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr, *d_rows = nullptr;
     uint64_t hbm_bytes = 0;
     bool wide = false;
+    DictView dict{};
     Slot slots[kSlots];
-    unsigned long long *d_cursor_user = nullptr;  // cursor for MEM_DEVICE launches
+    LaunchScratch user;  // scratch for MEM_DEVICE launches
     // host copies of the BWT/mask/kLCP planes, kept only for indexes made by fmsi_gpu_index_build
     std::vector<uint64_t> plane_lo, plane_hi, plane_mask, plane_klcp;
 };
@@ -75,6 +85,8 @@ int ensure(void **p, size_t *cap, size_t need) {
     return FMSI_GPU_OK;
 }
 
+inline unsigned blocks_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
 template <typename Kernel>
 int persistent_grid(const fmsi_gpu_index *idx, Kernel kern, int block) {
     int per_sm = 0;
@@ -91,38 +103,68 @@ u32 pick_chunk(size_t n, int grid, int block) {
     return (u32)c;
 }
 
+// Backward-search kernel over all n queries.
 template <int MODE, int OUT, int STRANDS, bool WIDE>
 int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
-                 unsigned long long *cursor, cudaStream_t st) {
-    auto kern = query_kmers_kernel<MODE, OUT, STRANDS, WIDE>;
+                 LaunchScratch &ls, cudaStream_t st) {
+    auto kern = query_kmers_kernel<MODE, OUT, STRANDS, WIDE, false>;
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     const u32 chunk = pick_chunk(n, grid, kQueryBlock);
-    CU(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, cursor, chunk);
+    CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
+    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
 }
 
+// Dictionary kernel over all n queries (n < 2^32) + the backward-search fixup launch over the
+// queries it put on the overflow list (usually none: that launch then exits at once).
+template <int MODE, int OUT, int STRANDS>
+int launch_dict(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
+                LaunchScratch &ls, cudaStream_t st) {
+    int rc;
+    if ((rc = ensure(&ls.ovf, &ls.ovf_cap, n * sizeof(u32)))) return rc;
+    CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
+    const bool pay64 = idx->dict.B > 16;
+    int grid;
+    if (pay64) {
+        auto kern = dict_query_kernel<MODE, OUT, STRANDS, true>;
+        grid = persistent_grid(idx, kern, kQueryBlock);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, idx->dict, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), (u32 *)ls.ovf, ls.ctr + 1);
+    } else {
+        auto kern = dict_query_kernel<MODE, OUT, STRANDS, false>;
+        grid = persistent_grid(idx, kern, kQueryBlock);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, idx->dict, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), (u32 *)ls.ovf, ls.ctr + 1);
+    }
+    CU(cudaGetLastError());
+    auto fix = query_kmers_kernel<MODE, OUT, STRANDS, false, true>;
+    const int fgrid = persistent_grid(idx, fix, kQueryBlock);
+    fix<<<fgrid, kQueryBlock, 0, st>>>(d, kmers, 0, out, ls.ctr + 2, 32u, (const u32 *)ls.ovf, ls.ctr + 1);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(2);
+    return FMSI_GPU_OK;
+}
+
 template <int MODE, int OUT, int STRANDS>
 int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
-                   unsigned long long *cursor, cudaStream_t st) {
-    if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, cursor, st);
-    return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, cursor, st);
+                   LaunchScratch &ls, cudaStream_t st) {
+    if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, ls, st);
+    if (idx->dict.enabled && d.k == idx->dict.k && d.t && n < (1ull << 32)) return launch_dict<MODE, OUT, STRANDS>(idx, d, kmers, n, out, ls, st);
+    return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, ls, st);
 }
 
 int dispatch_query(const fmsi_gpu_index *idx, const DevIndex &d, int mode, int output, int strands,
-                   const u64 *kmers, size_t n, void *out, unsigned long long *cursor, cudaStream_t st) {
+                   const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
     if (output == FMSI_GPU_OUT_ORDERS) {
-        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
-        return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
+        return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
     }
     if (mode == FMSI_GPU_MODE_ALL) {
-        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
-        return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
+        return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
     }
-    if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, cursor, st);
-    return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, cursor, st);
+    if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
+    return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
 }
 
 size_t result_bytes(int output, int strands) {
@@ -138,10 +180,10 @@ DevIndex dev_for_k(const fmsi_gpu_index *idx, int k) {
     return d;
 }
 
+// Suffix table at depth t as a plain {i, j} array (level by level; returns the full level).
 template <bool WIDE>
-int build_table(fmsi_gpu_index *idx, u32 t) {
+int build_table_levels(fmsi_gpu_index *idx, u32 t, TableEntry<WIDE> **out_full) {
     typedef TableEntry<WIDE> E;
-    if (t == 0) return FMSI_GPU_OK;
     const u64 total = 1ull << (2 * t);
     E *full = nullptr, *quarter = nullptr;
     CU(cudaMalloc(&full, total * sizeof(E)));
@@ -159,10 +201,80 @@ int build_table(fmsi_gpu_index *idx, u32 t) {
     }
     CU(cudaDeviceSynchronize());
     if (quarter) cudaFree(quarter);
+    *out_full = full;
+    return FMSI_GPU_OK;
+}
+
+template <bool WIDE>
+int build_table(fmsi_gpu_index *idx, u32 t) {
+    if (t == 0) return FMSI_GPU_OK;
+    TableEntry<WIDE> *full = nullptr;
+    int rc = build_table_levels<WIDE>(idx, t, &full);
+    if (rc) return rc;
     idx->d_table = full;
     idx->dev.table = full;
     idx->dev.t = t;
-    idx->hbm_bytes += total * sizeof(E);
+    idx->dev.tshift = WIDE ? 4 : 3;
+    idx->hbm_bytes += (1ull << (2 * t)) * sizeof(TableEntry<WIDE>);
+    return FMSI_GPU_OK;
+}
+
+// Dictionary tier (dict.cuh): rows from the BWT, then 32-byte buckets in place of the {i, j} table.
+int build_dict(fmsi_gpu_index *idx, u32 t) {
+    const HostIndex &h = idx->meta;
+    const u64 N = h.n;
+    const u32 k = (u32)h.k, B = k - t;
+    DevIndex d = idx->dev;
+    u32 *psi = nullptr;
+    u64 *rows = nullptr;
+    CU(cudaMalloc(&psi, N * sizeof(u32)));
+    if (cudaMalloc(&rows, N * sizeof(u64)) != cudaSuccess) {
+        cudaFree(psi);
+        return fail(FMSI_GPU_ERR_NOMEM, "dictionary rows: out of device memory");
+    }
+    psi_scatter_kernel<<<blocks_for(N), 256>>>(d, psi);
+    rows_walk_kernel<<<blocks_for(N), 256>>>(d, psi, (u32)h.counts[1], (u32)h.counts[2], (u32)h.counts[3], t, B, rows);
+    rows_invalidate_kernel<<<1, 32>>>(d, k, rows);
+    g_launches.fetch_add(3);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(psi);
+    if (e != cudaSuccess) {
+        cudaFree(rows);
+        return fail(FMSI_GPU_ERR_CUDA, std::string("dictionary rows: ") + cudaGetErrorString(e));
+    }
+    TableEntry<false> *full = nullptr;
+    int rc = build_table_levels<false>(idx, t, &full);
+    if (rc) {
+        cudaFree(rows);
+        return rc;
+    }
+    const u64 total = 1ull << (2 * t);
+    Bucket *buckets = nullptr;
+    if (cudaMalloc(&buckets, total * sizeof(Bucket)) != cudaSuccess) {
+        cudaFree(rows);
+        cudaFree(full);
+        return fail(FMSI_GPU_ERR_NOMEM, "dictionary buckets: out of device memory");
+    }
+    if (B > 16) bucket_fill_kernel<true><<<blocks_for(total), 256>>>(full, rows, total, buckets);
+    else bucket_fill_kernel<false><<<blocks_for(total), 256>>>(full, rows, total, buckets);
+    g_launches.fetch_add(1);
+    e = cudaDeviceSynchronize();
+    cudaFree(full);
+    if (e != cudaSuccess) {
+        cudaFree(rows);
+        cudaFree(buckets);
+        return fail(FMSI_GPU_ERR_CUDA, std::string("dictionary buckets: ") + cudaGetErrorString(e));
+    }
+    idx->d_table = buckets;
+    idx->d_rows = rows;
+    idx->dev.table = buckets;
+    idx->dev.t = t;
+    idx->dev.tshift = 5;
+    idx->dict.rows = rows;
+    idx->dict.B = B;
+    idx->dict.k = k;
+    idx->dict.enabled = 1;
+    idx->hbm_bytes += total * sizeof(Bucket) + N * sizeof(u64);
     return FMSI_GPU_OK;
 }
 
@@ -178,7 +290,13 @@ int select_device(fmsi_gpu_index *idx) {
     return FMSI_GPU_OK;
 }
 
-// Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table, streams, cursors.
+int alloc_scratch(LaunchScratch &ls) {
+    CU(cudaMalloc(&ls.ctr, 4 * sizeof(unsigned long long)));
+    return FMSI_GPU_OK;
+}
+
+// Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table or dictionary,
+// streams, launch scratch.
 int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     HostIndex &h = idx->meta;
     DevIndex &d = idx->dev;
@@ -189,34 +307,59 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     d.n = h.n;
     d.dollar = h.dollar;
     d.t = 0;
+    d.tshift = 3;
     d.sb_shift = h.sb_shift >= 63 ? 63 : h.sb_shift;
     d.k = (u32)h.k;
     d.has_klcp = h.has_klcp;
 
-    // Suffix-table depth: auto = largest t with 4^t <= N (table no larger than ~2x the rank
-    // array), capped by k, by 16 and by a quarter of the free device memory.
     int t = opts ? opts->prefix_t : -1;
     if (const char *e = std::getenv("FMSI_GPU_PREFIX_T")) t = std::atoi(e);
-    if (t < 0) {
-        t = 0;
-        while (t < 16 && (1ull << (2 * (t + 1))) <= h.n) ++t;
-    }
-    if (t > h.k) t = h.k;
-    if (t > 16) t = 16;
+    int want_dict = opts ? opts->dict : -1;
+    if (const char *e = std::getenv("FMSI_GPU_DICT")) want_dict = std::atoi(e);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const size_t esz = idx->wide ? 16 : 8;
-    while (t > 0 && ((1ull << (2 * t)) * esz * 5 / 4) > free_b / 4) --t;
-    int rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
+
+    // Dictionary tier: narrow indexes with k <= 32. Depth = the largest t <= min(k, 15) with
+    // 4^t <= 4N (on average at most ~4 and at least ~0.25 rows per bucket) whose buckets (32 B each)
+    // plus rows (8 B per SA row, + 4 B per row of build scratch) fit in half of the free memory.
+    bool dict = want_dict != 0 && !idx->wide && h.k >= 1 && h.k <= 32 && h.n < (1ull << 32) - 64;
+    if (dict) {
+        int td = t;
+        if (td < 0) {
+            td = 1;
+            while (td < 15 && (1ull << (2 * (td + 1))) <= 4 * h.n) ++td;
+        }
+        if (td > h.k) td = h.k;
+        if (td > 15) td = 15;
+        const size_t rows_b = (size_t)h.n * 12;
+        while (td > 1 && t < 0 && ((1ull << (2 * td)) * 40 + rows_b) > free_b / 2) --td;
+        if (td < 1 || ((1ull << (2 * td)) * 40 + rows_b) > free_b - free_b / 8) dict = false;
+        else t = td;
+    }
+    int rc;
+    if (dict) {
+        rc = build_dict(idx, (u32)t);
+    } else {
+        // Suffix-table depth: auto = largest t with 4^t <= N (table no larger than ~2x the rank
+        // array), capped by k, by 16 and by a quarter of the free device memory.
+        if (t < 0) {
+            t = 0;
+            while (t < 16 && (1ull << (2 * (t + 1))) <= h.n) ++t;
+        }
+        if (t > h.k) t = h.k;
+        if (t > 16) t = 16;
+        const size_t esz = idx->wide ? 16 : 8;
+        while (t > 0 && ((1ull << (2 * t)) * esz * 5 / 4) > free_b / 4) --t;
+        rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
+    }
     if (rc) return rc;
 
     for (int s = 0; s < kSlots; ++s) {
         CU(cudaStreamCreateWithFlags(&idx->slots[s].stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&idx->slots[s].done, cudaEventDisableTiming));
-        CU(cudaMalloc(&idx->slots[s].d_cursor, sizeof(unsigned long long)));
+        if ((rc = alloc_scratch(idx->slots[s].ls))) return rc;
     }
-    CU(cudaMalloc(&idx->d_cursor_user, sizeof(unsigned long long)));
-    return FMSI_GPU_OK;
+    return alloc_scratch(idx->user);
 }
 
 int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
@@ -269,8 +412,6 @@ struct DevBuf {
     }
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
-
-inline unsigned blocks_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace
 
@@ -468,10 +609,10 @@ int fmsi_gpu_index_save(const fmsi_gpu_index *idx, const char *prefix) {
 int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     if (!idx) return FMSI_GPU_OK;
     cudaSetDevice(idx->device);
-    for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, (void *)idx->d_cursor_user})
+    for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
     for (auto &s : idx->slots) {
-        for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.d_cursor})
+        for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.ls.ctr, s.ls.ovf})
             if (p) cudaFree(p);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -491,6 +632,7 @@ int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info
     info->k = idx->meta.k;
     info->has_klcp = idx->meta.has_klcp;
     info->prefix_t = (int32_t)idx->dev.t;
+    info->dict = (int32_t)idx->dict.enabled;
     info->wide = idx->wide;
     info->device = idx->device;
     return FMSI_GPU_OK;
@@ -606,7 +748,7 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
     const size_t rbytes = result_bytes(output, strands);
 
     if (mem == FMSI_GPU_MEM_DEVICE) {
-        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->d_cursor_user, (cudaStream_t)stream);
+        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->user, (cudaStream_t)stream);
     }
     if (mem != FMSI_GPU_MEM_HOST) return fail(FMSI_GPU_ERR_ARG, "bad mem");
 
@@ -620,7 +762,7 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
         int rc;
         if ((rc = ensure(&s.d_in, &s.in_cap, m * 8)) || (rc = ensure(&s.d_out, &s.out_cap, m * rbytes))) return rc;
         CU(cudaMemcpyAsync(s.d_in, kmers + done, m * 8, cudaMemcpyHostToDevice, s.stream));
-        if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.d_cursor, s.stream))) return rc;
+        if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.ls, s.stream))) return rc;
         CU(cudaMemcpyAsync((char *)results + done * rbytes, s.d_out, m * rbytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
         done += m;
@@ -695,10 +837,10 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
         extract_kmers_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
         CU(cudaGetLastError());
         g_launches.fetch_add(1);
-        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.d_cursor : idx->d_cursor_user, st))) return rc;
+        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.ls : idx->user, st))) return rc;
     } else {
         if ((rc = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off, d_len, d_res, n_chunks, d_results,
-                                  on_host ? s.d_cursor : idx->d_cursor_user, st)))
+                                  on_host ? s.ls.ctr : idx->user.ctr, st)))
             return fail(FMSI_GPU_ERR_CUDA, std::string("streaming kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
         g_launches.fetch_add(1);
     }

@@ -34,14 +34,15 @@ template <bool WIDE> struct TableEntry { u32 i, j; };
 template <> struct TableEntry<true> { u64 i, j; };
 
 template <bool WIDE>
-__device__ __forceinline__ void ld_table(const void *table, u64 slot, typename PosT<WIDE>::type &i,
+__device__ __forceinline__ void ld_table(const DevIndex &d, u64 slot, typename PosT<WIDE>::type &i,
                                          typename PosT<WIDE>::type &j) {
+    const char *p = reinterpret_cast<const char *>(d.table) + (slot << d.tshift);
     if (WIDE) {
-        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(table) + slot);
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(p));
         i = (typename PosT<WIDE>::type)e.x;
         j = (typename PosT<WIDE>::type)e.y;
     } else {
-        const uint2 e = __ldg(reinterpret_cast<const uint2 *>(table) + slot);
+        const uint2 e = __ldg(reinterpret_cast<const uint2 *>(p));
         i = (typename PosT<WIDE>::type)e.x;
         j = (typename PosT<WIDE>::type)e.y;
     }
@@ -64,11 +65,15 @@ __device__ __forceinline__ long long strand_result(u64 i, u64 j, u64 mask_i, u64
     return any ? (long long)ri : -1ll;
 }
 
-template <int MODE, int OUT, int STRANDS, bool WIDE>
+// INDIRECT: the launch answers only the queries listed in sel[0 .. *n_dev) (the dictionary kernel's
+// overflow list, dict.cuh): query q of the launch is kmers[sel[q]] and its result goes to slot sel[q].
+template <int MODE, int OUT, int STRANDS, bool WIDE, bool INDIRECT = false>
 __global__ void __launch_bounds__(kQueryBlock)
-query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n, void *__restrict__ out,
-                   unsigned long long *__restrict__ cursor, const u32 chunk) {
+query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_arg, void *__restrict__ out,
+                   unsigned long long *__restrict__ cursor, const u32 chunk, const u32 *__restrict__ sel = nullptr,
+                   const unsigned long long *__restrict__ n_dev = nullptr) {
     typedef typename PosT<WIDE>::type pos_t;
+    const u64 n = INDIRECT ? (u64)*n_dev : n_arg;
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -84,7 +89,20 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n,
     long long res_f = 0;
     // warp state (uniform)
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
+    u32 selA = 0, selB = 0;  // INDIRECT: result slots of the register tiles
     bool exhausted = false;
+    auto fetch = [&](u64 q, u64 &km, u32 &sl) {
+        km = 0;
+        sl = 0;
+        if (q < cend) {
+            if (INDIRECT) {
+                sl = sel[q];
+                km = kmers[sl];
+            } else {
+                km = kmers[q];
+            }
+        }
+    };
 
     for (;;) {
         // ---------------------------------------------------------------- refill idle lanes
@@ -99,8 +117,8 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n,
                 } else {
                     wnext = tile_base = c0;
                     cend = (c0 + chunk < n) ? c0 + chunk : n;
-                    bufA = (tile_base + lane < cend) ? kmers[tile_base + lane] : 0ull;
-                    bufB = (tile_base + 32 + lane < cend) ? kmers[tile_base + 32 + lane] : 0ull;
+                    fetch(tile_base + lane, bufA, selA);
+                    fetch(tile_base + 32 + lane, bufB, selB);
                 }
             }
             if (!exhausted) {
@@ -109,9 +127,14 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n,
                 const bool take = !active && my < cend;
                 const u32 src = (u32)(my - tile_base);  // < 64
                 u64 km = __shfl_sync(FULL, bufA, src & 31u);
+                u32 sl = INDIRECT ? __shfl_sync(FULL, selA, src & 31u) : 0u;
                 if (__any_sync(FULL, take && src >= 32u)) {
                     const u64 kb = __shfl_sync(FULL, bufB, src & 31u);
-                    if (src >= 32u) km = kb;
+                    const u32 sb = INDIRECT ? __shfl_sync(FULL, selB, src & 31u) : 0u;
+                    if (src >= 32u) {
+                        km = kb;
+                        sl = sb;
+                    }
                 }
                 const u64 left = cend - wnext;
                 const u32 want = __popc(need);
@@ -119,11 +142,12 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n,
                 if (wnext - tile_base >= 32) {  // uniform: slide the register tiles
                     tile_base += 32;
                     bufA = bufB;
-                    bufB = (tile_base + 32 + lane < cend) ? kmers[tile_base + 32 + lane] : 0ull;
+                    selA = selB;
+                    fetch(tile_base + 32 + lane, bufB, selB);
                 }
                 if (take) {
                     active = true;
-                    idx = my;
+                    idx = INDIRECT ? (u64)sl : my;
                     kf = km;
                     pat = km;
                     strand = 0;
@@ -152,7 +176,7 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n,
         const bool two = (isS || (isM && need_j)) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         pos_t ti = 0, tj = 0;
-        if (isT) ld_table<WIDE>(d.table, pat & tmask, ti, tj);
+        if (isT) ld_table<WIDE>(d, pat & tmask, ti, tj);
         if (isS || isM) {
             const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
             ld_sector(pa, a0, a1, a2, a3);
@@ -346,7 +370,7 @@ __global__ void probe_get_range_kernel(const DevIndex d, const u64 *kmers, u32 k
     u32 steps = k;
     if (use_table && d.t && d.t <= k) {
         pos_t ti, tj;
-        ld_table<WIDE>(d.table, pat & ((d.t >= 32) ? ~0ull : ((1ull << (2 * d.t)) - 1ull)), ti, tj);
+        ld_table<WIDE>(d, pat & ((d.t >= 32) ? ~0ull : ((1ull << (2 * d.t)) - 1ull)), ti, tj);
         i = ti;
         j = tj;
         pat >>= 2 * d.t;

@@ -189,7 +189,7 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
         const bool two = (isS || (isM && (need_j || will_cont))) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         pos_t ti = 0, tj = 0;
-        if (isT) ld_table<WIDE>(d.table, pat & tmask, ti, tj);
+        if (isT) ld_table<WIDE>(d, pat & tmask, ti, tj);
         if (isS || isM) {
             const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
             ld_sector_l1(pa, a0, a1, a2, a3);

@@ -56,7 +56,9 @@ typedef struct fmsi_gpu_index fmsi_gpu_index;
 typedef struct {
     int32_t prefix_t;      /* depth of the k-mer suffix lookup table; -1 = auto, 0 = none */
     int32_t sb_shift_log2; /* test hook: superblock size (log2 blocks); 0 = auto */
-    int64_t reserved[6];
+    int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto, 0 = off, 1 = on */
+    int32_t reserved32;
+    int64_t reserved[5];
 } fmsi_gpu_options;
 
 typedef struct {
@@ -70,7 +72,8 @@ typedef struct {
     int32_t prefix_t;
     int32_t wide;        /* 1 when N >= 2^32 (64-bit positions on device) */
     int32_t device;
-    int32_t reserved[7];
+    int32_t dict;        /* 1 when the dictionary tier is resident */
+    int32_t reserved[6];
 } fmsi_gpu_index_info;
 
 const char *fmsi_gpu_last_error(void);

@@ -105,12 +105,15 @@ def _random_kmers(rng, ms_codes, k, n):
 
 
 @pytest.mark.parametrize("case", golden_cases())
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3"])
 def test_device_matches_oracle(case, variant):
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
     k = meta["k"]
-    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}}[variant]
+    # dict_t1 / dict_t3: shallow dictionary buckets hold far more rows than fit a sector, which drives
+    # the ROWS phase and the overflow list -> backward-search fixup launch of dict.cuh.
+    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "nodict": {"dict": 0},
+          "dict_t1": {"dict": 1, "prefix_t": 1}, "dict_t3": {"dict": 1, "prefix_t": 3}}[variant]
     if variant != "auto" and case not in ("syn_k31_max", "syn_k9_min", "syn_k5_min", "quirks_k3", "data_k13", "syn_k32"):
         pytest.skip("variants run on a subset")
     prefix = os.path.join(d, "ms.fa")
@@ -118,6 +121,7 @@ def test_device_matches_oracle(case, variant):
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.n == oi.n and gi.k == k and gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
     assert gi.wide == (variant == "wide")
+    assert gi.dict == (variant in ("auto", "dict_t1", "dict_t3") and k <= 32)
     rng = np.random.default_rng(zlib.crc32(case.encode()))
     N = gi.n
     # rank / update_range
@@ -170,6 +174,49 @@ def test_device_matches_oracle(case, variant):
             assert [tuple(r) for r in both.tolist()] == want
     gi.close()
     oi.close()
+
+
+def test_dictionary_tier_on_repetitive_index(tmp_path):
+    """Repeats (mutated copies + homopolymer runs) give buckets with many rows at the automatic depth:
+    the dictionary answers (bucket scan, ROWS phase, overflow -> fixup launch) must equal the
+    backward-search kernel's and the oracle's, in every mode, on a non-max-ones mask."""
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/fmsi not shipped")
+    rng = np.random.default_rng(99)
+    unit = rng.integers(0, 4, size=3000).astype(np.uint8)
+    parts = []
+    for c in range(40):
+        u = unit.copy()
+        sub = rng.random(len(u)) < 0.01
+        u[sub] = (u[sub] + rng.integers(1, 4, size=int(sub.sum()))) & 3
+        parts += [u, np.full(int(rng.integers(20, 200)), c & 3, np.uint8)]
+    g = np.concatenate(parts)
+    for k in (31, 13):
+        mask = rng.random(len(g)) < 0.7
+        mask[len(g) - (k - 1):] = False
+        fa = str(tmp_path / f"rep{k}.fa")
+        synth.write_fasta_single(fa, "ms", synth.codes_to_ascii(g, mask))
+        subprocess.run([REF_EXE, "index", "-k", str(k), fa], check=True, capture_output=True)
+        oi = OracleIndex.load(fa, use_klcp=False)
+        kmers = np.concatenate([_random_kmers(rng, g, k, 20000), synth.pack_kmers(g[:5000], k),
+                                synth.pack_rows(np.stack([np.full(k, c, np.uint8) for c in range(4)]))])
+        strs = None
+        for kw in ({}, {"dict": 1, "prefix_t": 4}, {"dict": 1, "prefix_t": 7}):
+            gd = fg.Index.load(fa, use_klcp=False, **kw)
+            gb = fg.Index.load(fa, use_klcp=False, dict=0)
+            assert gd.dict and not gb.dict
+            for mode, out, omode, oord in ((fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False),
+                                           (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
+                want = oi.query_packed(kmers, k, omode, oord)
+                for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+                    a = gd.query_kmers(kmers, k, mode, out, strands)
+                    b = gb.query_kmers(kmers, k, mode, out, strands)
+                    assert np.array_equal(a, b), (k, kw, mode, out, strands)
+                    if strands == fg.STRANDS_LAZY:
+                        assert np.array_equal(a.astype(np.int64), want), (k, kw, mode, out)
+            gd.close()
+            gb.close()
+        oi.close()
 
 
 def _chunks_of(seq_codes_list, k, max_kmers):
