@@ -478,7 +478,9 @@ def main():
         if os.path.exists(apath):
             alg = json.load(open(apath))
     if alg:
-        launch_ms = ms_per_step  # one query_kmers_kernel launch per step (+ an 8-byte memset)
+        # one dict_query_kernel (or query_kmers_kernel) launch per step dominates; the fixup launch over
+        # the overflow list exits at once on this workload and the 32-byte memset is negligible
+        launch_ms = ms_per_step
         achieved = alg["bytes"] * batch / (launch_ms / 1e3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -486,12 +488,25 @@ def main():
             tj = json.load(open(tpath)).get(args.workload)
             if tj and tj.get("batch"):
                 traffic = tj["dram_bytes_per_launch"] * (batch / tj["batch"])
+        kernel_name = "dict_query_kernel<ALL,PRESENCE,LAZY>" if gi.dict else "query_kmers_kernel<ALL,PRESENCE,LAZY>"
+        hw = None
+        if traffic:
+            # what the hardware actually did (ncu, profiles/traffic.json): DRAM bytes moved per second
+            # against the same measured peak, and L2-miss requests per second against the measured
+            # random-request ceiling of this part (profiles/r01b_randbw2_b200.jsonl)
+            hw = dict(dram_gbs=round(traffic / (launch_ms / 1e3) / 1e9, 1), dram_frac=round(traffic / (launch_ms / 1e3) / 1e9 / peak, 4))
+            if tj.get("l1_sectors_per_launch"):
+                req = tj["l1_sectors_per_launch"] * (batch / tj["batch"]) / (launch_ms / 1e3) / 1e9
+                hw.update(requests_per_kmer=round(tj["l1_sectors_per_launch"] / tj["batch"], 3), grequests_s=round(req, 1),
+                          random_request_ceiling_grequests_s=tj.get("random_request_ceiling_grequests_s"))
         roofline = dict(bound="hbm", achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=traffic,
-                        kernel="query_kmers_kernel<ALL,PRESENCE,LAZY>", launch_ms=round(launch_ms, 4), peak_source=peak_src,
+                        kernel=kernel_name, launch_ms=round(launch_ms, 4), peak_source=peak_src, hardware=hw,
                         algorithmic=dict(bytes_per_kmer=round(alg["bytes"], 1), lf_steps_per_kmer=round(alg["lf_steps"], 2),
                                          rank_sectors_per_kmer=round(alg["rank_sectors"], 2), mask_sectors_per_kmer=round(alg["mask_sectors"], 2)),
-                        note="algorithmic bytes = the reference algorithm's dependent sector probes per k-mer (SURVEY 8d: 32 B per "
-                             "rank/mask probe + 8 B query + 1 B result), counted by the instrumented oracle on the same query distribution")
+                        note="algorithmic bytes = the REFERENCE algorithm's dependent sector probes per k-mer (SURVEY 8d: 32 B per "
+                             "rank/mask probe + 8 B query + 1 B result), counted by the instrumented oracle on the same query "
+                             "distribution; frac > 1 because the dictionary tier answers a strand search in ~1 request instead of "
+                             "k-t LF-steps - `hardware` says how close the kernel runs to the memory system's own limits")
 
     info = gi.info
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
