@@ -460,7 +460,7 @@ def main():
     roofline, cpu, parity = None, None, None
     have_files = os.path.exists(wl["prefix"] + ".fmsi.misc")
     alg = None
-    if have_files and not args.no_cpu_baseline:
+    if have_files and not args.no_cpu_baseline and world == 1:
         # cpu_baseline leg: the oracle counts the reference algorithm's sector probes on a sample and
         # checks the GPU's answers on it; the reference binary is timed on the host cores.
         alg = algorithmic_bytes_per_kmer(wl, 100_000 if device_built else 200_000, seed=77)
@@ -468,11 +468,10 @@ def main():
         parity = bool(np.array_equal(got.astype(np.int64), alg["_expected"]))
         with open(os.path.join(ROOT, "profiles", f"algorithmic_{args.workload}.json"), "w") as f:
             json.dump({kk: vv for kk, vv in alg.items() if not kk.startswith("_")}, f)
-        if world == 1:
-            try:
-                cpu = reference_cpu_rate(wl, cpu_sample, seed=9000)
-            except Exception as ex:  # keep the bench line even if the reference binary did not travel
-                cpu = dict(value=None, unit=UNIT, cores=0, kind="reference", sample=f"unavailable: {ex}")
+        try:
+            cpu = reference_cpu_rate(wl, cpu_sample, seed=9000)
+        except Exception as ex:  # keep the bench line even if the reference binary did not travel
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="reference", sample=f"unavailable: {ex}")
     else:
         apath = os.path.join(ROOT, "profiles", f"algorithmic_{args.workload}.json")
         if os.path.exists(apath):
