@@ -24,7 +24,8 @@ EXPORTED_SYMBOLS = [
     "fmsi_gpu_index_from_bits", "fmsi_gpu_index_build", "fmsi_gpu_index_save", "fmsi_gpu_index_free", "fmsi_gpu_index_get_info", "fmsi_gpu_rank",
     "fmsi_gpu_update_range", "fmsi_gpu_extend_range_with_klcp", "fmsi_gpu_get_range_with_pattern",
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
-    "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count",
+    "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_free",
+    "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks",
 ]
 
 
@@ -86,6 +87,12 @@ def lib() -> C.CDLL:
     L.fmsi_gpu_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp,
                                         C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    L.fmsi_gpu_pool_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.fmsi_gpu_pool_size.argtypes = [vp]
+    L.fmsi_gpu_pool_free.argtypes = [vp]
+    L.fmsi_gpu_pool_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp]
+    L.fmsi_gpu_pool_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, C.c_size_t,
+                                             C.c_size_t, C.c_int, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("fmsi_gpu_abi_version", "fmsi_gpu_device_count"):
@@ -278,6 +285,52 @@ class Index:
         _check(lib().fmsi_gpu_query_chunks(self._h, mode, output, strands, int(streaming), b.ctypes.data, b.size,
                                           off.ctypes.data, ln.ctypes.data, res_off.ctypes.data, off.size, n_res, k,
                                           out.ctypes.data, MEM_HOST, None))
+        return out
+
+
+class Pool:
+    """Multi-GPU scheduler: `primary` plus device-to-device replicas on `devices`; host batches are
+    split into contiguous ranges, one host thread per member, results in query order."""
+
+    def __init__(self, primary: Index, devices):
+        self.primary = primary
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _check(lib().fmsi_gpu_pool_create(primary._h, devs, len(devices), C.byref(h)))
+        self._h = h
+        self.size = int(lib().fmsi_gpu_pool_size(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().fmsi_gpu_pool_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query_kmers(self, kmers, k: int | None = None, mode: int = MODE_OR, output: int = OUT_PRESENCE,
+                    strands: int = STRANDS_LAZY) -> np.ndarray:
+        kmers = _u64(kmers)
+        k = self.primary.k if k is None else k
+        dt, shape = result_dtype_shape(output, strands, kmers.size)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_pool_query_kmers(self._h, mode, output, strands, kmers.ctypes.data, kmers.size, k, out.ctypes.data))
+        return out
+
+    def query_chunks(self, bases, chunk_off, chunk_len, k: int | None = None, mode: int = MODE_OR, output: int = OUT_PRESENCE,
+                     strands: int = STRANDS_LAZY, streaming: bool = False) -> np.ndarray:
+        k = self.primary.k if k is None else k
+        b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.ascontiguousarray(bases, dtype=np.uint8)
+        off = _u64(chunk_off)
+        ln = np.ascontiguousarray(chunk_len, dtype=np.uint32)
+        n_res = int((ln.astype(np.int64) - k + 1).sum())
+        dt, shape = result_dtype_shape(output, strands, n_res)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_pool_query_chunks(self._h, mode, output, strands, int(streaming), b.ctypes.data, b.size,
+                                               off.ctypes.data, ln.ctypes.data, off.size, n_res, k, out.ctypes.data))
         return out
 
 

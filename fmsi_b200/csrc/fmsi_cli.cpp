@@ -293,6 +293,7 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
 
 struct Engine {
     fmsi_gpu_index *idx = nullptr;
+    fmsi_gpu_pool *pool = nullptr;  // set when $FMSI_GPU_DEVICES names more than one replica
     int k = 0;
     bool streaming = false, orders = false, lazy = false;
     fmsi::QueryMode mode = fmsi::QueryMode::Or;
@@ -322,7 +323,10 @@ struct Engine {
             raw8.resize(n);
             raw = raw8.data();
         }
-        if (n)
+        if (n && pool)
+            check(fmsi_gpu_pool_query_chunks(pool, gmode, gout, gstr, streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
+                                             b.chunk_len.data(), b.chunk_off.size(), n, k, raw));
+        else if (n)
             check(fmsi_gpu_query_chunks(idx, gmode, gout, gstr, streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
                                         b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, k, raw, FMSI_GPU_MEM_HOST, nullptr));
         // ---- final values in query order
@@ -443,8 +447,26 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     }
     if (f_name != "or" && f_name != "all") return -2;  // general f-MS mode: caller forwards to the reference
 
+    // $FMSI_GPU_DEVICES = "all" | "0,1,2,..." : shard every batch over replicas on these GPUs
+    // (multi-GPU scheduler of the C-ABI); otherwise $FMSI_GPU_DEVICE (default 0) alone.
     int device = 0;
     if (const char *e = std::getenv("FMSI_GPU_DEVICE")) device = atoi(e);
+    std::vector<int> devices;
+    if (const char *e = std::getenv("FMSI_GPU_DEVICES")) {
+        const std::string v = e;
+        if (v == "all") {
+            for (int dvc = 0; dvc < fmsi_gpu_device_count(); ++dvc) devices.push_back(dvc);
+        } else {
+            size_t at = 0;
+            while (at < v.size()) {
+                size_t end = v.find(',', at);
+                if (end == std::string::npos) end = v.size();
+                if (end > at) devices.push_back(atoi(v.substr(at, end - at).c_str()));
+                at = end + 1;
+            }
+        }
+        if (!devices.empty()) device = devices[0];
+    }
     fmsi_gpu_index *idx = nullptr;
     int rc = fmsi_gpu_index_load(fn.c_str(), has_klcp ? 1 : 0, device, nullptr, &idx);
     if (rc == FMSI_GPU_ERR_IO) {
@@ -473,6 +495,13 @@ int ms_query(int argc, char *argv[], bool output_orders) {
 
     Engine eng;
     eng.idx = idx;
+    if (devices.size() > 1) {
+        rc = fmsi_gpu_pool_create(idx, devices.data(), (int)devices.size(), &eng.pool);
+        if (rc != FMSI_GPU_OK) {
+            std::cerr << "ERROR: " << fmsi_gpu_last_error() << std::endl;
+            return 1;
+        }
+    }
     eng.k = k;
     eng.streaming = has_klcp;
     eng.orders = output_orders;
@@ -496,6 +525,7 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     }
     if (!batch.records.empty()) eng.run(batch);
     std::fflush(stdout);
+    fmsi_gpu_pool_free(eng.pool);
     fmsi_gpu_index_free(idx);
     return 0;
 }

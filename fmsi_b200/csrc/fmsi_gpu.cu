@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_index.cuh"
@@ -63,6 +64,7 @@ struct fmsi_gpu_index {
     HostIndex meta;  // vectors released after upload
     DevIndex dev{};
     void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr, *d_rows = nullptr;
+    size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
     uint64_t hbm_bytes = 0;
     bool wide = false;
     DictView dict{};
@@ -215,7 +217,8 @@ int build_table(fmsi_gpu_index *idx, u32 t) {
     idx->dev.table = full;
     idx->dev.t = t;
     idx->dev.tshift = WIDE ? 4 : 3;
-    idx->hbm_bytes += (1ull << (2 * t)) * sizeof(TableEntry<WIDE>);
+    idx->b_table = (1ull << (2 * t)) * sizeof(TableEntry<WIDE>);
+    idx->hbm_bytes += idx->b_table;
     return FMSI_GPU_OK;
 }
 
@@ -274,7 +277,9 @@ int build_dict(fmsi_gpu_index *idx, u32 t) {
     idx->dict.B = B;
     idx->dict.k = k;
     idx->dict.enabled = 1;
-    idx->hbm_bytes += total * sizeof(Bucket) + N * sizeof(u64);
+    idx->b_table = total * sizeof(Bucket);
+    idx->b_rows = N * sizeof(u64);
+    idx->hbm_bytes += idx->b_table + idx->b_rows;
     return FMSI_GPU_OK;
 }
 
@@ -293,6 +298,16 @@ int select_device(fmsi_gpu_index *idx) {
 int alloc_scratch(LaunchScratch &ls) {
     CU(cudaMalloc(&ls.ctr, 4 * sizeof(unsigned long long)));
     return FMSI_GPU_OK;
+}
+
+int alloc_slots(fmsi_gpu_index *idx) {
+    int rc;
+    for (int s = 0; s < kSlots; ++s) {
+        CU(cudaStreamCreateWithFlags(&idx->slots[s].stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&idx->slots[s].done, cudaEventDisableTiming));
+        if ((rc = alloc_scratch(idx->slots[s].ls))) return rc;
+    }
+    return alloc_scratch(idx->user);
 }
 
 // Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table or dictionary,
@@ -353,13 +368,7 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
         rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
     }
     if (rc) return rc;
-
-    for (int s = 0; s < kSlots; ++s) {
-        CU(cudaStreamCreateWithFlags(&idx->slots[s].stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&idx->slots[s].done, cudaEventDisableTiming));
-        if ((rc = alloc_scratch(idx->slots[s].ls))) return rc;
-    }
-    return alloc_scratch(idx->user);
+    return alloc_slots(idx);
 }
 
 int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
@@ -377,6 +386,9 @@ int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     CU(cudaMemcpy(idx->d_sb, h.sb_base.data(), h.sb_base.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice));
     idx->hbm_bytes = rb + ab + h.sb_base.size() * 8 + 32;
+    idx->b_rank = rb;
+    idx->b_aux = ab;
+    idx->b_sb = h.sb_base.size() * 8;
     std::vector<RankBlock>().swap(h.rank);
     std::vector<AuxBlock>().swap(h.aux);
     return finish_device_setup(idx, opts);
@@ -510,6 +522,9 @@ int fmsi_gpu_index_build(const char *ms, size_t n, int k, int with_klcp, int mem
         idx->d_rank = b.rank.p;
         idx->d_aux = b.aux.p;
         idx->hbm_bytes = (b.rank.n + b.aux.n) * 32 + 64;
+        idx->b_rank = b.rank.n * 32;
+        idx->b_aux = b.aux.n * 32;
+        idx->b_sb = 32;
         b.rank.p = nullptr;
         b.aux.p = nullptr;
         idx->plane_lo.swap(b.lo);
@@ -850,6 +865,197 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
         CU(cudaStreamSynchronize(st));
     }
     return FMSI_GPU_OK;
+}
+
+
+// ---------------------------------------------------------------------------------- multi-GPU pool
+}  // extern "C"
+
+struct fmsi_gpu_pool {
+    std::vector<fmsi_gpu_index *> members;  // members[0] is the caller's primary (not owned)
+};
+
+namespace {
+
+// Device-to-device copy of one array of the primary onto `dev` (NVLink peer copy when the driver
+// allows peer access, staged through the host by the driver otherwise).
+int replicate_array(void **dst, int dev, const void *src, int src_dev, size_t bytes) {
+    *dst = nullptr;
+    if (!src || !bytes) return FMSI_GPU_OK;
+    CU(cudaSetDevice(dev));
+    CU(cudaMalloc(dst, bytes));
+    if (dev == src_dev) CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyDeviceToDevice));
+    else CU(cudaMemcpyPeer(*dst, dev, src, src_dev, bytes));
+    return FMSI_GPU_OK;
+}
+
+int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
+    std::unique_ptr<fmsi_gpu_index> r(new fmsi_gpu_index());
+    r->device = dev;
+    int rc = select_device(r.get());
+    if (rc) return rc;
+    if (dev != src->device) {  // enable NVLink/PCIe peer access in both directions when available
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, src->device) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(FMSI_GPU_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    r->meta = src->meta;
+    r->wide = src->wide;
+    r->dev = src->dev;
+    r->dict = src->dict;
+    r->hbm_bytes = src->hbm_bytes;
+    r->b_rank = src->b_rank;
+    r->b_aux = src->b_aux;
+    r->b_table = src->b_table;
+    r->b_sb = src->b_sb;
+    r->b_rows = src->b_rows;
+    auto bail = [&](int code) {
+        fmsi_gpu_index_free(r.release());
+        return code;
+    };
+    if ((rc = replicate_array(&r->d_rank, dev, src->d_rank, src->device, src->b_rank)) ||
+        (rc = replicate_array(&r->d_aux, dev, src->d_aux, src->device, src->b_aux)) ||
+        (rc = replicate_array(&r->d_table, dev, src->d_table, src->device, src->b_table)) ||
+        (rc = replicate_array(&r->d_sb, dev, src->d_sb, src->device, src->b_sb)) ||
+        (rc = replicate_array(&r->d_counts, dev, src->d_counts, src->device, 32)) ||
+        (rc = replicate_array(&r->d_rows, dev, src->d_rows, src->device, src->b_rows)))
+        return bail(rc);
+    r->dev.rank = reinterpret_cast<const RankBlock *>(r->d_rank);
+    r->dev.aux = reinterpret_cast<const AuxBlock *>(r->d_aux);
+    r->dev.table = r->d_table;
+    r->dev.sb_base = reinterpret_cast<const u64 *>(r->d_sb);
+    r->dict.rows = reinterpret_cast<const u64 *>(r->d_rows);
+    if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(FMSI_GPU_ERR_CUDA, "cudaSetDevice"));
+    if ((rc = alloc_slots(r.get()))) return bail(rc);
+    *out = r.release();
+    return FMSI_GPU_OK;
+}
+
+// Run fn(member, shard) on one host thread per member; first failure wins.
+template <typename Fn>
+int pool_run(fmsi_gpu_pool *pool, size_t n_shards, Fn fn) {
+    std::vector<int> rcs(n_shards, FMSI_GPU_OK);
+    std::vector<std::string> errs(n_shards);
+    std::vector<std::thread> th;
+    for (size_t s = 0; s < n_shards; ++s)
+        th.emplace_back([&, s] {
+            rcs[s] = fn(pool->members[s], s);
+            if (rcs[s]) errs[s] = fmsi_gpu_last_error();  // thread-local in the worker
+        });
+    for (auto &t : th) t.join();
+    for (size_t s = 0; s < n_shards; ++s)
+        if (rcs[s]) return fail(rcs[s], "pool member " + std::to_string(s) + ": " + errs[s]);
+    return FMSI_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fmsi_gpu_pool_create(fmsi_gpu_index *primary, const int *devices, int n_devices, fmsi_gpu_pool **out) {
+    if (!primary || !devices || n_devices < 1 || !out) return fail(FMSI_GPU_ERR_ARG, "bad pool arguments");
+    *out = nullptr;
+    std::unique_ptr<fmsi_gpu_pool> pool(new fmsi_gpu_pool());
+    bool primary_used = false;
+    for (int m = 0; m < n_devices; ++m) {
+        if (devices[m] == primary->device && !primary_used) {
+            pool->members.push_back(primary);
+            primary_used = true;
+            continue;
+        }
+        fmsi_gpu_index *r = nullptr;
+        int rc = replicate_index(primary, devices[m], &r);
+        if (rc) {
+            fmsi_gpu_pool_free(pool.release());
+            return rc;
+        }
+        pool->members.push_back(r);
+    }
+    if (!primary_used) {  // keep the invariant members[0] == primary by rotating it in front
+        pool->members.insert(pool->members.begin(), primary);
+    }
+    // the primary must sit at position 0 so that pool_free knows which member it does not own
+    for (size_t m = 1; m < pool->members.size(); ++m)
+        if (pool->members[m] == primary) std::swap(pool->members[0], pool->members[m]);
+    CU(cudaSetDevice(primary->device));
+    *out = pool.release();
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_pool_size(const fmsi_gpu_pool *pool) { return pool ? (int)pool->members.size() : 0; }
+
+int fmsi_gpu_pool_free(fmsi_gpu_pool *pool) {
+    if (!pool) return FMSI_GPU_OK;
+    for (size_t m = 1; m < pool->members.size(); ++m) fmsi_gpu_index_free(pool->members[m]);
+    delete pool;
+    return FMSI_GPU_OK;
+}
+
+int fmsi_gpu_pool_query_kmers(fmsi_gpu_pool *pool, int mode, int output, int strands, const uint64_t *kmers,
+                              size_t n, int k, void *results) {
+    if (!pool || pool->members.empty()) return fail(FMSI_GPU_ERR_ARG, "null pool");
+    if (n == 0) return FMSI_GPU_OK;
+    if (!kmers || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    if ((output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    const size_t W = pool->members.size(), rbytes = result_bytes(output, strands);
+    const size_t base = n / W, extra = n % W;  // contiguous ranges, sizes differing by at most one
+    std::vector<size_t> begin(W + 1, 0);
+    for (size_t s = 0; s < W; ++s) begin[s + 1] = begin[s] + base + (s < extra ? 1 : 0);
+    return pool_run(pool, W, [&](fmsi_gpu_index *m, size_t s) {
+        const size_t b = begin[s], cnt = begin[s + 1] - b;
+        if (!cnt) return (int)FMSI_GPU_OK;
+        return fmsi_gpu_query_kmers(m, mode, output, strands, kmers + b, cnt, k, (char *)results + b * rbytes, FMSI_GPU_MEM_HOST, nullptr);
+    });
+}
+
+int fmsi_gpu_pool_query_chunks(fmsi_gpu_pool *pool, int mode, int output, int strands, int streaming, const char *bases,
+                               size_t n_bases, const uint64_t *chunk_off, const uint32_t *chunk_len, size_t n_chunks,
+                               size_t n_results, int k, void *results) {
+    if (!pool || pool->members.empty()) return fail(FMSI_GPU_ERR_ARG, "null pool");
+    if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
+    if (!bases || !chunk_off || !chunk_len || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
+    if ((output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    // results of chunk c start at roff[c] = sum of (chunk_len - k + 1) over earlier chunks
+    std::vector<uint64_t> roff(n_chunks + 1, 0);
+    for (size_t c = 0; c < n_chunks; ++c) {
+        if (chunk_len[c] < (uint32_t)k || chunk_off[c] + chunk_len[c] > n_bases) return fail(FMSI_GPU_ERR_ARG, "chunk out of range or shorter than k");
+        roff[c + 1] = roff[c] + (chunk_len[c] - (uint32_t)k + 1);
+    }
+    if (roff[n_chunks] != n_results) return fail(FMSI_GPU_ERR_ARG, "n_results does not match the chunks");
+    const size_t W = pool->members.size(), rbytes = result_bytes(output, strands);
+    std::vector<size_t> cb(W + 1, 0);  // chunk ranges balanced by k-mer count; chunks are never split
+    for (size_t s = 1; s < W; ++s) {
+        const uint64_t target = n_results / W * s;
+        cb[s] = (size_t)(std::lower_bound(roff.begin(), roff.end(), target) - roff.begin());
+        if (cb[s] > n_chunks) cb[s] = n_chunks;
+        if (cb[s] < cb[s - 1]) cb[s] = cb[s - 1];
+    }
+    cb[W] = n_chunks;
+    return pool_run(pool, W, [&](fmsi_gpu_index *m, size_t s) {
+        const size_t b = cb[s], e = cb[s + 1];
+        if (b == e) return (int)FMSI_GPU_OK;
+        uint64_t lo = ~0ull, hi = 0;
+        for (size_t c = b; c < e; ++c) {
+            lo = std::min<uint64_t>(lo, chunk_off[c]);
+            hi = std::max<uint64_t>(hi, chunk_off[c] + chunk_len[c]);
+        }
+        std::vector<uint64_t> off(e - b), ro(e - b);
+        for (size_t c = b; c < e; ++c) {
+            off[c - b] = chunk_off[c] - lo;
+            ro[c - b] = roff[c] - roff[b];
+        }
+        return fmsi_gpu_query_chunks(m, mode, output, strands, streaming, bases + lo, (size_t)(hi - lo), off.data(), chunk_len + b,
+                                     ro.data(), e - b, (size_t)(roff[e] - roff[b]), k, (char *)results + roff[b] * rbytes,
+                                     FMSI_GPU_MEM_HOST, nullptr);
+    });
 }
 
 }  // extern "C"

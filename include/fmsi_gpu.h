@@ -150,6 +150,29 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
                           const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                           size_t n_results, int k, void *results, int mem, void *stream);
 
+/* ---- multi-GPU scheduler -------------------------------------------------------------------- */
+/* The query path shards by independent units (k-mers; chunks for -S) with a full index replica per
+ * GPU and no data-path collective (the reference is single-threaded: ms_query, src/main.cpp:238-375,
+ * answers records one after another). A pool holds `primary` plus one replica per further entry of
+ * devices[] — copied device to device (cudaMemcpyPeer: NVLink when peer access is available), so the
+ * index files are parsed and converted once. An ordinal may repeat (several replicas on one GPU).
+ * Calls take HOST buffers, split them into contiguous ranges (chunk ranges balanced by k-mer count,
+ * chunks never split), drive every member from its own host thread and return when all results are
+ * in `results`, in query order. fmsi_gpu_pool_free releases the replicas, not `primary`. */
+typedef struct fmsi_gpu_pool fmsi_gpu_pool;
+int fmsi_gpu_pool_create(fmsi_gpu_index *primary, const int *devices, int n_devices, fmsi_gpu_pool **out);
+int fmsi_gpu_pool_size(const fmsi_gpu_pool *pool);
+int fmsi_gpu_pool_free(fmsi_gpu_pool *pool);
+/* as fmsi_gpu_query_kmers with mem = HOST */
+int fmsi_gpu_pool_query_kmers(fmsi_gpu_pool *pool, int mode, int output, int strands, const uint64_t *kmers,
+                              size_t n, int k, void *results);
+/* as fmsi_gpu_query_chunks with mem = HOST and results back to back in chunk order
+ * (res_off[c] = sum over earlier chunks of chunk_len - k + 1) */
+int fmsi_gpu_pool_query_chunks(fmsi_gpu_pool *pool, int mode, int output, int strands, int streaming,
+                               const char *bases, size_t n_bases, const uint64_t *chunk_off,
+                               const uint32_t *chunk_len, size_t n_chunks, size_t n_results, int k,
+                               void *results);
+
 /* Number of kernel launches issued by this library on behalf of the calling process so far
  * (bench.py reports it as gpu_launches). */
 uint64_t fmsi_gpu_launch_count(void);

@@ -63,6 +63,17 @@ def test_cli_small_batches_stdin_gzip_and_k_flag(tmp_path):
     assert r.stdout == want
 
 
+def test_cli_multi_gpu_scheduler_is_byte_identical():
+    """$FMSI_GPU_DEVICES shards every batch over index replicas (repeated ordinals share one GPU)."""
+    for case, flags, exp in (("syn_k31_max", ["query", "-O", "-S"], "exp_query_OS.txt"), ("syn_k9_min", ["lookup"], "exp_lookup.txt"),
+                             ("syn_k31_min", ["query"], "exp_query.txt")):
+        d = os.path.join(GOLDEN, case)
+        want = open(os.path.join(d, exp), "rb").read()
+        for devs in ("0,0,0", "all"):
+            r = run_cli([*flags, "-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")], env={"FMSI_GPU_DEVICES": devs})
+            assert r.returncode == 0 and r.stdout == want, (case, devs, r.stderr[-300:])
+
+
 def test_cli_errors_match_reference_behaviour():
     d = os.path.join(GOLDEN, "syn_k31_noklcp")
     r = run_cli(["query", "-S", "-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")])

@@ -279,6 +279,39 @@ def test_chunks_streaming_and_single_match_oracle(case):
     oi.close()
 
 
+def test_multi_gpu_pool_matches_single_index():
+    """The scheduler (fmsi_gpu_pool_*): replicas made by device-to-device copy answer contiguous
+    shards from their own host threads; results must equal the single-index call, in query order.
+    With one GPU the replicas share it (repeated ordinals), with more they spread over the GPUs."""
+    d = os.path.join(GOLDEN, "syn_k31_max")
+    prefix = os.path.join(d, "ms.fa")
+    k = 31
+    gi = fg.Index.load(prefix, use_klcp=True)
+    ndev = fg.device_count()
+    devices = [0, 1 % ndev, 2 % ndev, 0]
+    pool = fg.Pool(gi, devices)
+    assert pool.size == 4
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    rng = np.random.default_rng(17)
+    for n in (0, 1, 3, 4, 5003):
+        kmers = _random_kmers(rng, ms_codes, k, n)[:n] if n else np.zeros(0, np.uint64)
+        for mode, out in ((fg.MODE_ALL, fg.OUT_PRESENCE), (fg.MODE_OR, fg.OUT_PRESENCE), (fg.MODE_OR, fg.OUT_ORDERS)):
+            for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+                assert np.array_equal(pool.query_kmers(kmers, k, mode, out, strands), gi.query_kmers(kmers, k, mode, out, strands))
+    reads = [r for r in synth.read_queries(ms_codes, 150, 57, 4)] + [ms_codes[:k].copy()]
+    for max_kmers in (64, 7):
+        bases, offs, lens = _chunks_of(reads, k, max_kmers)
+        for streaming in (False, True):
+            for out in (fg.OUT_PRESENCE, fg.OUT_ORDERS):
+                a = pool.query_chunks(bases, offs, lens, k, fg.MODE_ALL, out, fg.STRANDS_BOTH, streaming)
+                b = gi.query_chunks(bases, offs, lens, k, fg.MODE_ALL, out, fg.STRANDS_BOTH, streaming)
+                assert np.array_equal(a, b)
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Pool(gi, [ndev + 7])
+    pool.close()
+    gi.close()
+
+
 def test_error_behaviour():
     with pytest.raises(fg.FmsiGpuError) as e:
         fg.Index.load("/nonexistent/prefix")
