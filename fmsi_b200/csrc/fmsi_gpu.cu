@@ -15,6 +15,7 @@
 #include "device_index.cuh"
 #include "dict.cuh"
 #include "index_build.cuh"
+#include "index_convert.cuh"
 #include "index_layout.hpp"
 #include "query_kernels.cuh"
 #include "stream_kernels.cuh"
@@ -371,27 +372,96 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     return alloc_slots(idx);
 }
 
-int upload(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+// Raw index material (host words as read from the files, or packed from bit arrays) -> device layout
+// (index_convert.cuh) -> suffix table / dictionary, streams, scratch.
+struct RawIndex {
+    BitVec ac_gt, ac, gt, klcp, mask_plain;  // mask_plain used when has_rrr == false
+    RrrFile rrr;
+    bool has_rrr = false, has_klcp = false;
+    uint64_t counts[4] = {0, 0, 0, 0};
+    uint64_t dollar = 0;
+    int k = 0;
+};
+
+int convert_and_setup(fmsi_gpu_index *idx, const RawIndex &raw, const fmsi_gpu_options *opts) {
     int rc = select_device(idx);
     if (rc) return rc;
     HostIndex &h = idx->meta;
-    idx->wide = h.wide();
-    const size_t rb = h.rank.size() * sizeof(RankBlock), ab = h.aux.size() * sizeof(AuxBlock);
-    CU(cudaMalloc(&idx->d_rank, rb));
-    CU(cudaMalloc(&idx->d_aux, ab));
-    CU(cudaMalloc(&idx->d_sb, h.sb_base.size() * 8));
-    CU(cudaMalloc(&idx->d_counts, 4 * 8));
-    CU(cudaMemcpy(idx->d_rank, h.rank.data(), rb, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(idx->d_aux, h.aux.data(), ab, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(idx->d_sb, h.sb_base.data(), h.sb_base.size() * 8, cudaMemcpyHostToDevice));
+    h.n = raw.ac_gt.nbits;
+    h.k = raw.k;
+    h.dollar = raw.dollar;
+    for (int c = 0; c < 4; ++c) h.counts[c] = raw.counts[c];
+    const u64 N = h.n, nblk = (N >> 6) + 1;
+    uint64_t launches = 0;
+    try {
+        if (N == 0) throw std::runtime_error("empty index");
+        const u64 mask_bits = raw.has_rrr ? raw.rrr.size : raw.mask_plain.nbits;
+        if (mask_bits != N) throw std::runtime_error("mask length does not match the BWT length");
+        if (raw.has_klcp && raw.klcp.nbits != N) throw std::runtime_error("kLCP length does not match the BWT length");
+        if (raw.dollar >= N) throw std::runtime_error("dollar_position out of range");
+        h.has_klcp = raw.has_klcp;
+        DevArr<u64> d_acgt, d_ac, d_gt, d_klcp, d_mask;
+        upload_words(d_acgt, raw.ac_gt.w.data(), (N + 63) >> 6, nblk + 2);
+        upload_words(d_ac, raw.ac.w.data(), (raw.ac.nbits + 63) >> 6, ((raw.ac.nbits + 63) >> 6) + 2);
+        upload_words(d_gt, raw.gt.w.data(), (raw.gt.nbits + 63) >> 6, ((raw.gt.nbits + 63) >> 6) + 2);
+        if (raw.has_klcp) upload_words(d_klcp, raw.klcp.w.data(), (N + 63) >> 6, nblk + 2);
+        if (raw.has_rrr) rrr_decode_on_device(raw.rrr, nblk, d_mask, &launches);
+        else upload_words(d_mask, raw.mask_plain.w.data(), (N + 63) >> 6, nblk + 2);
+        ConvertedIndex cv;
+        convert_on_device(N, d_acgt, d_ac, raw.ac.nbits, d_gt, raw.gt.nbits, d_mask.p, raw.has_klcp ? d_klcp.p : nullptr, raw.counts,
+                          opts ? (unsigned)opts->sb_shift_log2 : 0u, cv, &launches);
+        BCU(cudaDeviceSynchronize());
+        g_launches.fetch_add(launches);
+        h.mask_ones = cv.mask_ones;
+        h.sb_shift = cv.sb_shift;
+        idx->wide = cv.sb_shift < 63;
+        idx->b_rank = cv.rank.n * sizeof(RankBlock);
+        idx->b_aux = cv.aux.n * sizeof(AuxBlock);
+        idx->b_sb = cv.nsb * 32;
+        idx->d_rank = cv.rank.p;
+        idx->d_aux = cv.aux.p;
+        idx->d_sb = cv.sb_base.p;
+        cv.rank.p = nullptr;
+        cv.aux.p = nullptr;
+        cv.sb_base.p = nullptr;
+    } catch (const std::exception &e) {
+        return fail(FMSI_GPU_ERR_IO, e.what());
+    }
+    CU(cudaMalloc(&idx->d_counts, 32));
     CU(cudaMemcpy(idx->d_counts, h.counts, 32, cudaMemcpyHostToDevice));
-    idx->hbm_bytes = rb + ab + h.sb_base.size() * 8 + 32;
-    idx->b_rank = rb;
-    idx->b_aux = ab;
-    idx->b_sb = h.sb_base.size() * 8;
-    std::vector<RankBlock>().swap(h.rank);
-    std::vector<AuxBlock>().swap(h.aux);
+    idx->hbm_bytes = idx->b_rank + idx->b_aux + idx->b_sb + 32;
     return finish_device_setup(idx, opts);
+}
+
+// Parse <prefix>.fmsi.{ac_gt,ac,gt,mask,klcp,misc} (formats: sdsl_io.hpp). A missing file is the
+// reference's "index not correctly loaded" (main.cpp:304-307).
+void read_raw_index_files(const std::string &prefix, bool use_klcp, RawIndex &raw) {
+    const std::string base = prefix + ".fmsi";
+    for (const char *ext : {".ac_gt", ".ac", ".gt", ".mask", ".misc"})
+        if (!file_exists(base + ext)) throw std::runtime_error("index not correctly loaded: missing " + base + ext);
+    {
+        ByteReader r(base + ".ac_gt");
+        r.read_bitvec(raw.ac_gt);
+    }
+    {
+        ByteReader r(base + ".ac");
+        r.read_bitvec(raw.ac);
+    }
+    {
+        ByteReader r(base + ".gt");
+        r.read_bitvec(raw.gt);
+    }
+    raw.rrr = read_rrr(base + ".mask");
+    raw.has_rrr = true;
+    raw.has_klcp = false;
+    if (use_klcp && file_exists(base + ".klcp")) {
+        ByteReader r(base + ".klcp");
+        r.read_bitvec(raw.klcp);
+        raw.has_klcp = raw.klcp.nbits > 0;
+    }
+    std::ifstream in(base + ".misc");
+    if (!(in >> raw.dollar >> raw.counts[0] >> raw.counts[1] >> raw.counts[2] >> raw.counts[3] >> raw.k))
+        throw std::runtime_error("malformed " + base + ".misc");
 }
 
 BitVec bits_to_vec(const uint8_t *bits, size_t n) {
@@ -444,15 +514,14 @@ int fmsi_gpu_index_load(const char *prefix, int use_klcp, int device, const fmsi
     *out = nullptr;
     std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
     idx->device = device;
+    RawIndex raw;
     try {
-        IndexFiles f = read_index_files(prefix, use_klcp != 0);
-        if (f.mask.nbits == 0) return fail(FMSI_GPU_ERR_IO, "index not correctly loaded (empty mask)");
-        idx->meta = build_host_index(f.ac_gt, f.ac, f.gt, f.mask, f.klcp_present ? &f.klcp : nullptr, f.counts,
-                                     f.dollar, f.k, opts ? (unsigned)opts->sb_shift_log2 : 0u);
+        read_raw_index_files(prefix, use_klcp != 0, raw);
+        if (raw.rrr.size == 0) return fail(FMSI_GPU_ERR_IO, "index not correctly loaded (empty mask)");
     } catch (const std::exception &e) {
         return fail(FMSI_GPU_ERR_IO, e.what());
     }
-    int rc = upload(idx.get(), opts);
+    int rc = convert_and_setup(idx.get(), raw, opts);
     if (rc) {
         fmsi_gpu_index_free(idx.release());
         return rc;
@@ -470,16 +539,17 @@ int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t
     *out = nullptr;
     std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
     idx->device = device;
-    try {
-        BitVec b_acgt = bits_to_vec(ac_gt, n_ac_gt), b_ac = bits_to_vec(ac, n_ac), b_gt = bits_to_vec(gt, n_gt),
-               b_mask = bits_to_vec(mask, n_mask), b_klcp;
-        if (klcp && n_klcp) b_klcp = bits_to_vec(klcp, n_klcp);
-        idx->meta = build_host_index(b_acgt, b_ac, b_gt, b_mask, (klcp && n_klcp) ? &b_klcp : nullptr, counts,
-                                     dollar_position, k, opts ? (unsigned)opts->sb_shift_log2 : 0u);
-    } catch (const std::exception &e) {
-        return fail(FMSI_GPU_ERR_IO, e.what());
-    }
-    int rc = upload(idx.get(), opts);
+    RawIndex raw;
+    raw.ac_gt = bits_to_vec(ac_gt, n_ac_gt);
+    raw.ac = bits_to_vec(ac, n_ac);
+    raw.gt = bits_to_vec(gt, n_gt);
+    raw.mask_plain = bits_to_vec(mask, n_mask);
+    raw.has_klcp = klcp && n_klcp;
+    if (raw.has_klcp) raw.klcp = bits_to_vec(klcp, n_klcp);
+    for (int c = 0; c < 4; ++c) raw.counts[c] = counts[c];
+    raw.dollar = dollar_position;
+    raw.k = k;
+    int rc = convert_and_setup(idx.get(), raw, opts);
     if (rc) {
         fmsi_gpu_index_free(idx.release());
         return rc;
