@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "fmsi_gpu_index_from_bits", "fmsi_gpu_index_build", "fmsi_gpu_index_save", "fmsi_gpu_index_free", "fmsi_gpu_index_get_info", "fmsi_gpu_rank",
     "fmsi_gpu_update_range", "fmsi_gpu_extend_range_with_klcp", "fmsi_gpu_get_range_with_pattern",
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
-    "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_free",
+    "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_member", "fmsi_gpu_pool_free",
     "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks",
 ]
 
@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
                                         C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_pool_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.fmsi_gpu_pool_size.argtypes = [vp]
+    L.fmsi_gpu_pool_member.argtypes = [vp, C.c_int]
+    L.fmsi_gpu_pool_member.restype = vp
     L.fmsi_gpu_pool_free.argtypes = [vp]
     L.fmsi_gpu_pool_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp]
     L.fmsi_gpu_pool_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, C.c_size_t,

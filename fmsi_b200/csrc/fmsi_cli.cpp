@@ -17,7 +17,13 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -130,6 +136,7 @@ class RecordReader {
         if (fp_) gzclose(fp_);
     }
     // Returns sequence length (>= 0), or a negative code: -1 EOF, -2 truncated quality.
+    // name and seq are overwritten (their capacity is reused from record to record).
     int64_t next(std::string &name, std::string &seq) {
         int c;
         if (last_char_ == 0) {
@@ -219,12 +226,13 @@ struct Op {  // one stretch of a record's output
     bool kmers;  // true: `count` consecutive k-mer results; false: `count` invalid-position fillers
 };
 struct Record {
-    std::string name;
+    size_t name_begin, name_len;  // into Batch::names
     size_t op_begin, op_end;
 };
 
 struct Batch {
     std::vector<Record> records;
+    std::string names;                  // record names back to back
     std::vector<Op> ops;
     std::string bases;                  // valid runs (>= k) back to back
     std::vector<uint64_t> chunk_off;    // GPU chunks
@@ -234,6 +242,7 @@ struct Batch {
     uint64_t n_results = 0;
     void clear() {
         records.clear();
+        names.clear();
         ops.clear();
         bases.clear();
         chunk_off.clear();
@@ -248,7 +257,9 @@ struct Batch {
 // reference cuts its chunks, and how many filler results each invalid character produces.
 void layout_record(Batch &b, const std::string &name, const std::string &s, int k, bool streaming) {
     Record rec;
-    rec.name = name;
+    rec.name_begin = b.names.size();
+    rec.name_len = std::strlen(name.c_str());  // C-string semantics of `cout << seq->name.s`
+    b.names.append(name.data(), rec.name_len);
     rec.op_begin = b.ops.size();
     int64_t sequence_length = (int64_t)s.size();
     int64_t max_chunk = 400;
@@ -291,82 +302,223 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
     b.records.push_back(std::move(rec));
 }
 
-struct Engine {
-    fmsi_gpu_index *idx = nullptr;
-    fmsi_gpu_pool *pool = nullptr;  // set when $FMSI_GPU_DEVICES names more than one replica
+// ---------------------------------------------------------------------------------------------
+// Host pipeline. The reference handles one record at a time on one thread (main.cpp:328-373); here
+//   reader (main thread)  : kseq-compatible parsing + layout into batches
+//   workers (W threads)   : GPU query of a batch on a free index replica; later its text formatting
+//   sequencer (1 thread)  : strand-predictor replay, strictly in batch order (the predictor's state
+//                           runs through every k-mer of the run) — skipped in lazy mode
+//   writer (1 thread)     : stdout, in batch order
+// With $FMSI_GPU_DEVICES the replicas live on several GPUs and batches go to whichever is free.
+struct Job {
+    uint64_t seq = 0;
+    Batch b;
+    std::vector<uint8_t> raw8, fin8;
+    std::vector<int64_t> raw64, fin64;
+    std::string out;
+};
+
+struct Config {
     int k = 0;
     bool streaming = false, orders = false, lazy = false;
     fmsi::QueryMode mode = fmsi::QueryMode::Or;
-    fmsi::StrandPredictor predictor;
-    std::vector<uint8_t> raw8;
-    std::vector<int64_t> raw64, fin64;
-    std::vector<uint8_t> fin8;
-    std::string out;
+};
 
-    void check(int rc) {
-        if (rc != FMSI_GPU_OK) {
-            std::cerr << "ERROR: GPU query failed: " << fmsi_gpu_last_error() << std::endl;
-            std::exit(1);
+class Pipeline {
+  public:
+    Pipeline(const Config &cfg, std::vector<fmsi_gpu_index *> members, int workers)
+        : cfg_(cfg), members_(std::move(members)), member_busy_(members_.size(), false) {
+        max_inflight_ = (size_t)(2 * workers + 2);
+        for (int w = 0; w < workers; ++w) threads_.emplace_back([this] { worker(); });
+        threads_.emplace_back([this] { sequencer(); });
+        threads_.emplace_back([this] { writer(); });
+    }
+    // reader side: blocks while too many batches are in flight
+    void submit(Job *job) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return inflight_ < max_inflight_ || failed_; });
+        job->seq = submitted_++;
+        ++inflight_;
+        tasks_.push_back({job, false});
+        cv_.notify_all();
+    }
+    bool finish() {
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            closed_ = true;
+            cv_.notify_all();
+        }
+        for (auto &t : threads_) t.join();
+        return !failed_;
+    }
+
+  private:
+    struct Task {
+        Job *job;
+        bool format;
+    };
+    void fail(const std::string &msg) {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!failed_) std::cerr << "ERROR: GPU query failed: " << msg << std::endl;
+        failed_ = true;
+        cv_.notify_all();
+    }
+    void worker() {
+        for (;;) {
+            Task t;
+            int member = -1;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                for (;;) {
+                    if (failed_) return;
+                    // formatting first (drains memory), then queries when a replica is free
+                    auto it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return x.format; });
+                    if (it == tasks_.end()) {
+                        member = free_member();
+                        if (member >= 0) it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return !x.format; });
+                    }
+                    if (it != tasks_.end()) {
+                        t = *it;
+                        tasks_.erase(it);
+                        if (!t.format) member_busy_[member] = true;
+                        break;
+                    }
+                    if (closed_ && written_ == submitted_) return;
+                    cv_.wait(lk);
+                }
+            }
+            if (t.format) {
+                format(*t.job);
+                std::unique_lock<std::mutex> lk(mu_);
+                formatted_[t.job->seq] = t.job;
+                cv_.notify_all();
+            } else {
+                const bool ok = query(*t.job, members_[member]);
+                std::unique_lock<std::mutex> lk(mu_);
+                member_busy_[member] = false;
+                if (ok) queried_[t.job->seq] = t.job;
+                cv_.notify_all();
+            }
+        }
+    }
+    int free_member() const {
+        for (size_t m = 0; m < member_busy_.size(); ++m)
+            if (!member_busy_[m]) return (int)m;
+        return -1;
+    }
+    void sequencer() {
+        uint64_t next = 0;
+        for (;;) {
+            Job *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return failed_ || queried_.count(next) || (closed_ && next == submitted_); });
+                if (failed_ || !queried_.count(next)) return;
+                job = queried_[next];
+                queried_.erase(next);
+            }
+            if (!cfg_.lazy) replay(*job);
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                tasks_.push_front({job, true});
+                cv_.notify_all();
+            }
+            ++next;
+        }
+    }
+    void writer() {
+        uint64_t next = 0;
+        for (;;) {
+            Job *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return failed_ || formatted_.count(next) || (closed_ && next == submitted_); });
+                if (failed_ || !formatted_.count(next)) return;
+                job = formatted_[next];
+                formatted_.erase(next);
+            }
+            if (!job->out.empty()) std::fwrite(job->out.data(), 1, job->out.size(), stdout);
+            delete job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                --inflight_;
+                ++written_;
+                cv_.notify_all();
+            }
+            ++next;
         }
     }
 
-    void run(Batch &b) {
+    bool query(Job &j, fmsi_gpu_index *idx) {
+        Batch &b = j.b;
         const uint64_t n = b.n_results;
-        const int gmode = mode == fmsi::QueryMode::All ? FMSI_GPU_MODE_ALL : FMSI_GPU_MODE_OR;
-        const int gout = orders ? FMSI_GPU_OUT_ORDERS : FMSI_GPU_OUT_PRESENCE;
-        const int gstr = lazy ? FMSI_GPU_STRANDS_LAZY : FMSI_GPU_STRANDS_BOTH;
+        const int gmode = cfg_.mode == fmsi::QueryMode::All ? FMSI_GPU_MODE_ALL : FMSI_GPU_MODE_OR;
+        const int gout = cfg_.orders ? FMSI_GPU_OUT_ORDERS : FMSI_GPU_OUT_PRESENCE;
+        const int gstr = cfg_.lazy ? FMSI_GPU_STRANDS_LAZY : FMSI_GPU_STRANDS_BOTH;
         void *raw = nullptr;
-        if (orders) {
-            raw64.resize(n * (lazy ? 1 : 2));
-            raw = raw64.data();
+        if (cfg_.orders) {
+            j.raw64.resize(n * (cfg_.lazy ? 1 : 2));
+            raw = j.raw64.data();
         } else {
-            raw8.resize(n);
-            raw = raw8.data();
+            j.raw8.resize(n);
+            raw = j.raw8.data();
         }
-        if (n && pool)
-            check(fmsi_gpu_pool_query_chunks(pool, gmode, gout, gstr, streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
-                                             b.chunk_len.data(), b.chunk_off.size(), n, k, raw));
-        else if (n)
-            check(fmsi_gpu_query_chunks(idx, gmode, gout, gstr, streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
-                                        b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, k, raw, FMSI_GPU_MEM_HOST, nullptr));
-        // ---- final values in query order
-        const uint8_t *p8 = nullptr;
-        const int64_t *p64 = nullptr;
-        if (lazy) {
-            p8 = raw8.data();
-            p64 = raw64.data();
-        } else {
-            if (orders) fin64.resize(n);
-            else fin8.resize(n);
-            auto f_of = [&](uint64_t q) -> int64_t { return orders ? raw64[2 * q] : (int64_t)(raw8[q] & 3) - 1; };
-            auto r_of = [&](uint64_t q) -> int64_t { return orders ? raw64[2 * q + 1] : (int64_t)((raw8[q] >> 2) & 3) - 1; };
-            uint64_t q0 = 0;
-            for (uint32_t m : b.ref_chunks) {
-                if (streaming) {
-                    fmsi::replay_streaming_chunk(
-                        predictor, mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
-                        [&](size_t q, int64_t v) {
-                            if (orders) fin64[q0 + q] = v;
-                            else fin8[q0 + q] = v == 1;
-                        });
-                } else {
-                    for (uint32_t q = 0; q < m; ++q) {
-                        const int64_t v = fmsi::replay_single(predictor, mode, orders, f_of(q0 + q), r_of(q0 + q));
-                        if (orders) fin64[q0 + q] = v;
-                        else fin8[q0 + q] = v == 1;
-                    }
-                }
-                q0 += m;
+        if (n) {
+            const int rc = fmsi_gpu_query_chunks(idx, gmode, gout, gstr, cfg_.streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
+                                                 b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, cfg_.k, raw, FMSI_GPU_MEM_HOST, nullptr);
+            if (rc != FMSI_GPU_OK) {
+                fail(fmsi_gpu_last_error());
+                return false;
             }
-            p8 = fin8.data();
-            p64 = fin64.data();
         }
-        // ---- text (main.cpp:333, :341-342, :358-372 and fms_index.h:242-253 / :301-309)
+        std::string().swap(b.bases);  // no longer needed: free early
+        return true;
+    }
+
+    // final values in query order from the both-strand results (exact mode)
+    void replay(Job &j) {
+        Batch &b = j.b;
+        const uint64_t n = b.n_results;
+        const bool orders = cfg_.orders;
+        if (orders) j.fin64.resize(n);
+        else j.fin8.resize(n);
+        const int64_t *r64 = j.raw64.data();
+        const uint8_t *r8 = j.raw8.data();
+        auto f_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q] : (int64_t)(r8[q] & 3) - 1; };
+        auto r_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q + 1] : (int64_t)((r8[q] >> 2) & 3) - 1; };
+        uint64_t q0 = 0;
+        for (uint32_t m : b.ref_chunks) {
+            if (cfg_.streaming) {
+                fmsi::replay_streaming_chunk(
+                    predictor_, cfg_.mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
+                    [&](size_t q, int64_t v) {
+                        if (orders) j.fin64[q0 + q] = v;
+                        else j.fin8[q0 + q] = v == 1;
+                    });
+            } else {
+                for (uint32_t q = 0; q < m; ++q) {
+                    const int64_t v = fmsi::replay_single(predictor_, cfg_.mode, orders, f_of(q0 + q), r_of(q0 + q));
+                    if (orders) j.fin64[q0 + q] = v;
+                    else j.fin8[q0 + q] = v == 1;
+                }
+            }
+            q0 += m;
+        }
+    }
+
+    // text (main.cpp:333, :341-342, :358-372 and fms_index.h:242-253 / :301-309)
+    void format(Job &j) {
+        Batch &b = j.b;
+        const bool orders = cfg_.orders;
+        const uint8_t *p8 = cfg_.lazy ? j.raw8.data() : j.fin8.data();
+        const int64_t *p64 = cfg_.lazy ? j.raw64.data() : j.fin64.data();
+        std::string &out = j.out;
         out.clear();
+        out.reserve(b.names.size() + 2 * b.records.size() + (orders ? 8 : 1) * (size_t)b.n_results + 64);
         uint64_t q = 0;
         char num[24];
         for (const Record &rec : b.records) {
-            out.append(rec.name.c_str());  // C-string semantics of `cout << seq->name.s`
+            out.append(b.names.data() + rec.name_begin, rec.name_len);
             out.push_back('\t');
             bool comma = false;
             for (size_t o = rec.op_begin; o < rec.op_end; ++o) {
@@ -385,7 +537,7 @@ struct Engine {
                         if (comma) out.push_back(',');
                         comma = true;
                         if (op.kmers) {
-                            const int len = std::snprintf(num, sizeof num, "%lld", (long long)p64[q + t]);
+                            const int len = fast_itoa(p64[q + t], num);
                             out.append(num, (size_t)len);
                         } else {
                             out.append("-1");
@@ -396,8 +548,36 @@ struct Engine {
             }
             out.push_back('\n');
         }
-        if (!out.empty()) std::fwrite(out.data(), 1, out.size(), stdout);
     }
+    static int fast_itoa(int64_t v, char *buf) {
+        if (v < 0) {  // only -1 occurs
+            buf[0] = '-';
+            buf[1] = '1';
+            return 2;
+        }
+        char tmp[24];
+        int n = 0;
+        uint64_t u = (uint64_t)v;
+        do {
+            tmp[n++] = (char)('0' + u % 10);
+            u /= 10;
+        } while (u);
+        for (int t = 0; t < n; ++t) buf[t] = tmp[n - 1 - t];
+        return n;
+    }
+
+    Config cfg_;
+    std::vector<fmsi_gpu_index *> members_;
+    std::vector<bool> member_busy_;
+    fmsi::StrandPredictor predictor_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Task> tasks_;
+    std::map<uint64_t, Job *> queried_, formatted_;
+    std::vector<std::thread> threads_;
+    size_t max_inflight_ = 4, inflight_ = 0;
+    uint64_t submitted_ = 0, written_ = 0;
+    bool closed_ = false, failed_ = false;
 };
 
 int ms_query(int argc, char *argv[], bool output_orders) {
@@ -468,7 +648,16 @@ int ms_query(int argc, char *argv[], bool output_orders) {
         if (!devices.empty()) device = devices[0];
     }
     fmsi_gpu_index *idx = nullptr;
-    int rc = fmsi_gpu_index_load(fn.c_str(), has_klcp ? 1 : 0, device, nullptr, &idx);
+    // The dictionary tier costs ~2 s of build time at human scale and pays off only beyond ~10^10
+    // k-mers per run, far above what FASTA parsing can feed: off unless $FMSI_GPU_DICT=1.
+    const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    fmsi_gpu_options opts;
+    std::memset(&opts, 0, sizeof opts);
+    opts.prefix_t = -1;
+    opts.dict = 0;
+    int rc = fmsi_gpu_index_load(fn.c_str(), has_klcp ? 1 : 0, device, &opts, &idx);
     if (rc == FMSI_GPU_ERR_IO) {
         std::cerr << "ERROR: index not correctly loaded. Ensure that you correctly call `fmsi index` before." << std::endl;
         return usage_query(output_orders);
@@ -493,41 +682,58 @@ int ms_query(int argc, char *argv[], bool output_orders) {
         return 1;
     }
 
-    Engine eng;
-    eng.idx = idx;
+    fmsi_gpu_pool *pool = nullptr;
+    std::vector<fmsi_gpu_index *> members{idx};
     if (devices.size() > 1) {
-        rc = fmsi_gpu_pool_create(idx, devices.data(), (int)devices.size(), &eng.pool);
+        rc = fmsi_gpu_pool_create(idx, devices.data(), (int)devices.size(), &pool);
         if (rc != FMSI_GPU_OK) {
             std::cerr << "ERROR: " << fmsi_gpu_last_error() << std::endl;
             return 1;
         }
+        members.clear();
+        for (int m = 0; m < fmsi_gpu_pool_size(pool); ++m) members.push_back(fmsi_gpu_pool_member(pool, m));
     }
-    eng.k = k;
-    eng.streaming = has_klcp;
-    eng.orders = output_orders;
-    eng.mode = f_name == "all" ? fmsi::QueryMode::All : fmsi::QueryMode::Or;
-    if (const char *e = std::getenv("FMSI_GPU_STRANDS")) eng.lazy = std::string(e) == "lazy";
+    Config cfg;
+    cfg.k = k;
+    cfg.streaming = has_klcp;
+    cfg.orders = output_orders;
+    cfg.mode = f_name == "all" ? fmsi::QueryMode::All : fmsi::QueryMode::Or;
+    if (const char *e = std::getenv("FMSI_GPU_STRANDS")) cfg.lazy = std::string(e) == "lazy";
+    int workers = (int)std::min<unsigned>(8, std::max(2u, std::thread::hardware_concurrency() / 2));
+    if (const char *e = std::getenv("FMSI_GPU_THREADS")) workers = std::max(1, atoi(e));
+    workers = std::max<int>(workers, (int)members.size());
 
-    RecordReader reader(query_fn);
-    Batch batch;
-    std::string name, seq;
-    size_t batch_bases = 64u << 20;
-    if (const char *e = std::getenv("FMSI_GPU_BATCH_BASES")) batch_bases = (size_t)atoll(e);
-    size_t pending = 0;
-    while (reader.next(name, seq) >= 0) {
-        layout_record(batch, name, seq, k, eng.streaming);
-        pending += seq.size() + 1;
-        if (pending >= batch_bases) {
-            eng.run(batch);
-            batch.clear();
-            pending = 0;
+    if (timing) std::cerr << "[fmsi timing] index load + replicas: " << since(t_start) << " s" << std::endl;
+    const auto t_query = std::chrono::steady_clock::now();
+    bool ok;
+    {
+        RecordReader reader(query_fn);  // throws std::invalid_argument when the file cannot be opened (as the reference)
+        Pipeline pipe(cfg, members, workers);
+        std::string name, seq;
+        size_t batch_bases = 16u << 20;
+        if (const char *e = std::getenv("FMSI_GPU_BATCH_BASES")) batch_bases = (size_t)atoll(e);
+        size_t pending = 0;
+        Job *job = new Job();
+        while (reader.next(name, seq) >= 0) {
+            layout_record(job->b, name, seq, k, cfg.streaming);
+            pending += seq.size() + 1;
+            if (pending >= batch_bases) {
+                pipe.submit(job);
+                job = new Job();
+                pending = 0;
+            }
         }
+        if (!job->b.records.empty()) pipe.submit(job);
+        else delete job;
+        if (timing) std::cerr << "[fmsi timing] reader done: " << since(t_query) << " s" << std::endl;
+        ok = pipe.finish();
+        if (timing) std::cerr << "[fmsi timing] pipeline drained: " << since(t_query) << " s" << std::endl;
     }
-    if (!batch.records.empty()) eng.run(batch);
     std::fflush(stdout);
-    fmsi_gpu_pool_free(eng.pool);
+    fmsi_gpu_pool_free(pool);
     fmsi_gpu_index_free(idx);
-    return 0;
+    if (timing) std::cerr << "[fmsi timing] total: " << since(t_start) << " s" << std::endl;
+    return ok ? 0 : 1;
 }
 
 }  // namespace

@@ -1057,6 +1057,11 @@ int fmsi_gpu_pool_create(fmsi_gpu_index *primary, const int *devices, int n_devi
 
 int fmsi_gpu_pool_size(const fmsi_gpu_pool *pool) { return pool ? (int)pool->members.size() : 0; }
 
+fmsi_gpu_index *fmsi_gpu_pool_member(fmsi_gpu_pool *pool, int m) {
+    if (!pool || m < 0 || (size_t)m >= pool->members.size()) return nullptr;
+    return pool->members[(size_t)m];
+}
+
 int fmsi_gpu_pool_free(fmsi_gpu_pool *pool) {
     if (!pool) return FMSI_GPU_OK;
     for (size_t m = 1; m < pool->members.size(); ++m) fmsi_gpu_index_free(pool->members[m]);

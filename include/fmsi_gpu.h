@@ -162,6 +162,8 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
 typedef struct fmsi_gpu_pool fmsi_gpu_pool;
 int fmsi_gpu_pool_create(fmsi_gpu_index *primary, const int *devices, int n_devices, fmsi_gpu_pool **out);
 int fmsi_gpu_pool_size(const fmsi_gpu_pool *pool);
+/* member m (0 = primary) for callers that schedule whole batches themselves; owned by the pool */
+fmsi_gpu_index *fmsi_gpu_pool_member(fmsi_gpu_pool *pool, int m);
 int fmsi_gpu_pool_free(fmsi_gpu_pool *pool);
 /* as fmsi_gpu_query_kmers with mem = HOST */
 int fmsi_gpu_pool_query_kmers(fmsi_gpu_pool *pool, int mode, int output, int strands, const uint64_t *kmers,

@@ -4,6 +4,7 @@ for every command/flag combination, including the cases whose output depends on 
 stateful strand predictor."""
 import gzip
 import json
+from concurrent.futures import ThreadPoolExecutor
 import os
 import subprocess
 
@@ -27,12 +28,18 @@ def run_cli(args, env=None, stdin=None):
     return subprocess.run([CLI] + args, capture_output=True, env=e, input=stdin)
 
 
+def run_many(arg_lists, env=None):
+    """Several CLI processes at once: creating a CUDA context costs 1-3 s per process on the box."""
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        return list(ex.map(lambda a: run_cli(a, env=env), arg_lists))
+
+
 @pytest.mark.parametrize("case", golden_cases())
 def test_cli_matches_reference_outputs(case):
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
-    for cmd in meta["cmds"]:
-        r = run_cli(ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")])
+    runs = run_many([ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")] for cmd in meta["cmds"]])
+    for cmd, r in zip(meta["cmds"], runs):
         assert r.returncode == 0, r.stderr.decode()
         want = open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read()
         assert r.stdout == want, f"{case}/{cmd}"
@@ -41,8 +48,9 @@ def test_cli_matches_reference_outputs(case):
 @pytest.mark.parametrize("case", sorted(LAZY_EXACT))
 def test_cli_lazy_mode_where_order_independent(case):
     d = os.path.join(GOLDEN, case)
-    for cmd in LAZY_EXACT[case]:
-        r = run_cli(ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")], env={"FMSI_GPU_STRANDS": "lazy"})
+    runs = run_many([ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")] for cmd in LAZY_EXACT[case]],
+                    env={"FMSI_GPU_STRANDS": "lazy"})
+    for cmd, r in zip(LAZY_EXACT[case], runs):
         assert r.returncode == 0, r.stderr.decode()
         assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}"
 
