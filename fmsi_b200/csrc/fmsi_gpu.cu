@@ -232,10 +232,11 @@ int build_dict(fmsi_gpu_index *idx, u32 t) {
     u32 *psi = nullptr;
     u64 *rows = nullptr;
     CU(cudaMalloc(&psi, N * sizeof(u32)));
-    if (cudaMalloc(&rows, N * sizeof(u64)) != cudaSuccess) {
+    if (cudaMalloc(&rows, (N + 8) * sizeof(u64)) != cudaSuccess) {  // + one sector: ROWS reads whole sectors
         cudaFree(psi);
         return fail(FMSI_GPU_ERR_NOMEM, "dictionary rows: out of device memory");
     }
+    cudaMemset(rows + N, 0, 8 * sizeof(u64));
     psi_scatter_kernel<<<blocks_for(N), 256>>>(d, psi);
     rows_walk_kernel<<<blocks_for(N), 256>>>(d, psi, (u32)h.counts[1], (u32)h.counts[2], (u32)h.counts[3], t, B, rows);
     rows_invalidate_kernel<<<1, 32>>>(d, k, rows);
@@ -279,7 +280,7 @@ int build_dict(fmsi_gpu_index *idx, u32 t) {
     idx->dict.k = k;
     idx->dict.enabled = 1;
     idx->b_table = total * sizeof(Bucket);
-    idx->b_rows = N * sizeof(u64);
+    idx->b_rows = (N + 8) * sizeof(u64);
     idx->hbm_bytes += idx->b_table + idx->b_rows;
     return FMSI_GPU_OK;
 }
@@ -883,10 +884,14 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
     void *d_results = results;
     int rc;
     // scratch: [packed bases | (host mode) bases, offsets, lens, res_off | packed k-mers (non-streaming)]
+    // Per-k-mer strand values do not depend on how they are computed (kLCP interval reuse is only a
+    // shortcut), so when the dictionary tier is resident streamed chunks take it too: ~2 requests per
+    // k-mer instead of an aux probe + an LF-step per k-mer and strand (profiles/r01d_modes_*.json).
+    const bool via_kmers = !streaming || (idx->dict.enabled && (u32)k == idx->dict.k && d.t && !idx->wide && n_results < (1ull << 32));
     const size_t n_words = (n_bases + 31) / 32 + 4;
     size_t aux_need = n_words * 8;
     const size_t kmers_off = aux_need;
-    if (!streaming) aux_need += n_results * 8;
+    if (via_kmers) aux_need += n_results * 8;
     if (on_host) {
         CU(cudaEventSynchronize(s.done));
         if (streaming) {
@@ -917,7 +922,7 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
 
-    if (!streaming) {
+    if (via_kmers) {
         u64 *d_kmers = (u64 *)((char *)s.d_aux + kmers_off);
         extract_kmers_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
         CU(cudaGetLastError());
