@@ -7,12 +7,12 @@ functions (load_index, query_kmers, rank, update_range, ...). There is no CPU fa
 works without a GPU, any call needs the library and a device.
 """
 from .api import (  # noqa: F401
-    FmsiGpuError, Index, Pool, load_index, lib, lib_path, MODE_OR, MODE_ALL, OUT_PRESENCE, OUT_ORDERS,
+    FmsiGpuError, Function, Index, Pool, load_index, lib, lib_path, MODE_OR, MODE_ALL, OUT_PRESENCE, OUT_ORDERS,
     STRANDS_LAZY, STRANDS_BOTH, MEM_HOST, MEM_DEVICE, EXPORTED_SYMBOLS, launch_count, device_count,
 )
 
 __all__ = [
-    "FmsiGpuError", "Index", "Pool", "load_index", "lib", "lib_path", "MODE_OR", "MODE_ALL", "OUT_PRESENCE",
+    "FmsiGpuError", "Function", "Index", "Pool", "load_index", "lib", "lib_path", "MODE_OR", "MODE_ALL", "OUT_PRESENCE",
     "OUT_ORDERS", "STRANDS_LAZY", "STRANDS_BOTH", "MEM_HOST", "MEM_DEVICE", "EXPORTED_SYMBOLS",
     "launch_count", "device_count",
 ]

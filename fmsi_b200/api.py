@@ -25,8 +25,9 @@ EXPORTED_SYMBOLS = [
     "fmsi_gpu_update_range", "fmsi_gpu_extend_range_with_klcp", "fmsi_gpu_get_range_with_pattern",
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
     "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_member", "fmsi_gpu_pool_free",
-    "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks",
+    "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks", "fmsi_gpu_query_kmers_general", "fmsi_gpu_query_chunks_general",
 ]
+F_OR, F_AND, F_XOR, F_RANGE = 0, 1, 2, 3
 
 
 class FmsiGpuError(RuntimeError):
@@ -38,6 +39,18 @@ class FmsiGpuError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("prefix_t", C.c_int32), ("sb_shift_log2", C.c_int32), ("dict", C.c_int32), ("reserved32", C.c_int32),
                 ("reserved", C.c_int64 * 5)]
+
+
+class Function(C.Structure):
+    """Demasking function of the f-MS framework (reference src/functions.h)."""
+    _fields_ = [("kind", C.c_int32), ("r", C.c_int32), ("s", C.c_int32), ("reserved", C.c_int32)]
+
+    @staticmethod
+    def parse(name: str) -> "Function":
+        if name in ("or", "and", "xor"):
+            return Function(kind={"or": F_OR, "and": F_AND, "xor": F_XOR}[name])
+        r, s = name.split("-")
+        return Function(kind=F_RANGE, r=int(r), s=int(s))
 
 
 class IndexInfo(C.Structure):
@@ -87,6 +100,9 @@ def lib() -> C.CDLL:
     L.fmsi_gpu_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp,
                                         C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    L.fmsi_gpu_query_kmers_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    L.fmsi_gpu_query_chunks_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int,
+                                                vp, C.c_int, vp]
     L.fmsi_gpu_pool_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.fmsi_gpu_pool_size.argtypes = [vp]
     L.fmsi_gpu_pool_member.argtypes = [vp, C.c_int]
@@ -259,6 +275,15 @@ class Index:
         out = np.empty(shape, dtype=dt)
         _check(lib().fmsi_gpu_query_kmers(self._h, mode, output, strands, kmers.ctypes.data, kmers.size, k,
                                          out.ctypes.data, MEM_HOST, None))
+        return out
+
+    def query_kmers_general(self, kmers, f: "Function | str", k: int | None = None) -> np.ndarray:
+        """query_kmers<general>: f(#ON occurrences, #occurrences) over both strands; uint8 0/1."""
+        kmers = _u64(kmers)
+        k = self.k if k is None else k
+        fn = Function.parse(f) if isinstance(f, str) else f
+        out = np.empty(kmers.size, dtype=np.uint8)
+        _check(lib().fmsi_gpu_query_kmers_general(self._h, C.byref(fn), kmers.ctypes.data, kmers.size, k, out.ctypes.data, MEM_HOST, None))
         return out
 
     def query_kmers_ptr(self, kmers_ptr: int, n: int, out_ptr: int, k: int | None = None, mode: int = MODE_OR,

@@ -321,6 +321,8 @@ struct Job {
 struct Config {
     int k = 0;
     bool streaming = false, orders = false, lazy = false;
+    bool general = false;  // -f and|xor|INT-INT: counts over both strands, no predictor (fms_index.h:317-327)
+    fmsi_gpu_function f{};
     fmsi::QueryMode mode = fmsi::QueryMode::Or;
 };
 
@@ -463,7 +465,14 @@ class Pipeline {
             j.raw8.resize(n);
             raw = j.raw8.data();
         }
-        if (n) {
+        if (n && cfg_.general) {
+            const int rc = fmsi_gpu_query_chunks_general(idx, &cfg_.f, b.bases.data(), b.bases.size(), b.chunk_off.data(), b.chunk_len.data(),
+                                                         b.res_off.data(), b.chunk_off.size(), n, cfg_.k, j.raw8.data(), FMSI_GPU_MEM_HOST, nullptr);
+            if (rc != FMSI_GPU_OK) {
+                fail(fmsi_gpu_last_error());
+                return false;
+            }
+        } else if (n) {
             const int rc = fmsi_gpu_query_chunks(idx, gmode, gout, gstr, cfg_.streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
                                                  b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, cfg_.k, raw, FMSI_GPU_MEM_HOST, nullptr);
             if (rc != FMSI_GPU_OK) {
@@ -625,7 +634,7 @@ int ms_query(int argc, char *argv[], bool output_orders) {
         std::cerr << "ERROR: FMSI as Minimum Perfect Hash Function is not allowed with f-masked superstrings in the current version." << std::endl;
         return usage_query(output_orders);
     }
-    if (f_name != "or" && f_name != "all") return -2;  // general f-MS mode: caller forwards to the reference
+    const bool general = f_name != "or" && f_name != "all";
 
     // $FMSI_GPU_DEVICES = "all" | "0,1,2,..." : shard every batch over replicas on these GPUs
     // (multi-GPU scheduler of the C-ABI); otherwise $FMSI_GPU_DEVICE (default 0) alone.
@@ -699,6 +708,19 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     cfg.orders = output_orders;
     cfg.mode = f_name == "all" ? fmsi::QueryMode::All : fmsi::QueryMode::Or;
     if (const char *e = std::getenv("FMSI_GPU_STRANDS")) cfg.lazy = std::string(e) == "lazy";
+    if (general) {  // mask_function(), src/functions.h:23-57
+        cfg.general = true;
+        cfg.lazy = true;        // one value per k-mer, nothing to replay
+        cfg.streaming = false;  // query_kmers() ignores kLCP in general mode (fms_index.h:337)
+        if (f_name == "and") cfg.f.kind = FMSI_GPU_F_AND;
+        else if (f_name == "xor") cfg.f.kind = FMSI_GPU_F_XOR;
+        else {
+            const size_t dash = f_name.find('-', 1);
+            cfg.f.kind = FMSI_GPU_F_RANGE;
+            cfg.f.r = std::stoi(f_name.substr(0, dash));
+            cfg.f.s = std::stoi(f_name.substr(dash + 1));
+        }
+    }
     int workers = (int)std::min<unsigned>(8, std::max(2u, std::thread::hardware_concurrency() / 2));
     if (const char *e = std::getenv("FMSI_GPU_THREADS")) workers = std::max(1, atoi(e));
     workers = std::max<int>(workers, (int)members.size());

@@ -114,7 +114,24 @@ int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers,
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     const u32 chunk = pick_chunk(n, grid, kQueryBlock);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr);
+    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr, GenF{0, 0, 0});
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return FMSI_GPU_OK;
+}
+
+int launch_general(const fmsi_gpu_index *idx, const DevIndex &d, const GenF &gf, const u64 *kmers, size_t n, void *out, LaunchScratch &ls,
+                   cudaStream_t st) {
+    CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
+    if (idx->wide) {
+        auto kern = query_kmers_kernel<K_MODE_GENERAL, K_OUT_PRESENCE, K_STRANDS_LAZY, true, false>;
+        const int grid = persistent_grid(idx, kern, kQueryBlock);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf);
+    } else {
+        auto kern = query_kmers_kernel<K_MODE_GENERAL, K_OUT_PRESENCE, K_STRANDS_LAZY, false, false>;
+        const int grid = persistent_grid(idx, kern, kQueryBlock);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf);
+    }
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
@@ -142,7 +159,7 @@ int launch_dict(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, 
     CU(cudaGetLastError());
     auto fix = query_kmers_kernel<MODE, OUT, STRANDS, false, true>;
     const int fgrid = persistent_grid(idx, fix, kQueryBlock);
-    fix<<<fgrid, kQueryBlock, 0, st>>>(d, kmers, 0, out, ls.ctr + 2, 32u, (const u32 *)ls.ovf, ls.ctr + 1);
+    fix<<<fgrid, kQueryBlock, 0, st>>>(d, kmers, 0, out, ls.ctr + 2, 32u, (const u32 *)ls.ovf, ls.ctr + 1, GenF{0, 0, 0});
     CU(cudaGetLastError());
     g_launches.fetch_add(2);
     return FMSI_GPU_OK;
@@ -156,8 +173,11 @@ int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmer
     return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, ls, st);
 }
 
+// mode FMSI_GPU_MODE_GENERAL_ (internal) carries its function in *gf
+constexpr int FMSI_GPU_MODE_GENERAL_ = 2;
 int dispatch_query(const fmsi_gpu_index *idx, const DevIndex &d, int mode, int output, int strands,
-                   const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
+                   const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const GenF *gf = nullptr) {
+    if (mode == FMSI_GPU_MODE_GENERAL_) return launch_general(idx, d, *gf, kmers, n, out, ls, st);
     if (output == FMSI_GPU_OUT_ORDERS) {
         if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
         return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
@@ -820,11 +840,23 @@ int fmsi_gpu_kmer_order_if_present(fmsi_gpu_index *idx, const uint64_t *sa_start
 }
 
 // ---------------------------------------------------------------------------------- hot path
-int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
-                         const uint64_t *kmers, size_t n, int k, void *results, int mem, void *stream) {
+}  // extern "C"
+
+namespace {
+
+bool to_genf(const fmsi_gpu_function *f, GenF &g) {
+    if (!f || f->kind < FMSI_GPU_F_OR || f->kind > FMSI_GPU_F_RANGE || f->r < 0 || f->s < 0) return false;
+    g.kind = f->kind;
+    g.r = (unsigned)f->r;
+    g.s = (unsigned)f->s;
+    return true;
+}
+
+int query_kmers_impl(fmsi_gpu_index *idx, int mode, int output, int strands, const GenF *gf,
+                     const uint64_t *kmers, size_t n, int k, void *results, int mem, void *stream) {
     if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
     if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32] for packed k-mers");
-    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL && !(mode == FMSI_GPU_MODE_GENERAL_ && gf)) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
         (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
     if (n == 0) return FMSI_GPU_OK;
@@ -834,7 +866,7 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
     const size_t rbytes = result_bytes(output, strands);
 
     if (mem == FMSI_GPU_MEM_DEVICE) {
-        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->user, (cudaStream_t)stream);
+        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->user, (cudaStream_t)stream, gf);
     }
     if (mem != FMSI_GPU_MEM_HOST) return fail(FMSI_GPU_ERR_ARG, "bad mem");
 
@@ -848,7 +880,7 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
         int rc;
         if ((rc = ensure(&s.d_in, &s.in_cap, m * 8)) || (rc = ensure(&s.d_out, &s.out_cap, m * rbytes))) return rc;
         CU(cudaMemcpyAsync(s.d_in, kmers + done, m * 8, cudaMemcpyHostToDevice, s.stream));
-        if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.ls, s.stream))) return rc;
+        if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.ls, s.stream, gf))) return rc;
         CU(cudaMemcpyAsync((char *)results + done * rbytes, s.d_out, m * rbytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
         done += m;
@@ -858,13 +890,13 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
     return FMSI_GPU_OK;
 }
 
-int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
-                          const char *bases, size_t n_bases, const uint64_t *chunk_off,
-                          const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
-                          size_t n_results, int k, void *results, int mem, void *stream) {
+int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming, const GenF *gf,
+                      const char *bases, size_t n_bases, const uint64_t *chunk_off,
+                      const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
+                      size_t n_results, int k, void *results, int mem, void *stream) {
     if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
     if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
-    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
+    if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL && !(mode == FMSI_GPU_MODE_GENERAL_ && gf)) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
         (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
     if (streaming && !idx->meta.has_klcp) return fail(FMSI_GPU_ERR_KLCP, "kLCP array was not loaded for the given index");
@@ -927,7 +959,7 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
         extract_kmers_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
         CU(cudaGetLastError());
         g_launches.fetch_add(1);
-        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.ls : idx->user, st))) return rc;
+        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.ls : idx->user, st, gf))) return rc;
     } else {
         if ((rc = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off, d_len, d_res, n_chunks, d_results,
                                   on_host ? s.ls.ctr : idx->user.ctr, st)))
@@ -942,6 +974,39 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
     return FMSI_GPU_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands, const uint64_t *kmers, size_t n, int k,
+                         void *results, int mem, void *stream) {
+    if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    return query_kmers_impl(idx, mode, output, strands, nullptr, kmers, n, k, results, mem, stream);
+}
+
+int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming, const char *bases,
+                          size_t n_bases, const uint64_t *chunk_off, const uint32_t *chunk_len, const uint64_t *res_off,
+                          size_t n_chunks, size_t n_results, int k, void *results, int mem, void *stream) {
+    if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, bases, n_bases, chunk_off, chunk_len, res_off, n_chunks,
+                             n_results, k, results, mem, stream);
+}
+
+int fmsi_gpu_query_kmers_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const uint64_t *kmers, size_t n, int k,
+                                 uint8_t *results, int mem, void *stream) {
+    GenF gf;
+    if (!to_genf(f, gf)) return fail(FMSI_GPU_ERR_ARG, "bad demasking function");
+    return query_kmers_impl(idx, FMSI_GPU_MODE_GENERAL_, FMSI_GPU_OUT_PRESENCE, FMSI_GPU_STRANDS_LAZY, &gf, kmers, n, k, results, mem, stream);
+}
+
+int fmsi_gpu_query_chunks_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const char *bases, size_t n_bases,
+                                  const uint64_t *chunk_off, const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
+                                  size_t n_results, int k, uint8_t *results, int mem, void *stream) {
+    GenF gf;
+    if (!to_genf(f, gf)) return fail(FMSI_GPU_ERR_ARG, "bad demasking function");
+    return query_chunks_impl(idx, FMSI_GPU_MODE_GENERAL_, FMSI_GPU_OUT_PRESENCE, FMSI_GPU_STRANDS_LAZY, 0, &gf, bases, n_bases, chunk_off, chunk_len,
+                             res_off, n_chunks, n_results, k, results, mem, stream);
+}
 
 // ---------------------------------------------------------------------------------- multi-GPU pool
 }  // extern "C"

@@ -24,7 +24,23 @@
 namespace fmsi {
 
 enum { PH_TABLE = 0, PH_STEP = 1, PH_MASK = 2 };
-enum { K_MODE_OR = 0, K_MODE_ALL = 1 };
+enum { K_MODE_OR = 0, K_MODE_ALL = 1, K_MODE_GENERAL = 2 };
+enum { K_F_OR = 0, K_F_AND = 1, K_F_XOR = 2, K_F_RANGE = 3 };
+
+// Demasking function of the f-MS framework (reference src/functions.h:7-57), applied to the number
+// of ON occurrences and of all occurrences of a k-mer over both strands.
+struct GenF {
+    int kind;
+    unsigned r, s;
+};
+__device__ __forceinline__ bool apply_f(const GenF &f, u64 ones, u64 total) {
+    switch (f.kind) {
+    case K_F_AND: return total && ones == total;       // f_and
+    case K_F_XOR: return ones & 1ull;                  // f_xor
+    case K_F_RANGE: return ones <= f.s && ones >= f.r; // f_r_to_s
+    default: return ones != 0;                         // f_or
+    }
+}
 enum { K_OUT_PRESENCE = 0, K_OUT_ORDERS = 1 };
 enum { K_STRANDS_LAZY = 0, K_STRANDS_BOTH = 1 };
 
@@ -71,7 +87,7 @@ template <int MODE, int OUT, int STRANDS, bool WIDE, bool INDIRECT = false>
 __global__ void __launch_bounds__(kQueryBlock)
 query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_arg, void *__restrict__ out,
                    unsigned long long *__restrict__ cursor, const u32 chunk, const u32 *__restrict__ sel = nullptr,
-                   const unsigned long long *__restrict__ n_dev = nullptr) {
+                   const unsigned long long *__restrict__ n_dev = nullptr, const GenF gf = GenF{0, 0, 0}) {
     typedef typename PosT<WIDE>::type pos_t;
     const u64 n = INDIRECT ? (u64)*n_dev : n_arg;
     const unsigned FULL = 0xffffffffu;
@@ -87,6 +103,7 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
     u64 kf = 0, pat = 0, idx = 0;
     pos_t i = 0, j = 0;
     long long res_f = 0;
+    u64 g_ones = 0, g_total = 0;  // K_MODE_GENERAL: occurrences summed over the strands
     // warp state (uniform)
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
     u32 selA = 0, selB = 0;  // INDIRECT: result slots of the register tiles
@@ -148,6 +165,7 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
                 if (take) {
                     active = true;
                     idx = INDIRECT ? (u64)sl : my;
+                    g_ones = g_total = 0;
                     kf = km;
                     pat = km;
                     strand = 0;
@@ -213,13 +231,22 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
             if (!two) {
                 b1 = a1; b2 = a2;
             }
-            res = strand_result<MODE, OUT>((u64)i, (u64)j, a1, a2, b1, b2);
+            if (MODE == K_MODE_GENERAL) {  // single_query_general, fms_index.h:171-179
+                g_ones += mask_rank_incl(b1, b2, (u32)((u64)j - 1) & 63u) - mask_rank_excl(a1, a2, (u32)i & 63u);
+                g_total += (u64)j - (u64)i;
+            } else {
+                res = strand_result<MODE, OUT>((u64)i, (u64)j, a1, a2, b1, b2);
+            }
             done = true;
         }
 
         if (done) {
             bool other;  // run the other strand next?
-            if (STRANDS == K_STRANDS_BOTH) {
+            if (MODE == K_MODE_GENERAL) {
+                // both strands, except that a self-complementary k-mer is counted once (:318-323)
+                other = strand == 0 && revcomp_packed(kf, k) != kf;
+                if (!other) res = apply_f(gf, g_ones, g_total) ? 1 : 0;
+            } else if (STRANDS == K_STRANDS_BOTH) {
                 other = strand == 0;
                 if (other) res_f = res;
             } else if (OUT == K_OUT_ORDERS) {

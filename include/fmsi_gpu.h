@@ -39,7 +39,7 @@ enum {
     FMSI_GPU_ERR_NOMEM = -6
 };
 
-/* query_mode, reference src/fms_index.h:256-260 (`general` / -f functions are out of scope). */
+/* query_mode, reference src/fms_index.h:256-260 (`general`: see fmsi_gpu_query_kmers_general). */
 enum { FMSI_GPU_MODE_OR = 0, FMSI_GPU_MODE_ALL = 1 };
 /* output_orders of query_kmers(): presence bits (`fmsi query`) or mask-rank ids (`fmsi lookup`). */
 enum { FMSI_GPU_OUT_PRESENCE = 0, FMSI_GPU_OUT_ORDERS = 1 };
@@ -149,6 +149,25 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
                           const char *bases, size_t n_bases, const uint64_t *chunk_off,
                           const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                           size_t n_results, int k, void *results, int mem, void *stream);
+
+/* ---- f-MS framework: general demasking functions -------------------------------------------- */
+/* query_kmers<query_mode::general>() — reference src/fms_index.h:317-327 with single_query_general
+ * (:171-179) and the demasking functions of src/functions.h:7-57: the number of ON occurrences and of
+ * all occurrences of the k-mer and of its reverse complement (a self-complementary k-mer is counted
+ * once) are passed to f; results[q] = 1 iff the reference prints '1'. kLCP streaming does not apply
+ * (the reference ignores -S in this mode) and the strand predictor is not involved. */
+enum { FMSI_GPU_F_OR = 0, FMSI_GPU_F_AND = 1, FMSI_GPU_F_XOR = 2, FMSI_GPU_F_RANGE = 3 };
+typedef struct {
+    int32_t kind; /* FMSI_GPU_F_* */
+    int32_t r, s; /* FMSI_GPU_F_RANGE: represented iff r <= #ON occurrences <= s ("INT-INT") */
+    int32_t reserved;
+} fmsi_gpu_function;
+int fmsi_gpu_query_kmers_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const uint64_t *kmers,
+                                 size_t n, int k, uint8_t *results, int mem, void *stream);
+int fmsi_gpu_query_chunks_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const char *bases,
+                                  size_t n_bases, const uint64_t *chunk_off, const uint32_t *chunk_len,
+                                  const uint64_t *res_off, size_t n_chunks, size_t n_results, int k,
+                                  uint8_t *results, int mem, void *stream);
 
 /* ---- multi-GPU scheduler -------------------------------------------------------------------- */
 /* The query path shards by independent units (k-mers; chunks for -S) with a full index replica per

@@ -45,6 +45,25 @@ def test_cli_matches_reference_outputs(case):
         assert r.stdout == want, f"{case}/{cmd}"
 
 
+F_ARGS = {"query_f_xor": ["query", "-f", "xor"], "query_f_and": ["query", "-f", "and"], "query_f_1-1": ["query", "-f", "1-1"],
+          "query_f_2-9": ["query", "-f", "2-9"], "query_S_f_xor": ["query", "-S", "-f", "xor"]}
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_cli_general_demasking_functions(case):
+    """`query -f xor|and|INT-INT` (f-MS framework, reference fms_index.h:317-327 + functions.h) against
+    the reference binary's outputs, incl. the reference's own golden result_b_complements_xor.txt."""
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    cmds = meta.get("cmds_f", [])
+    runs = run_many([F_ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")] for cmd in cmds])
+    for cmd, r in zip(cmds, runs):
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}"
+    if case == "integration_b":
+        assert runs[cmds.index("query_f_xor")].stdout == open(os.path.join(d, "ref_golden_query_f_xor.txt"), "rb").read()
+
+
 @pytest.mark.parametrize("case", sorted(LAZY_EXACT))
 def test_cli_lazy_mode_where_order_independent(case):
     d = os.path.join(GOLDEN, case)

@@ -279,6 +279,42 @@ def test_chunks_streaming_and_single_match_oracle(case):
     oi.close()
 
 
+@pytest.mark.parametrize("case", ["syn_k31_min", "syn_k9_min", "syn_k5_min", "quirks_k3_nonmax", "syn_k31_max"])
+def test_general_demasking_functions_properties(case):
+    """fmsi_gpu_query_kmers_general (single_query_general on both strands, fms_index.h:171-179,
+    :317-327): cross-checked against the oracle-verified modes through identities of the functions
+    of src/functions.h — 1..inf == or; xor == (1-1) + (3-3) + ...; and on a max-ones mask == -O."""
+    d = os.path.join(GOLDEN, case)
+    k = json.load(open(os.path.join(d, "meta.json")))["k"]
+    prefix = os.path.join(d, "ms.fa")
+    rng = np.random.default_rng(5)
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    kmers = _random_kmers(rng, ms_codes, k, 4000)
+    for kw in ({}, {"prefix_t": 0}, {"sb_shift_log2": 1, "prefix_t": 2}):
+        gi = fg.Index.load(prefix, use_klcp=False, **kw)
+        orr = gi.query_kmers(kmers, k, fg.MODE_OR)
+        ge1 = gi.query_kmers_general(kmers, "1-1000000", k)
+        assert np.array_equal(ge1, orr)
+        odd = np.zeros(len(kmers), dtype=np.uint8)
+        for c in range(1, 40, 2):
+            odd |= gi.query_kmers_general(kmers, f"{c}-{c}", k)
+        big = gi.query_kmers_general(kmers, "40-1000000", k)
+        xor = gi.query_kmers_general(kmers, "xor", k)
+        assert np.array_equal(xor[big == 0], odd[big == 0])
+        land = gi.query_kmers_general(kmers, "and", k)
+        assert not (land & ~orr).any()          # and => or
+        if case == "syn_k31_max":                # every occurrence ON: and == or == -O
+            assert np.array_equal(land, orr) and np.array_equal(land, gi.query_kmers(kmers, k, fg.MODE_ALL))
+        assert np.array_equal(gi.query_kmers_general(kmers, fg.Function(kind=0), k), orr)  # f_or
+        gi.close()
+    with pytest.raises(fg.FmsiGpuError):
+        gi = fg.Index.load(prefix, use_klcp=False)
+        try:
+            gi.query_kmers_general(kmers, fg.Function(kind=7), k)
+        finally:
+            gi.close()
+
+
 def test_multi_gpu_pool_matches_single_index():
     """The scheduler (fmsi_gpu_pool_*): replicas made by device-to-device copy answer contiguous
     shards from their own host threads; results must equal the single-index call, in query order.
