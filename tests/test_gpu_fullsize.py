@@ -1,0 +1,94 @@
+"""BASELINE.json configs[3] at FULL size (3.1 Gbp, k = 31) through size-independent properties:
+the oracle cannot build or hold an index of this size in test time, so the GPU paths are checked
+against each other and against facts that hold by construction of the workload (every sampled
+genome k-mer is present on either strand, random 31-mers are absent, ids are a strand-symmetric
+injection into [0, mask_ones)). bench.py additionally checks a 100 k-query sample of the same
+workload against the oracle on every run (`parity_vs_oracle_sample`)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT  # noqa: F401
+
+import fmsi_b200 as fg
+from fmsi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+N_GENOME = int(os.environ.get("FMSI_TEST_FULLSIZE", 3_100_000_000))
+K = 31
+
+
+@pytest.fixture(scope="module")
+def human():
+    torch = pytest.importorskip("torch")
+    from bench import device_genome, device_queries
+    dev = torch.device("cuda", 0)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 110e9 * (N_GENOME / 3.1e9):
+        pytest.skip("not enough free device memory for the full-size index")
+    codes, ascii_ = device_genome(N_GENOME, 4, K, dev)
+    gd = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=1)
+    gb = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=0)
+    del ascii_
+    yield torch, dev, codes, gd, gb, device_queries
+    gd.close()
+    gb.close()
+
+
+def test_full_size_index_shape(human):
+    torch, dev, codes, gd, gb, _ = human
+    assert gd.n == N_GENOME + 1 == gb.n and gd.k == K
+    assert gd.dict and not gb.dict and not gd.wide
+    assert gd.counts == gb.counts and gd.counts[0] == 1 and gd.dollar_position == gb.dollar_position
+    # counts[] = {1, #A+1, #A+#C+1, #A+#C+#G+1} (construct(), fms_index.h:451) against the text itself
+    hist = torch.bincount(codes[:1 << 28].long(), minlength=4)  # spot check of the generator only
+    assert int(hist.sum()) == min(N_GENOME, 1 << 28)
+    assert gd.mask_ones == N_GENOME - (K - 1)  # every k-mer occurrence ON
+
+
+def test_full_size_query_properties(human):
+    torch, dev, codes, gd, gb, device_queries = human
+    n = 1 << 23
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(123)
+    pos = torch.randint(0, N_GENOME - K + 1, (n,), device=dev, generator=gen)
+    fw = torch.zeros(n, dtype=torch.int64, device=dev)
+    for t in range(K):
+        fw = (fw << 2) | codes[pos + t].long()
+    present = fw.cpu().numpy().view(np.uint64)
+    present_rc = synth.revcomp_packed(present, K)
+    rnd = torch.randint(0, 1 << (2 * K), (n,), dtype=torch.int64, device=dev, generator=gen).cpu().numpy().view(np.uint64)
+    mixed = device_queries(codes, K, n, 7, dev).cpu().numpy().view(np.uint64)
+    for gi in (gd, gb):
+        for mode in (fg.MODE_ALL, fg.MODE_OR):
+            assert gi.query_kmers(present, K, mode).all()
+            assert gi.query_kmers(present_rc, K, mode).all()       # the other strand is found too
+            assert int(gi.query_kmers(rnd, K, mode).sum()) <= 2     # 2 * 3.1e9 / 4^31 per query: essentially none
+    # dictionary tier == backward search, every mode and strand policy, on the bench's query mix
+    for mode, out in ((fg.MODE_ALL, fg.OUT_PRESENCE), (fg.MODE_OR, fg.OUT_PRESENCE), (fg.MODE_OR, fg.OUT_ORDERS)):
+        for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+            a = gd.query_kmers(mixed, K, mode, out, strands)
+            b = gb.query_kmers(mixed, K, mode, out, strands)
+            assert np.array_equal(a, b), (mode, out, strands)
+    r = gd.query_kmers(mixed, K, fg.MODE_ALL)
+    assert 0.49 < r.mean() < 0.51
+    assert np.array_equal(r, gd.query_kmers(synth.revcomp_packed(mixed, K), K, fg.MODE_ALL))  # strand symmetry
+    assert np.array_equal(r, gd.query_kmers(mixed, K, fg.MODE_ALL))                           # idempotence
+    # lookup: ids of genome k-mers lie in [0, mask_ones); a k-mer and its reverse complement share the id;
+    # distinct canonical k-mers get distinct ids
+    ids = gd.query_kmers(present[:1 << 20], K, output=fg.OUT_ORDERS)
+    ids_rc = gd.query_kmers(present_rc[:1 << 20], K, output=fg.OUT_ORDERS)
+    assert (ids >= 0).all() and int(ids.max()) < gd.mask_ones and np.array_equal(ids, ids_rc)
+    canon = synth.canonical_packed(present[:1 << 20], K)
+    uc, first = np.unique(canon, return_index=True)
+    assert len(np.unique(ids[first])) == len(uc)
+    assert (gd.query_kmers(rnd[:1 << 20], K, output=fg.OUT_ORDERS) == -1).sum() >= (1 << 20) - 2
+    # streamed reads (chunks) agree with single k-mers at this size
+    reads = codes[:150 * 2000].cpu().numpy().reshape(2000, 150)
+    bases = b"".join(synth.codes_to_ascii(x) for x in reads)
+    offs = np.repeat(np.arange(2000, dtype=np.uint64) * 150, 2) + np.tile(np.array([0, 64], dtype=np.uint64), 2000)
+    lens = np.tile(np.array([64 + K - 1, 150 - 64], dtype=np.uint32), 2000)
+    s = gd.query_chunks(bases, offs, lens, K, fg.MODE_ALL)
+    assert s.all() and len(s) == 2000 * 120
