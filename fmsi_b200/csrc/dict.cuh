@@ -19,9 +19,13 @@
 // Rows of one bucket are suffixes sharing x, in lexicographic order, so the rows whose next B bases
 // equal the k-mer's last B bases are exactly the k-mer's SA interval [i', j'):  -O presence =
 // mask[i'] (first match), or-presence = any mask bit among the matches, lookup id = rank1(i') when
-// any match is ON (one aux-sector probe). Buckets with more than kDictMaxScan extra rows (highly
-// repetitive t-mers) put the k-mer on an overflow list that the backward-search kernel answers in a
-// second launch (query_kmers_kernel<..., INDIRECT>), so results are exact for every input.
+// any match is ON (one aux-sector probe). Payloads are non-decreasing inside a bucket (rows whose
+// suffix ends before k characters are padded with A after the sentinel, which keeps them in order, and
+// are flagged invalid), so a bucket with many rows is binary-searched for the first payload >= the
+// k-mer's, one sector per step, before the linear scan. Only a k-mer whose matches run on for more than
+// kDictMaxScan rows without settling the answer (a long run of OFF occurrences in or/lookup mode) is
+// put on an overflow list that the backward-search kernel answers in a second launch
+// (query_kmers_kernel<..., INDIRECT>), so results are exact for every input.
 //
 // The rows are derived from the BWT alone (works for file-loaded and device-built indexes alike):
 // psi = inverse of the LF-mapping (one scatter pass), then every row walks psi k-1 times reading
@@ -32,7 +36,8 @@
 namespace fmsi {
 
 constexpr u32 kDictCap32 = 5, kDictCap64 = 2;
-constexpr u32 kDictMaxScan = 64;  // rows beyond the bucket scanned linearly before giving up to the fixup pass
+constexpr u32 kDictMaxScan = 64;  // rows scanned linearly from the first candidate before giving up to the fixup pass
+constexpr u32 kDictBsearchMin = 16;  // windows larger than this are narrowed by binary search first
 
 struct DictView {
     const u64 *rows;   // [N]
@@ -68,10 +73,12 @@ __global__ void rows_walk_kernel(const DevIndex d, const u32 *__restrict__ psi, 
     u32 cur = (u32)r;
     for (u32 s = 0; s < t; ++s) cur = __ldg(psi + cur);
     u64 pay = 0;
+    bool ended = false;  // reached the sentinel: the rest is padding (A = 0), which keeps the bucket sorted
     for (u32 s = 0; s < B; ++s) {
-        const u32 c = (cur >= c3) ? 3u : (cur >= c2) ? 2u : (cur >= c1) ? 1u : 0u;
+        if (cur == 0) ended = true;
+        const u32 c = ended ? 0u : (cur >= c3) ? 3u : (cur >= c2) ? 2u : (cur >= c1) ? 1u : 0u;
         pay = (pay << 2) | c;
-        if (s + 1 < B) cur = __ldg(psi + cur);
+        if (!ended && s + 1 < B) cur = __ldg(psi + cur);
     }
     const u64 m = (d.aux[r >> 6].mask >> (r & 63)) & 1ull;
     rows[r] = (pay << 2) | 2ull | m;
@@ -125,7 +132,7 @@ __global__ void bucket_fill_kernel(const TableEntry<false> *__restrict__ tab, co
 }
 
 // ------------------------------------------------------------------------------------------- query
-enum { DP_BUCKET = 0, DP_ROWS = 1, DP_AUX = 2 };
+enum { DP_BUCKET = 0, DP_ROWS = 1, DP_AUX = 2, DP_BSEARCH = 3 };
 
 template <int MODE, int OUT, int STRANDS, bool PAY64>
 __global__ void __launch_bounds__(kQueryBlock)
@@ -144,7 +151,7 @@ dict_query_kernel(const DevIndex d, const DictView dv, const u64 *__restrict__ k
     bool active = false;
     u32 phase = DP_BUCKET, strand = 0;
     u64 kf = 0, pat = 0, idx = 0, q = 0;
-    u32 i = 0, j = 0, rpos = 0;
+    u32 i = 0, j = 0, rpos = 0, hi = 0;  // hi: binary-search window end, then the linear scan's give-up row
     u32 fm = 0;            // first matching row (valid when have)
     bool have = false, fm_mask = false, anymask = false;
     long long res_f = 0;
@@ -205,15 +212,16 @@ dict_query_kernel(const DevIndex d, const DictView dv, const u64 *__restrict__ k
         const bool isB = active && phase == DP_BUCKET;
         const bool isR = active && phase == DP_ROWS;
         const bool isA = active && phase == DP_AUX;
-        u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        const bool isS = active && phase == DP_BSEARCH;
+        const u32 msec = (rpos + ((hi - rpos) >> 1)) >> 2;  // sector probed by a binary-search step
+        u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         const u32 rsec = rpos >> 2;                         // rows sector (4 rows of 8 B)
-        const bool two = isR && ((rsec + 1) << 2) < j;
         if (isB) ld_sector(reinterpret_cast<const char *>(d.table) + ((pat >> (2 * B)) << 5), a0, a1, a2, a3);
         if (isR) {
             ld_sector(dv.rows + ((u64)rsec << 2), a0, a1, a2, a3);
-            if (two) ld_sector(dv.rows + (((u64)rsec + 1) << 2), b0, b1, b2, b3);
         }
         if (isA) ld_sector(d.aux + (fm >> 6), a0, a1, a2, a3);
+        if (isS) ld_sector(dv.rows + ((u64)msec << 2), a0, a1, a2, a3);
 
         // ---------------------------------------------------------------- consume
         bool done = false, overflow = false;
@@ -234,8 +242,8 @@ dict_query_kernel(const DevIndex d, const DictView dv, const u64 *__restrict__ k
                 if (PAY64) pay = s == 0 ? a2 : a3;
                 else pay = s == 0 ? (a1 >> 32) : s == 1 ? (a2 & 0xffffffffull) : s == 2 ? (a2 >> 32) : s == 3 ? (a3 & 0xffffffffull) : (a3 >> 32);
                 const bool valid = (meta >> s) & 1u, mb = (meta >> (8 + s)) & 1u;
-                if (s < m && valid) {
-                    if (pay == q) {
+                if (s < m) {
+                    if (pay == q && valid) {
                         if (!have) {
                             have = true;
                             fm = i + s;
@@ -250,22 +258,45 @@ dict_query_kernel(const DevIndex d, const DictView dv, const u64 *__restrict__ k
             const bool conclusive = cnt <= CAP || past || (first_only ? have : anymask);
             if (conclusive) {
                 done = true;
-            } else if (cnt - CAP > kDictMaxScan) {
-                overflow = true;
             } else {
                 rpos = i + CAP;
+                hi = j;
+                // matches already seen continue right after the inline rows; otherwise find the first
+                // payload >= q, by binary search when the bucket is large
+                if (!have && hi - rpos > kDictBsearchMin) {
+                    phase = DP_BSEARCH;
+                } else {
+                    phase = DP_ROWS;
+                    hi = rpos + kDictMaxScan;
+                }
+            }
+        } else if (isS) {
+            // invariant: rows [i+CAP, rpos) have payload < q; rows >= hi have payload >= q (or hi == j)
+            const u32 r0 = msec << 2;
+            const u32 lo_r = r0 > rpos ? r0 : rpos, hi_r = (r0 + 4 < hi) ? r0 + 4 : hi;  // in-window rows [lo_r, hi_r)
+            const u32 sf = lo_r - r0, sl = hi_r - 1 - r0;
+            const u64 first = (sf == 0 ? a0 : sf == 1 ? a1 : sf == 2 ? a2 : a3) >> 2;
+            const u64 last = (sl == 0 ? a0 : sl == 1 ? a1 : sl == 2 ? a2 : a3) >> 2;
+            if (last < q) rpos = hi_r;
+            else if (first >= q) hi = lo_r;
+            else {
+                rpos = lo_r;  // the first payload >= q lies inside this sector
+                hi = lo_r;
+            }
+            if (hi - rpos <= kDictBsearchMin) {
                 phase = DP_ROWS;
+                hi = rpos + kDictMaxScan;
             }
         } else if (isR) {
             bool past = false;
 #pragma unroll
-            for (u32 s = 0; s < 8; ++s) {
-                const u64 row = s == 0 ? a0 : s == 1 ? a1 : s == 2 ? a2 : s == 3 ? a3 : s == 4 ? b0 : s == 5 ? b1 : s == 6 ? b2 : b3;
+            for (u32 s = 0; s < 4; ++s) {
+                const u64 row = s == 0 ? a0 : s == 1 ? a1 : s == 2 ? a2 : a3;
                 const u32 r = (rsec << 2) + s;
-                if (r >= rpos && r < j && (s < 4 || two) && (row & 2ull)) {
+                if (r >= rpos && r < j) {
                     const u64 pay = row >> 2;
                     const bool mb = row & 1ull;
-                    if (pay == q) {
+                    if (pay == q && (row & 2ull)) {
                         if (!have) {
                             have = true;
                             fm = r;
@@ -277,14 +308,15 @@ dict_query_kernel(const DevIndex d, const DictView dv, const u64 *__restrict__ k
                     }
                 }
             }
-            rpos = (rsec + 2) << 2;
+            rpos = (rsec + 1) << 2;
             if (rpos >= j || past || (first_only ? have : anymask)) done = true;
+            else if (rpos >= hi) overflow = true;
         } else if (isA) {
             res = (long long)mask_rank_excl(a1, a2, fm & 63u);
             done = true;
         }
 
-        if (done && !isA) {  // strand value from the matches (fms_index.h:126-156)
+        if (done && !isA && !overflow) {  // strand value from the matches (fms_index.h:126-156)
             if (!have) res = -1;
             else if (OUT == K_OUT_PRESENCE) res = first_only ? (fm_mask ? 1 : 0) : (anymask ? 1 : 0);
             else if (!anymask) res = -1;

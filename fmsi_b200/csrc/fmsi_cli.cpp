@@ -687,7 +687,12 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     }
     if (k == 0) k = index_k;
     if (k < 1 || k > 32) {
-        std::cerr << "ERROR: the GPU query engine supports k <= 32 (index has k = " << k << ")." << std::endl;
+        // packed 2-bit k-mers live in one 64-bit word on the device; longer k goes to the reference
+        fmsi_gpu_index_free(idx);
+        const char *ref = std::getenv("FMSI_REFERENCE_BIN");
+        if (ref && *ref) return -2;
+        std::cerr << "ERROR: the GPU query engine supports k <= 32 (index has k = " << k
+                  << "); set FMSI_REFERENCE_BIN to forward such queries to the reference binary." << std::endl;
         return 1;
     }
 

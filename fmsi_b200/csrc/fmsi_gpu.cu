@@ -359,7 +359,7 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     // Dictionary tier: narrow indexes with k <= 32. Depth = the largest t <= min(k, 15) with
     // 4^t <= 4N (on average at most ~4 and at least ~0.25 rows per bucket) whose buckets (32 B each)
     // plus rows (8 B per SA row, + 4 B per row of build scratch) fit in half of the free memory.
-    bool dict = want_dict != 0 && !idx->wide && h.k >= 1 && h.k <= 32 && h.n < (1ull << 32) - 64;
+    bool dict = want_dict != 0 && !idx->wide && h.k >= 1 && h.k <= 32 && h.n < (1ull << 32) - 256;
     if (dict) {
         int td = t;
         if (td < 0) {

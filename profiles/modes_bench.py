@@ -39,11 +39,26 @@ def main():
     ap.add_argument("--kmers", type=int, default=1 << 25)
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--k", type=int, default=31)
+    ap.add_argument("--copies", type=int, default=1, help="pangenome-like: this many mutated copies of the genome, concatenated")
+    ap.add_argument("--snp", type=float, default=0.01, help="per-base substitution rate of every copy")
     args = ap.parse_args()
     k = args.k
     dev = torch.device("cuda", 0)
     codes, ascii_ = device_genome(args.genome, 4, k, dev)
-    out = {"genome": args.genome, "k": k, "rows": []}
+    if args.copies > 1:  # BASELINE configs[4] shape, scaled: every k-mer occurs ~copies times (large SA intervals)
+        gen0 = torch.Generator(device=dev)
+        gen0.manual_seed(77)
+        parts = []
+        for c in range(args.copies):
+            sub = torch.rand(args.genome, device=dev, generator=gen0) < args.snp
+            shift = torch.randint(1, 4, (args.genome,), device=dev, generator=gen0, dtype=torch.uint8)
+            parts.append(torch.where(sub, (codes + shift) & 3, codes))
+        codes = torch.cat(parts)
+        lut0 = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+        ascii_ = lut0[codes.long()]
+        ascii_[codes.numel() - (k - 1):] += 32
+        args.genome = codes.numel()
+    out = {"genome": args.genome, "copies": args.copies, "k": k, "rows": []}
     idx = {}
     for name, dct in (("dict", 1), ("backward", 0)):
         t0 = time.time()

@@ -198,10 +198,14 @@ def test_dictionary_tier_on_repetitive_index(tmp_path):
         synth.write_fasta_single(fa, "ms", synth.codes_to_ascii(g, mask))
         subprocess.run([REF_EXE, "index", "-k", str(k), fa], check=True, capture_output=True)
         oi = OracleIndex.load(fa, use_klcp=False)
-        kmers = np.concatenate([_random_kmers(rng, g, k, 20000), synth.pack_kmers(g[:5000], k),
+        # k-mers made of the text's last characters padded with A's equal the padded payload of the
+        # invalid (too short) rows: they must not match through those rows
+        tails = np.stack([np.concatenate([g[len(g) - m:], np.zeros(k - m, np.uint8)]) for m in range(1, k)])
+        kmers = np.concatenate([_random_kmers(rng, g, k, 20000), synth.pack_kmers(g[:5000], k), synth.pack_kmers(g[-300:], k),
+                                synth.pack_rows(tails), synth.revcomp_packed(synth.pack_rows(tails), k),
                                 synth.pack_rows(np.stack([np.full(k, c, np.uint8) for c in range(4)]))])
         strs = None
-        for kw in ({}, {"dict": 1, "prefix_t": 4}, {"dict": 1, "prefix_t": 7}):
+        for kw in ({}, {"dict": 1, "prefix_t": 1}, {"dict": 1, "prefix_t": 4}, {"dict": 1, "prefix_t": 7}):
             gd = fg.Index.load(fa, use_klcp=False, **kw)
             gb = fg.Index.load(fa, use_klcp=False, dict=0)
             assert gd.dict and not gb.dict
