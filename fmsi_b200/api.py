@@ -58,7 +58,7 @@ class IndexInfo(C.Structure):
         ("n_bwt", C.c_uint64), ("counts", C.c_uint64 * 4), ("dollar_position", C.c_uint64),
         ("mask_ones", C.c_uint64), ("hbm_bytes", C.c_uint64), ("k", C.c_int32), ("has_klcp", C.c_int32),
         ("prefix_t", C.c_int32), ("wide", C.c_int32), ("device", C.c_int32), ("dict", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("dict_t", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -162,6 +162,8 @@ class Index:
         self.prefix_t = int(info.prefix_t)
         self.wide = bool(info.wide)
         self.dict = bool(info.dict)
+        self.dict_kind = int(info.dict)   # 0 none, 1 SA-ordered dictionary, 2 strand-folded dictionary
+        self.dict_t = int(info.dict_t)
         self.hbm_bytes = int(info.hbm_bytes)
         self.mask_ones = int(info.mask_ones)
 

@@ -14,6 +14,7 @@
 
 #include "device_index.cuh"
 #include "dict.cuh"
+#include "fold.cuh"
 #include "index_build.cuh"
 #include "index_convert.cuh"
 #include "index_layout.hpp"
@@ -65,10 +66,13 @@ struct fmsi_gpu_index {
     HostIndex meta;  // vectors released after upload
     DevIndex dev{};
     void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr, *d_rows = nullptr;
+    void *d_fbuckets = nullptr, *d_frows = nullptr, *d_fids = nullptr;  // strand-folded dictionary (fold.cuh)
     size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
+    size_t b_fbuckets = 0, b_frows = 0, b_fids = 0;
     uint64_t hbm_bytes = 0;
     bool wide = false;
     DictView dict{};
+    FoldView fold{};
     Slot slots[kSlots];
     LaunchScratch user;  // scratch for MEM_DEVICE launches
     // host copies of the BWT/mask/kLCP planes, kept only for indexes made by fmsi_gpu_index_build
@@ -165,10 +169,40 @@ int launch_dict(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, 
     return FMSI_GPU_OK;
 }
 
+// Strand-folded dictionary kernel over all n queries: one launch, every answer final.
+bool fold_ld64() {  // $FMSI_GPU_LD64=0: whole-line L2 fills for bucket probes (design experiment switch)
+    static const bool v = [] {
+        const char *e = std::getenv("FMSI_GPU_LD64");
+        return !(e && std::atoi(e) == 0);
+    }();
+    return v;
+}
+
+template <int MODE, int OUT, int STRANDS, bool PAY64, bool LD64>
+int launch_fold_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
+    auto kern = fold_query_kernel<MODE, OUT, STRANDS, PAY64, LD64>;
+    const int grid = persistent_grid(idx, kern, kQueryBlock);
+    CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
+    kern<<<grid, kQueryBlock, 0, st>>>(idx->fold, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock));
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return FMSI_GPU_OK;
+}
+
+template <int MODE, int OUT, int STRANDS>
+int launch_fold(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
+    const bool pay64 = idx->fold.B > 16, ld64 = fold_ld64();
+    if (pay64) return ld64 ? launch_fold_v<MODE, OUT, STRANDS, true, true>(idx, kmers, n, out, ls, st)
+                           : launch_fold_v<MODE, OUT, STRANDS, true, false>(idx, kmers, n, out, ls, st);
+    return ld64 ? launch_fold_v<MODE, OUT, STRANDS, false, true>(idx, kmers, n, out, ls, st)
+                : launch_fold_v<MODE, OUT, STRANDS, false, false>(idx, kmers, n, out, ls, st);
+}
+
 template <int MODE, int OUT, int STRANDS>
 int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
                    LaunchScratch &ls, cudaStream_t st) {
     if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, ls, st);
+    if (idx->fold.enabled && d.k == idx->fold.k) return launch_fold<MODE, OUT, STRANDS>(idx, kmers, n, out, ls, st);
     if (idx->dict.enabled && d.k == idx->dict.k && d.t && n < (1ull << 32)) return launch_dict<MODE, OUT, STRANDS>(idx, d, kmers, n, out, ls, st);
     return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, ls, st);
 }
@@ -305,6 +339,38 @@ int build_dict(fmsi_gpu_index *idx, u32 t) {
     return FMSI_GPU_OK;
 }
 
+// Strand-folded dictionary (fold.cuh) at bucket depth t, plus a plain {i, j} suffix table (depth tt) for
+// the backward-search kernels (general mode, queries with another k). Returns FMSI_GPU_ERR_NOMEM when the
+// device cannot hold the build, so that the caller can fall back to a smaller tier.
+int build_fold(fmsi_gpu_index *idx, u32 t, u32 tt) {
+    const HostIndex &h = idx->meta;
+    FoldArrays fa;
+    uint64_t launches = 0;
+    try {
+        build_fold_on_device(idx->dev, h.counts, (u32)h.k, t, fa, &launches);
+    } catch (const std::exception &e) {
+        const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || std::string(e.what()).find("out of memory") != std::string::npos;
+        return fail(oom ? FMSI_GPU_ERR_NOMEM : FMSI_GPU_ERR_CUDA, std::string("strand-folded dictionary: ") + e.what());
+    }
+    g_launches.fetch_add(launches);
+    idx->d_fbuckets = fa.buckets;
+    idx->d_frows = fa.rows;
+    idx->d_fids = fa.ids;
+    idx->b_fbuckets = (1ull << (2 * t)) * sizeof(FoldBucket);
+    idx->b_frows = (fa.n_rows + 8) * sizeof(u64);
+    idx->b_fids = (fa.n_rows + 1) * sizeof(uint2);
+    idx->hbm_bytes += idx->b_fbuckets + idx->b_frows + idx->b_fids;
+    idx->fold.buckets = fa.buckets;
+    idx->fold.rows = fa.rows;
+    idx->fold.ids = fa.ids;
+    idx->fold.n_rows = fa.n_rows;
+    idx->fold.t = t;
+    idx->fold.B = (u32)h.k - t;
+    idx->fold.k = (u32)h.k;
+    idx->fold.enabled = 1;
+    return build_table<false>(idx, tt);
+}
+
 int select_device(fmsi_gpu_index *idx) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -356,11 +422,15 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
 
-    // Dictionary tier: narrow indexes with k <= 32. Depth = the largest t <= min(k, 15) with
-    // 4^t <= 4N (on average at most ~4 and at least ~0.25 rows per bucket) whose buckets (32 B each)
-    // plus rows (8 B per SA row, + 4 B per row of build scratch) fit in half of the free memory.
-    bool dict = want_dict != 0 && !idx->wide && h.k >= 1 && h.k <= 32 && h.n < (1ull << 32) - 256;
-    if (dict) {
+    // Dictionary tiers: narrow indexes with k <= 32. Bucket depth = the largest t <= min(k, 15) with
+    // 4^t <= 4N (on average at most ~4 and at least ~0.25 rows per bucket).
+    //   dict = 2 / auto: the strand-folded dictionary (fold.cuh) when its build fits in the free memory
+    //                    and what stays resident in 60 % of it;
+    //   dict = 1 / auto: else the SA-ordered dictionary (dict.cuh): buckets (32 B each) plus rows (8 B per
+    //                    SA row, + 4 B per row of build scratch) in half of the free memory;
+    //   else the plain suffix table.
+    const bool narrow = !idx->wide && h.k >= 1 && h.k <= 32 && h.n < (1ull << 32) - 256;
+    auto auto_depth = [&]() {
         int td = t;
         if (td < 0) {
             td = 1;
@@ -368,21 +438,52 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
         }
         if (td > h.k) td = h.k;
         if (td > 15) td = 15;
+        return td;
+    };
+    auto table_depth = [&](int cap) {  // largest depth with 4^t <= N, capped by k, `cap` and a quarter of the free memory
+        int tt = 0;
+        while (tt < cap && (1ull << (2 * (tt + 1))) <= h.n) ++tt;
+        if (tt > h.k) tt = h.k;
+        const size_t esz = idx->wide ? 16 : 8;
+        while (tt > 0 && ((1ull << (2 * tt)) * esz * 5 / 4) > free_b / 4) --tt;
+        return tt;
+    };
+    int rc = FMSI_GPU_OK;
+    bool done = false;
+    if (narrow && (want_dict < 0 || want_dict == 2)) {
+        int td = auto_depth();
+        auto fits = [&](int x) {
+            return fold_build_peak_bytes(h.n, (u32)x) <= free_b - free_b / 10 && fold_resident_bytes(h.n, (u32)x) <= free_b / 10 * 6;
+        };
+        while (td > 1 && t < 0 && !fits(td)) --td;
+        if (td >= 1 && h.k - td <= 30 && fits(td)) {
+            rc = build_fold(idx, (u32)td, (u32)table_depth(13));
+            if (rc == FMSI_GPU_OK) done = true;
+            else if (rc != FMSI_GPU_ERR_NOMEM) return rc;
+            else {  // release whatever the failed build left and try the next tier
+                for (void **p : {&idx->d_fbuckets, &idx->d_frows, &idx->d_fids}) {
+                    if (*p) cudaFree(*p);
+                    *p = nullptr;
+                }
+                idx->fold = FoldView{};
+                CU(cudaMemGetInfo(&free_b, &total_b));
+            }
+        }
+    }
+    if (!done && narrow && want_dict != 0) {
+        int td = auto_depth();
         const size_t rows_b = (size_t)h.n * 12;
         while (td > 1 && t < 0 && ((1ull << (2 * td)) * 40 + rows_b) > free_b / 2) --td;
-        if (td < 1 || ((1ull << (2 * td)) * 40 + rows_b) > free_b - free_b / 8) dict = false;
-        else t = td;
+        if (td >= 1 && ((1ull << (2 * td)) * 40 + rows_b) <= free_b - free_b / 8) {
+            rc = build_dict(idx, (u32)td);
+            if (rc) return rc;
+            done = true;
+        }
     }
-    int rc;
-    if (dict) {
-        rc = build_dict(idx, (u32)t);
-    } else {
+    if (!done) {
         // Suffix-table depth: auto = largest t with 4^t <= N (table no larger than ~2x the rank
         // array), capped by k, by 16 and by a quarter of the free device memory.
-        if (t < 0) {
-            t = 0;
-            while (t < 16 && (1ull << (2 * (t + 1))) <= h.n) ++t;
-        }
+        if (t < 0) t = table_depth(16);
         if (t > h.k) t = h.k;
         if (t > 16) t = 16;
         const size_t esz = idx->wide ? 16 : 8;
@@ -715,7 +816,8 @@ int fmsi_gpu_index_save(const fmsi_gpu_index *idx, const char *prefix) {
 int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     if (!idx) return FMSI_GPU_OK;
     cudaSetDevice(idx->device);
-    for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, (void *)idx->user.ctr, idx->user.ovf})
+    for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, idx->d_fbuckets, idx->d_frows, idx->d_fids,
+                    (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
     for (auto &s : idx->slots) {
         for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.ls.ctr, s.ls.ovf})
@@ -738,7 +840,8 @@ int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info
     info->k = idx->meta.k;
     info->has_klcp = idx->meta.has_klcp;
     info->prefix_t = (int32_t)idx->dev.t;
-    info->dict = (int32_t)idx->dict.enabled;
+    info->dict = idx->fold.enabled ? 2 : (int32_t)idx->dict.enabled;
+    info->dict_t = idx->fold.enabled ? (int32_t)idx->fold.t : idx->dict.enabled ? (int32_t)idx->dev.t : 0;
     info->wide = idx->wide;
     info->device = idx->device;
     return FMSI_GPU_OK;
@@ -919,7 +1022,8 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // Per-k-mer strand values do not depend on how they are computed (kLCP interval reuse is only a
     // shortcut), so when the dictionary tier is resident streamed chunks take it too: ~2 requests per
     // k-mer instead of an aux probe + an LF-step per k-mer and strand (profiles/r01d_modes_*.json).
-    const bool via_kmers = !streaming || (idx->dict.enabled && (u32)k == idx->dict.k && d.t && !idx->wide && n_results < (1ull << 32));
+    const bool via_kmers = !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k) ||
+                                                         (idx->dict.enabled && (u32)k == idx->dict.k && d.t && n_results < (1ull << 32))));
     const size_t n_words = (n_bases + 31) / 32 + 4;
     size_t aux_need = n_words * 8;
     const size_t kmers_off = aux_need;
@@ -1046,6 +1150,10 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->wide = src->wide;
     r->dev = src->dev;
     r->dict = src->dict;
+    r->fold = src->fold;
+    r->b_fbuckets = src->b_fbuckets;
+    r->b_frows = src->b_frows;
+    r->b_fids = src->b_fids;
     r->hbm_bytes = src->hbm_bytes;
     r->b_rank = src->b_rank;
     r->b_aux = src->b_aux;
@@ -1061,13 +1169,19 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
         (rc = replicate_array(&r->d_table, dev, src->d_table, src->device, src->b_table)) ||
         (rc = replicate_array(&r->d_sb, dev, src->d_sb, src->device, src->b_sb)) ||
         (rc = replicate_array(&r->d_counts, dev, src->d_counts, src->device, 32)) ||
-        (rc = replicate_array(&r->d_rows, dev, src->d_rows, src->device, src->b_rows)))
+        (rc = replicate_array(&r->d_rows, dev, src->d_rows, src->device, src->b_rows)) ||
+        (rc = replicate_array(&r->d_fbuckets, dev, src->d_fbuckets, src->device, src->b_fbuckets)) ||
+        (rc = replicate_array(&r->d_frows, dev, src->d_frows, src->device, src->b_frows)) ||
+        (rc = replicate_array(&r->d_fids, dev, src->d_fids, src->device, src->b_fids)))
         return bail(rc);
     r->dev.rank = reinterpret_cast<const RankBlock *>(r->d_rank);
     r->dev.aux = reinterpret_cast<const AuxBlock *>(r->d_aux);
     r->dev.table = r->d_table;
     r->dev.sb_base = reinterpret_cast<const u64 *>(r->d_sb);
     r->dict.rows = reinterpret_cast<const u64 *>(r->d_rows);
+    r->fold.buckets = r->d_fbuckets;
+    r->fold.rows = reinterpret_cast<const u64 *>(r->d_frows);
+    r->fold.ids = reinterpret_cast<const uint2 *>(r->d_fids);
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(FMSI_GPU_ERR_CUDA, "cudaSetDevice"));
     if ((rc = alloc_slots(r.get()))) return bail(rc);
     *out = r.release();

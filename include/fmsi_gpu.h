@@ -56,7 +56,9 @@ typedef struct fmsi_gpu_index fmsi_gpu_index;
 typedef struct {
     int32_t prefix_t;      /* depth of the k-mer suffix lookup table; -1 = auto, 0 = none */
     int32_t sb_shift_log2; /* test hook: superblock size (log2 blocks); 0 = auto */
-    int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto, 0 = off, 1 = on */
+    int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto (2, else 1, else 0 as memory allows),
+                            * 0 = off (backward search), 1 = SA-ordered dictionary (one probe per strand search),
+                            * 2 = strand-folded dictionary (one probe per k-mer) */
     int32_t reserved32;
     int64_t reserved[5];
 } fmsi_gpu_options;
@@ -72,8 +74,9 @@ typedef struct {
     int32_t prefix_t;
     int32_t wide;        /* 1 when N >= 2^32 (64-bit positions on device) */
     int32_t device;
-    int32_t dict;        /* 1 when the dictionary tier is resident */
-    int32_t reserved[6];
+    int32_t dict;        /* resident dictionary tier: 0 none, 1 SA-ordered, 2 strand-folded */
+    int32_t dict_t;      /* bucket depth of that tier (bases) */
+    int32_t reserved[5];
 } fmsi_gpu_index_info;
 
 const char *fmsi_gpu_last_error(void);

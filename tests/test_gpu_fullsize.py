@@ -20,16 +20,17 @@ N_GENOME = int(os.environ.get("FMSI_TEST_FULLSIZE", 3_100_000_000))
 K = 31
 
 
-@pytest.fixture(scope="module")
-def human():
+@pytest.fixture(scope="module", params=[2, 1], ids=["fold", "dict"])
+def human(request):
     torch = pytest.importorskip("torch")
     from bench import device_genome, device_queries
     dev = torch.device("cuda", 0)
     free, _ = torch.cuda.mem_get_info(dev)
-    if free < 110e9 * (N_GENOME / 3.1e9):
+    if free < 170e9 * (N_GENOME / 3.1e9):
         pytest.skip("not enough free device memory for the full-size index")
     codes, ascii_ = device_genome(N_GENOME, 4, K, dev)
-    gd = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=1)
+    gd = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=request.param)
+    assert gd.dict_kind == request.param
     gb = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=0)
     del ascii_
     yield torch, dev, codes, gd, gb, device_queries

@@ -105,15 +105,18 @@ def _random_kmers(rng, ms_codes, k, n):
 
 
 @pytest.mark.parametrize("case", golden_cases())
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3", "dict_auto", "fold_t1", "fold_t3"])
 def test_device_matches_oracle(case, variant):
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
     k = meta["k"]
     # dict_t1 / dict_t3: shallow dictionary buckets hold far more rows than fit a sector, which drives
-    # the ROWS phase and the overflow list -> backward-search fixup launch of dict.cuh.
+    # the ROWS phase and the overflow list -> backward-search fixup launch of dict.cuh. fold_t1 / fold_t3: the
+    # same for the strand-folded dictionary (fold.cuh): every bucket is binary-searched in rows[].
+    # auto = strand-folded dictionary at the automatic depth; dict_auto = SA-ordered dictionary there.
     kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "nodict": {"dict": 0},
-          "dict_t1": {"dict": 1, "prefix_t": 1}, "dict_t3": {"dict": 1, "prefix_t": 3}}[variant]
+          "dict_t1": {"dict": 1, "prefix_t": 1}, "dict_t3": {"dict": 1, "prefix_t": 3}, "dict_auto": {"dict": 1},
+          "fold_t1": {"dict": 2, "prefix_t": 1}, "fold_t3": {"dict": 2, "prefix_t": 3}}[variant]
     if variant != "auto" and case not in ("syn_k31_max", "syn_k9_min", "syn_k5_min", "quirks_k3", "data_k13", "syn_k32"):
         pytest.skip("variants run on a subset")
     prefix = os.path.join(d, "ms.fa")
@@ -121,7 +124,10 @@ def test_device_matches_oracle(case, variant):
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.n == oi.n and gi.k == k and gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
     assert gi.wide == (variant == "wide")
-    assert gi.dict == (variant in ("auto", "dict_t1", "dict_t3") and k <= 32)
+    assert gi.dict == (variant not in ("t0", "wide", "nodict") and k <= 32)
+    if gi.dict:  # the tier asked for, unless the payload would not fit a row (k - t > 30: k = 32 at depth 1)
+        fold_ok = k - gi.dict_t <= 30
+        assert gi.dict_kind == (2 if variant in ("auto", "fold_t1", "fold_t3") and fold_ok else 1)
     rng = np.random.default_rng(zlib.crc32(case.encode()))
     N = gi.n
     # rank / update_range
@@ -205,10 +211,11 @@ def test_dictionary_tier_on_repetitive_index(tmp_path):
                                 synth.pack_rows(tails), synth.revcomp_packed(synth.pack_rows(tails), k),
                                 synth.pack_rows(np.stack([np.full(k, c, np.uint8) for c in range(4)]))])
         strs = None
-        for kw in ({}, {"dict": 1, "prefix_t": 1}, {"dict": 1, "prefix_t": 4}, {"dict": 1, "prefix_t": 7}):
+        for kw in ({}, {"dict": 2, "prefix_t": 1}, {"dict": 2, "prefix_t": 4}, {"dict": 2, "prefix_t": 7}, {"dict": 1},
+                   {"dict": 1, "prefix_t": 1}, {"dict": 1, "prefix_t": 4}, {"dict": 1, "prefix_t": 7}):
             gd = fg.Index.load(fa, use_klcp=False, **kw)
             gb = fg.Index.load(fa, use_klcp=False, dict=0)
-            assert gd.dict and not gb.dict
+            assert gd.dict and not gb.dict and gd.dict_kind == kw.get("dict", 2)
             for mode, out, omode, oord in ((fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False),
                                            (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
                 want = oi.query_packed(kmers, k, omode, oord)
