@@ -477,17 +477,20 @@ def main():
         if os.path.exists(apath):
             alg = json.load(open(apath))
     if alg:
-        # one dict_query_kernel (or query_kmers_kernel) launch per step dominates; the fixup launch over
-        # the overflow list exits at once on this workload and the 32-byte memset is negligible
+        # one fold_query_kernel (dict_query_kernel / query_kmers_kernel for the other tiers) launch per step
+        # is the step; the 32-byte cursor memset in front of it is negligible
         launch_ms = ms_per_step
         achieved = alg["bytes"] * batch / (launch_ms / 1e3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(args.workload)
+            if tj and tj.get("kernel", "").split("<")[0] != {2: "fold_query_kernel", 1: "dict_query_kernel", 0: "query_kmers_kernel"}[gi.dict_kind]:
+                tj = None  # the stored ncu capture is of another tier's kernel
             if tj and tj.get("batch"):
                 traffic = tj["dram_bytes_per_launch"] * (batch / tj["batch"])
-        kernel_name = "dict_query_kernel<ALL,PRESENCE,LAZY>" if gi.dict else "query_kmers_kernel<ALL,PRESENCE,LAZY>"
+        kernel_name = {2: "fold_query_kernel<ALL,PRESENCE,LAZY>", 1: "dict_query_kernel<ALL,PRESENCE,LAZY>",
+                       0: "query_kmers_kernel<ALL,PRESENCE,LAZY>"}[gi.dict_kind]
         hw = None
         if traffic:
             # what the hardware actually did (ncu, profiles/traffic.json): DRAM bytes moved per second
@@ -504,8 +507,8 @@ def main():
                                          rank_sectors_per_kmer=round(alg["rank_sectors"], 2), mask_sectors_per_kmer=round(alg["mask_sectors"], 2)),
                         note="algorithmic bytes = the REFERENCE algorithm's dependent sector probes per k-mer (SURVEY 8d: 32 B per "
                              "rank/mask probe + 8 B query + 1 B result), counted by the instrumented oracle on the same query "
-                             "distribution; frac > 1 because the dictionary tier answers a strand search in ~1 request instead of "
-                             "k-t LF-steps - `hardware` says how close the kernel runs to the memory system's own limits")
+                             "distribution; frac > 1 because the strand-folded dictionary answers a k-mer (both strands) in ~1 request "
+                             "instead of 2 x (k-t) LF-steps - `hardware` says how close the kernel runs to the memory system's own limits")
 
     info = gi.info
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
@@ -513,7 +516,7 @@ def main():
                 config=dict(workload=args.workload, desc=wl["desc"], k=k, superstring=wl["how"], kmers_per_step_per_gpu=batch,
                             mode="query -O (MODE_ALL, STRANDS_LAZY)", parallelism=f"replicas x{world}, queries sharded, no collective",
                             l2="inputs larger than L2: 2 alternating batches of %d MiB" % (batch * 8 >> 20), n_bwt=int(info.n_bwt),
-                            prefix_t=int(info.prefix_t), dictionary_tier=bool(info.dict), index_hbm_bytes=int(info.hbm_bytes), index_setup_s=round(load_s, 2),
+                            prefix_t=int(info.prefix_t), dictionary_tier=int(info.dict), dictionary_depth=int(info.dict_t), index_hbm_bytes=int(info.hbm_bytes), index_setup_s=round(load_s, 2),
                             frac_present=round(frac_present, 4), e2e_equals_device=same, parity_vs_oracle_sample=parity),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=batch * 8, d2h_bytes_per_step=batch * 1),
