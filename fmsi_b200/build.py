@@ -69,6 +69,10 @@ def build_tools(force: bool = False, verbose: bool = True) -> None:
     exe = os.path.join(BIN, "randbw")
     if force or _newer(exe, [src]):
         _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src], verbose)
+    src = os.path.join(CSRC, "tools", "fasta_dump.cpp")  # input-parser test tool (tests/test_fasta_blocks.py)
+    exe = os.path.join(BIN, "fasta_dump")
+    if force or _newer(exe, [src, os.path.join(CSRC, "fasta_blocks.hpp")]):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-lz"], verbose)
 
 
 def build_oracle(verbose: bool = True) -> None:

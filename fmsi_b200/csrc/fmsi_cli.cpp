@@ -6,13 +6,15 @@
 // than or/all) is out of scope for the GPU engine and is forwarded to the unchanged reference
 // binary when $FMSI_REFERENCE_BIN points at one.
 //
-// Flow per batch of records:  kseq-compatible reader -> valid ACGT runs -> GPU chunks
-//   -> fmsi_gpu_query_chunks (both strands) -> strand-predictor replay (predictor.hpp, exact
-//   reference semantics whatever the index/mask) -> text formatter.
+// Flow per block of records:  record-boundary scan (fasta_blocks.hpp; the only serial input step)
+//   -> kseq-exact parse -> valid ACGT runs -> GPU chunks -> fmsi_gpu_query_chunks (both strands)
+//   -> strand-predictor replay (predictor.hpp, exact reference semantics whatever the index/mask)
+//   -> text formatter.
 // $FMSI_GPU_STRANDS=lazy skips the replay (forward strand first, reverse complement only if
 // undecided): identical output whenever the strand predictor cannot change results (or-mode
 // always; -O on max-ones masks; lookup when no k-mer is ON on both strands), and much cheaper for -S.
 #include <fmsi_gpu.h>
+#include <malloc.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -21,7 +23,9 @@
 #include <cmath>
 #include <condition_variable>
 #include <deque>
+#include <future>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdint>
@@ -33,6 +37,7 @@
 #include <string>
 #include <vector>
 
+#include "fasta_blocks.hpp"
 #include "predictor.hpp"
 
 namespace {
@@ -119,100 +124,6 @@ int forward_to_reference(int argc, char *argv[]) {
     std::cerr << "ERROR: cannot execute " << ref << std::endl;
     return 1;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Record reader with the semantics of the reference's kseq (src/kseq.h:173-226) over zlib
-// (plain or gzip, file or stdin — parser.h:14-27).
-class RecordReader {
-  public:
-    explicit RecordReader(const std::string &path) {
-        FILE *in = path == "-" ? stdin : std::fopen(path.c_str(), "r");
-        if (!in) throw std::invalid_argument("couldn't open file " + path);  // uncaught in the reference too
-        fp_ = gzdopen(fileno(in), "r");
-        gzbuffer(fp_, 1 << 20);
-        buf_.resize(1 << 22);
-    }
-    ~RecordReader() {
-        if (fp_) gzclose(fp_);
-    }
-    // Returns sequence length (>= 0), or a negative code: -1 EOF, -2 truncated quality.
-    // name and seq are overwritten (their capacity is reused from record to record).
-    int64_t next(std::string &name, std::string &seq) {
-        int c;
-        if (last_char_ == 0) {
-            while ((c = getc()) >= 0 && c != '>' && c != '@') {}
-            if (c < 0) return c;
-            last_char_ = c;
-        }
-        seq.clear();
-        qual_len_ = 0;
-        int64_t r = getuntil(kSpace, name, &c, false);
-        if (r < 0) return r;
-        if (c != '\n') getuntil(kLine, scratch_, nullptr, false);  // comment
-        while ((c = getc()) >= 0 && c != '>' && c != '+' && c != '@') {
-            if (c == '\n') continue;
-            seq.push_back((char)c);
-            getuntil(kLine, seq, nullptr, true);
-        }
-        if (c == '>' || c == '@') last_char_ = c;
-        if (c != '+') return (int64_t)seq.size();
-        while ((c = getc()) >= 0 && c != '\n') {}
-        if (c == -1) return -2;
-        scratch_.clear();
-        while (getuntil(kLine, scratch_, nullptr, true) >= 0 && scratch_.size() < seq.size()) {}
-        last_char_ = 0;
-        if (seq.size() != scratch_.size()) return -2;
-        return (int64_t)seq.size();
-    }
-
-  private:
-    enum { kSpace = 0, kLine = 2 };
-    bool fill() {
-        if (eof_) return false;
-        int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-        begin_ = 0;
-        end_ = n > 0 ? (size_t)n : 0;
-        if (n <= 0) eof_ = true;
-        return n > 0;
-    }
-    int getc() {
-        if (begin_ >= end_ && !fill()) return -1;
-        return (unsigned char)buf_[begin_++];
-    }
-    int64_t getuntil(int delimiter, std::string &str, int *dret, bool append) {
-        bool gotany = false;
-        if (dret) *dret = 0;
-        if (!append) str.clear();
-        for (;;) {
-            if (begin_ >= end_ && !fill()) break;
-            size_t i;
-            if (delimiter == kLine) {
-                const char *sep = (const char *)memchr(buf_.data() + begin_, '\n', end_ - begin_);
-                i = sep ? (size_t)(sep - buf_.data()) : end_;
-            } else {
-                for (i = begin_; i < end_; ++i)
-                    if (isspace((unsigned char)buf_[i])) break;
-            }
-            gotany = true;
-            str.append(buf_.data() + begin_, i - begin_);
-            begin_ = i + 1;
-            if (i < end_) {
-                if (dret) *dret = (unsigned char)buf_[i];
-                break;
-            }
-        }
-        if (!gotany && eof_) return -1;
-        if (delimiter == kLine && str.size() > 1 && str.back() == '\r') str.pop_back();
-        return (int64_t)str.size();
-    }
-    gzFile fp_ = nullptr;
-    std::vector<char> buf_;
-    size_t begin_ = 0, end_ = 0;
-    bool eof_ = false;
-    int last_char_ = 0;
-    size_t qual_len_ = 0;
-    std::string scratch_;
-};
 
 inline bool is_acgt(unsigned char ch) {  // nucleotideToInt[ch] != 4, src/kmers.h:3-20
     switch (ch) {
@@ -304,14 +215,17 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
 
 // ---------------------------------------------------------------------------------------------
 // Host pipeline. The reference handles one record at a time on one thread (main.cpp:328-373); here
-//   reader (main thread)  : kseq-compatible parsing + layout into batches
-//   workers (W threads)   : GPU query of a batch on a free index replica; later its text formatting
-//   sequencer (1 thread)  : strand-predictor replay, strictly in batch order (the predictor's state
+//   reader (main thread)  : reads the file and cuts it into blocks of whole records (fasta_blocks.hpp:
+//                           a memchr per line) — starts while the index is still loading
+//   workers (W threads)   : per block: kseq-exact parsing + layout; GPU query on a free index replica;
+//                           later its text formatting
+//   sequencer (1 thread)  : strand-predictor replay, strictly in block order (the predictor's state
 //                           runs through every k-mer of the run) — skipped in lazy mode
-//   writer (1 thread)     : stdout, in batch order
-// With $FMSI_GPU_DEVICES the replicas live on several GPUs and batches go to whichever is free.
+//   writer (1 thread)     : stdout, in block order
+// With $FMSI_GPU_DEVICES the replicas live on several GPUs and blocks go to whichever is free.
 struct Job {
     uint64_t seq = 0;
+    std::vector<char> block;  // raw input: whole records
     Batch b;
     std::vector<uint8_t> raw8, fin8;
     std::vector<int64_t> raw64, fin64;
@@ -341,7 +255,7 @@ class Pipeline {
         cv_.wait(lk, [&] { return inflight_ < max_inflight_ || failed_; });
         job->seq = submitted_++;
         ++inflight_;
-        tasks_.push_back({job, false});
+        tasks_.push_back({job, kParse});
         cv_.notify_all();
     }
     bool finish() {
@@ -355,9 +269,10 @@ class Pipeline {
     }
 
   private:
+    enum Stage { kParse, kQuery, kFormat };
     struct Task {
         Job *job;
-        bool format;
+        Stage stage;
     };
     void fail(const std::string &msg) {
         std::unique_lock<std::mutex> lk(mu_);
@@ -373,26 +288,34 @@ class Pipeline {
                 std::unique_lock<std::mutex> lk(mu_);
                 for (;;) {
                     if (failed_) return;
-                    // formatting first (drains memory), then queries when a replica is free
-                    auto it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return x.format; });
+                    // formatting first (drains memory), then queries when a replica is free, then parsing
+                    auto it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return x.stage == kFormat; });
                     if (it == tasks_.end()) {
                         member = free_member();
-                        if (member >= 0) it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return !x.format; });
+                        if (member >= 0) it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return x.stage == kQuery; });
                     }
+                    if (it == tasks_.end()) it = std::find_if(tasks_.begin(), tasks_.end(), [](const Task &x) { return x.stage == kParse; });
                     if (it != tasks_.end()) {
                         t = *it;
                         tasks_.erase(it);
-                        if (!t.format) member_busy_[member] = true;
+                        if (t.stage == kQuery) member_busy_[member] = true;
                         break;
                     }
                     if (closed_ && written_ == submitted_) return;
                     cv_.wait(lk);
                 }
             }
-            if (t.format) {
+            if (t.stage == kFormat) {
                 format(*t.job);
                 std::unique_lock<std::mutex> lk(mu_);
                 formatted_[t.job->seq] = t.job;
+                cv_.notify_all();
+            } else if (t.stage == kParse) {
+                parse(*t.job);
+                std::unique_lock<std::mutex> lk(mu_);
+                // queries leave in block order so that a replica never idles behind a late block
+                auto at = std::find_if(tasks_.begin(), tasks_.end(), [&](const Task &x) { return x.stage == kQuery && x.job->seq > t.job->seq; });
+                tasks_.insert(at, {t.job, kQuery});
                 cv_.notify_all();
             } else {
                 const bool ok = query(*t.job, members_[member]);
@@ -422,7 +345,7 @@ class Pipeline {
             if (!cfg_.lazy) replay(*job);
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                tasks_.push_front({job, true});
+                tasks_.push_front({job, kFormat});
                 cv_.notify_all();
             }
             ++next;
@@ -449,6 +372,14 @@ class Pipeline {
             }
             ++next;
         }
+    }
+
+    // ms_query's record loop (main.cpp:328-373) over one block of whole records
+    void parse(Job &j) {
+        fmsi::MemRecordReader reader(j.block.data(), j.block.size());
+        std::string name, seq;
+        while (reader.next(name, seq) >= 0) layout_record(j.b, name, seq, cfg_.k, cfg_.streaming);
+        std::vector<char>().swap(j.block);
     }
 
     bool query(Job &j, fmsi_gpu_index *idx) {
@@ -589,6 +520,73 @@ class Pipeline {
     bool closed_ = false, failed_ = false;
 };
 
+// Reads ahead of the pipeline on its own thread (also while the index is still being loaded): blocks of
+// whole records, bounded by `max_bytes` of queued input.
+class BlockPrefetcher {
+  public:
+    BlockPrefetcher(const std::string &path, size_t block_bytes, size_t max_bytes)
+        : st_(std::make_shared<State>(path, block_bytes, max_bytes)) {}
+    ~BlockPrefetcher() {
+        if (!thread_.joinable()) return;
+        bool finished;
+        {
+            std::unique_lock<std::mutex> lk(st_->mu);
+            st_->stop = true;
+            finished = st_->done;
+            st_->cv.notify_all();
+        }
+        if (finished) thread_.join();
+        else thread_.detach();  // may sit in a blocking read of stdin; it owns its state
+    }
+    void start() {
+        std::shared_ptr<State> st = st_;
+        thread_ = std::thread([st] {
+            std::vector<char> block;
+            for (;;) {
+                const bool got = st->src.next(block);
+                std::unique_lock<std::mutex> lk(st->mu);
+                if (!got) {
+                    st->done = true;
+                    st->cv.notify_all();
+                    return;
+                }
+                st->cv.wait(lk, [&] { return st->stop || st->queued_bytes < st->max_bytes; });
+                if (st->stop) {
+                    st->done = true;
+                    return;
+                }
+                st->queued_bytes += block.size();
+                st->queue.emplace_back(std::move(block));
+                block = std::vector<char>();
+                st->cv.notify_all();
+            }
+        });
+    }
+    bool pop(std::vector<char> &out) {
+        std::unique_lock<std::mutex> lk(st_->mu);
+        st_->cv.wait(lk, [&] { return st_->done || !st_->queue.empty(); });
+        if (st_->queue.empty()) return false;
+        out = std::move(st_->queue.front());
+        st_->queue.pop_front();
+        st_->queued_bytes -= out.size();
+        st_->cv.notify_all();
+        return true;
+    }
+
+  private:
+    struct State {
+        State(const std::string &path, size_t block_bytes, size_t max_b) : src(path, block_bytes), max_bytes(max_b) {}
+        fmsi::BlockSource src;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<std::vector<char>> queue;
+        size_t queued_bytes = 0, max_bytes;
+        bool done = false, stop = false;
+    };
+    std::shared_ptr<State> st_;
+    std::thread thread_;
+};
+
 int ms_query(int argc, char *argv[], bool output_orders) {
     bool usage = false;
     int c;
@@ -656,6 +654,43 @@ int ms_query(int argc, char *argv[], bool output_orders) {
         }
         if (!devices.empty()) device = devices[0];
     }
+    if (devices.size() <= 1) {
+        // One GPU: hide the others from the CUDA runtime — driver initialisation is paid per visible
+        // device (seconds on an 8-GPU box) and a short query run is dominated by it.
+        const char *cvd = std::getenv("CUDA_VISIBLE_DEVICES");
+        std::string pick;
+        if (!cvd) {
+            pick = std::to_string(device);
+        } else {
+            const std::string v = cvd;
+            size_t at = 0;
+            for (int ord = 0; at <= v.size(); ++ord) {
+                size_t end = v.find(',', at);
+                if (end == std::string::npos) end = v.size();
+                if (ord == device) {
+                    pick = v.substr(at, end - at);
+                    break;
+                }
+                at = end + 1;
+            }
+        }
+        if (!pick.empty()) {
+            setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+            device = 0;
+        }
+    }
+    // The query file is opened (and, unless it is stdin, read ahead) while the index loads; a failure to
+    // open it is reported where the reference reports it: after the index checks (main.cpp:302-327).
+    size_t batch_bases = 16u << 20;
+    if (const char *e = std::getenv("FMSI_GPU_BATCH_BASES")) batch_bases = (size_t)atoll(e);
+    std::unique_ptr<BlockPrefetcher> input;
+    std::string open_error;
+    try {
+        input.reset(new BlockPrefetcher(query_fn, batch_bases, (size_t)1 << 30));
+    } catch (const std::invalid_argument &e) {
+        open_error = e.what();
+    }
+    if (input && query_fn != "-") input->start();
     fmsi_gpu_index *idx = nullptr;
     // The dictionary tier costs ~2 s of build time at human scale and pays off only beyond ~10^10
     // k-mers per run, far above what FASTA parsing can feed: off unless $FMSI_GPU_DICT=1.
@@ -733,29 +768,21 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     if (timing) std::cerr << "[fmsi timing] index load + replicas: " << since(t_start) << " s" << std::endl;
     const auto t_query = std::chrono::steady_clock::now();
     bool ok;
+    if (!input) throw std::invalid_argument(open_error);  // uncaught in the reference too (parser.h:21-23)
+    if (query_fn == "-") input->start();
     {
-        RecordReader reader(query_fn);  // throws std::invalid_argument when the file cannot be opened (as the reference)
         Pipeline pipe(cfg, members, workers);
-        std::string name, seq;
-        size_t batch_bases = 16u << 20;
-        if (const char *e = std::getenv("FMSI_GPU_BATCH_BASES")) batch_bases = (size_t)atoll(e);
-        size_t pending = 0;
         Job *job = new Job();
-        while (reader.next(name, seq) >= 0) {
-            layout_record(job->b, name, seq, k, cfg.streaming);
-            pending += seq.size() + 1;
-            if (pending >= batch_bases) {
-                pipe.submit(job);
-                job = new Job();
-                pending = 0;
-            }
+        while (input->pop(job->block)) {
+            pipe.submit(job);
+            job = new Job();
         }
-        if (!job->b.records.empty()) pipe.submit(job);
-        else delete job;
+        delete job;
         if (timing) std::cerr << "[fmsi timing] reader done: " << since(t_query) << " s" << std::endl;
         ok = pipe.finish();
         if (timing) std::cerr << "[fmsi timing] pipeline drained: " << since(t_query) << " s" << std::endl;
     }
+    input.reset();
     std::fflush(stdout);
     fmsi_gpu_pool_free(pool);
     fmsi_gpu_index_free(idx);
@@ -766,6 +793,10 @@ int ms_query(int argc, char *argv[], bool output_orders) {
 }  // namespace
 
 int main(int argc, char *argv[]) {
+    // blocks, layouts and output buffers are tens of MB each and short-lived: keep them in the heap
+    // instead of mmap/munmap + page faults for every one of them
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, -1);
     if (argc < 2) return usage();
     const std::string op = argv[1];
     int ret;

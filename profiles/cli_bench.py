@@ -33,6 +33,7 @@ def timed(cmd, env=None, stdout=None):
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(f"{cmd}: {r.stderr.decode()[-500:]}")
+    timed.last_stderr = r.stderr.decode(errors="replace")
     return dt
 
 
@@ -78,10 +79,15 @@ def main():
              ("lookup -S (150 bp reads)", ["lookup", "-S"], rfa, sub_r, n_read_kmers, args.ref_reads * (150 - k + 1))]
     for name, flags, qf, subf, units, sub_units in cases:
         row = {"case": name}
-        for label, env in (("exact", None), ("lazy", dict(os.environ, FMSI_GPU_STRANDS="lazy"))):
+        for label, env in (("exact", dict(os.environ, FMSI_GPU_TIMING="1")), ("lazy", dict(os.environ, FMSI_GPU_STRANDS="lazy", FMSI_GPU_TIMING="1"))):
             dt = timed([CLI, *flags, "-q", qf, prefix], env=env)
             row[f"{label}_s"] = round(dt, 3)
             row[f"{label}_mkmers_s"] = round(units / dt / 1e6, 2)
+            # the CLI's own phase clock: index load (incl. CUDA context creation), then the query pipeline
+            ph = {ln.split("] ")[1].split(":")[0]: float(ln.rsplit(":", 1)[1].split()[0]) for ln in timed.last_stderr.splitlines() if ln.startswith("[fmsi timing]")}
+            row[f"{label}_phases_s"] = ph
+            if "pipeline drained" in ph and ph["pipeline drained"] > 0:
+                row[f"{label}_mkmers_s_after_load"] = round(units / ph["pipeline drained"] / 1e6, 2)
         # parity + reference rate on the subsample
         a = os.path.join(d, "a.txt")
         b = os.path.join(d, "b.txt")

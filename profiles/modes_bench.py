@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Device-resident throughput of every query mode (not bench.py's headline line): single k-mers in
--O / or / lookup mode through the dictionary tier and through plain backward search, and 150 bp reads
+-O / or / lookup mode through the strand-folded dictionary, the SA-ordered dictionary and plain backward search, and 150 bp reads
 with 1 % substitutions through the kLCP streaming kernel vs the single-k-mer path, LAZY and BOTH
 strands. BASELINE configs[1] / configs[2] shapes on a GPU-built index.
 
@@ -41,6 +41,10 @@ def main():
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--copies", type=int, default=1, help="pangenome-like: this many mutated copies of the genome, concatenated")
     ap.add_argument("--snp", type=float, default=0.01, help="per-base substitution rate of every copy")
+    ap.add_argument("--variants", type=int, default=0,
+                    help="BASELINE configs[4] at its named scale: a masked superstring of the base genome + this many SNP variants, "
+                         "each contributing its k new k-mers as a 2k-1 window (ON) joined to the next by k-1 OFF positions")
+    ap.add_argument("--tiers", default="fold,dict,backward")
     args = ap.parse_args()
     k = args.k
     dev = torch.device("cuda", 0)
@@ -58,9 +62,45 @@ def main():
         ascii_ = lut0[codes.long()]
         ascii_[codes.numel() - (k - 1):] += 32
         args.genome = codes.numel()
-    out = {"genome": args.genome, "copies": args.copies, "k": k, "rows": []}
+    if args.variants > 0:
+        # Pangenome as a masked superstring (what kmercamel emits for many near-identical genomes): the base genome
+        # once, then for every SNP the window of 2k-1 bases around it (its k new k-mers, mask ON), windows back to
+        # back, so the k-1 k-mers that straddle two windows are OFF occurrences: a mask-heavy superstring whose
+        # distinct represented k-mers number ~ genome + variants * k.
+        gen0 = torch.Generator(device=dev)
+        gen0.manual_seed(78)
+        V, W = args.variants, 2 * k - 1
+        n_total = args.genome + V * W
+        sup = torch.empty(n_total, dtype=torch.uint8, device=dev)
+        upper = torch.ones(n_total, dtype=torch.bool, device=dev)
+        sup[:args.genome] = codes
+        upper[args.genome - (k - 1):args.genome] = False  # k-mers running from the genome into the first window
+        step = 1 << 22
+        ar = torch.arange(W, device=dev)
+        for a in range(0, V, step):
+            b = min(V, a + step)
+            pos = torch.randint(k - 1, args.genome - k, (b - a,), device=dev, generator=gen0)
+            win = codes[(pos[:, None] + (ar[None, :] - (k - 1)))]
+            shift = torch.randint(1, 4, (b - a,), device=dev, generator=gen0, dtype=torch.uint8)
+            win[:, k - 1] = (win[:, k - 1] + shift) & 3
+            sup[args.genome + a * W:args.genome + b * W] = win.reshape(-1)
+            del win, pos, shift
+        wpos = (torch.arange(V * W, device=dev) % W)
+        upper[args.genome:] = wpos < k  # the k k-mers that start inside a window's first k positions contain the SNP
+        del wpos
+        upper[n_total - (k - 1):] = False
+        lut0 = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+        ascii_ = lut0[sup.long()] + (~upper).to(torch.uint8) * 32
+        codes = sup
+        on_positions = upper
+        args.genome = n_total
+        del sup
+        torch.cuda.empty_cache()
+    out = {"genome": args.genome, "copies": args.copies, "variants": args.variants, "k": k, "rows": []}
     idx = {}
-    for name, dct in (("dict", 1), ("backward", 0)):
+    for name, dct in (("fold", 2), ("dict", 1), ("backward", 0)):
+        if name not in args.tiers.split(","):
+            continue
         t0 = time.time()
         idx[name] = fg.Index.build(ascii_.data_ptr(), k, with_klcp=True, device=0, n=args.genome, mem=fg.MEM_DEVICE, dict=dct)
         print(f"index[{name}]: built in {time.time() - t0:.2f}s, t={idx[name].prefix_t}, hbm={idx[name].hbm_bytes / 1e9:.2f} GB", flush=True)
@@ -72,7 +112,7 @@ def main():
     for label, mode, outp in (("query -O", fg.MODE_ALL, fg.OUT_PRESENCE), ("query (or)", fg.MODE_OR, fg.OUT_PRESENCE), ("lookup", fg.MODE_OR, fg.OUT_ORDERS)):
         for sname, strands in (("lazy", fg.STRANDS_LAZY), ("both", fg.STRANDS_BOTH)):
             row = {"case": f"single 31-mers, {label}, {sname}"}
-            for name in ("dict", "backward"):
+            for name in idx:
                 dst = res8 if outp == fg.OUT_PRESENCE else res64
                 dt = timed(lambda: idx[name].query_kmers_ptr(q.data_ptr(), n, dst.data_ptr(), k, mode, outp, strands, fg.MEM_DEVICE, stream))
                 row[f"{name}_gkmers_s"] = round(n / dt / 1e9, 2)
@@ -111,7 +151,7 @@ def main():
     for label, mode, outp in (("query -O", fg.MODE_ALL, fg.OUT_PRESENCE), ("lookup", fg.MODE_OR, fg.OUT_ORDERS)):
         for sname, strands in (("lazy", fg.STRANDS_LAZY), ("both", fg.STRANDS_BOTH)):
             row = {"case": f"150 bp reads (1% subs), {label}, {sname}"}
-            for name in ("dict", "backward"):
+            for name in idx:
                 for sm, streaming in (("S", 1), ("single", 0)):
                     dst = r8 if outp == fg.OUT_PRESENCE else r64
 
