@@ -721,13 +721,9 @@ int ms_query(int argc, char *argv[], bool output_orders) {
         return usage_query(output_orders);
     }
     if (k == 0) k = index_k;
-    if (k < 1 || k > 32) {
-        // packed 2-bit k-mers live in one 64-bit word on the device; longer k goes to the reference
+    if (k < 1 || k > FMSI_GPU_MAX_K) {
+        std::cerr << "ERROR: k must be between 1 and " << FMSI_GPU_MAX_K << " (index has k = " << k << ")." << std::endl;
         fmsi_gpu_index_free(idx);
-        const char *ref = std::getenv("FMSI_REFERENCE_BIN");
-        if (ref && *ref) return -2;
-        std::cerr << "ERROR: the GPU query engine supports k <= 32 (index has k = " << k
-                  << "); set FMSI_REFERENCE_BIN to forward such queries to the reference binary." << std::endl;
         return 1;
     }
 

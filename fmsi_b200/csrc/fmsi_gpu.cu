@@ -18,6 +18,7 @@
 #include "index_build.cuh"
 #include "index_convert.cuh"
 #include "index_layout.hpp"
+#include "longk_kernels.cuh"
 #include "query_kernels.cuh"
 #include "stream_kernels.cuh"
 
@@ -998,7 +999,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
                       const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                       size_t n_results, int k, void *results, int mem, void *stream) {
     if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
-    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
+    if (k < 1 || k > FMSI_GPU_MAX_K) return fail(FMSI_GPU_ERR_K, "k must be in [1, FMSI_GPU_MAX_K]");
     if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL && !(mode == FMSI_GPU_MODE_GENERAL_ && gf)) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
         (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
@@ -1022,7 +1023,9 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // Per-k-mer strand values do not depend on how they are computed (kLCP interval reuse is only a
     // shortcut), so when the dictionary tier is resident streamed chunks take it too: ~2 requests per
     // k-mer instead of an aux probe + an LF-step per k-mer and strand (profiles/r01d_modes_*.json).
-    const bool via_kmers = !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k) ||
+    // k > 32: queries are start positions into the packed text (longk_kernels.cuh), with or without -S.
+    const bool longk = k > 32;
+    const bool via_kmers = longk || !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k) ||
                                                          (idx->dict.enabled && (u32)k == idx->dict.k && d.t && n_results < (1ull << 32))));
     const size_t n_words = (n_bases + 31) / 32 + 4;
     size_t aux_need = n_words * 8;
@@ -1030,7 +1033,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     if (via_kmers) aux_need += n_results * 8;
     if (on_host) {
         CU(cudaEventSynchronize(s.done));
-        if (streaming) {
+        if (streaming && !longk) {
             // host-side validation of the per-chunk k-mer bound
             for (size_t c = 0; c < n_chunks; ++c)
                 if (chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS)
@@ -1058,7 +1061,15 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
 
-    if (via_kmers) {
+    if (longk) {
+        u64 *d_starts = (u64 *)((char *)s.d_aux + kmers_off);
+        extract_starts_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_starts);
+        CU(cudaGetLastError());
+        if ((rc = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_starts, n_results, d_results,
+                                on_host ? s.ls.ctr : idx->user.ctr, st)))
+            return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+        g_launches.fetch_add(2);
+    } else if (via_kmers) {
         u64 *d_kmers = (u64 *)((char *)s.d_aux + kmers_off);
         extract_kmers_kernel<<<blocks_for(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
         CU(cudaGetLastError());
@@ -1278,7 +1289,7 @@ int fmsi_gpu_pool_query_chunks(fmsi_gpu_pool *pool, int mode, int output, int st
     if (!pool || pool->members.empty()) return fail(FMSI_GPU_ERR_ARG, "null pool");
     if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
     if (!bases || !chunk_off || !chunk_len || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
-    if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32]");
+    if (k < 1 || k > FMSI_GPU_MAX_K) return fail(FMSI_GPU_ERR_K, "k must be in [1, FMSI_GPU_MAX_K]");
     if ((output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
         (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");

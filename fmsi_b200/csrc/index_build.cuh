@@ -195,14 +195,18 @@ __global__ void planes_kernel(const u32 *__restrict__ sa, const u64 N, const u64
                 const u64 p1 = sa[r + 1];
                 const u64 km1 = k - 1;
                 if (p + km1 <= n && p1 + km1 <= n) {
-                    if (km1 == 0) kb = 1;
-                    else {
-                        const u64 w0 = packed[p >> 5], w1 = packed[(p >> 5) + 1];
-                        const u32 s0 = 2u * ((u32)p & 31u);
-                        const u64 a = (s0 ? ((w0 << s0) | (w1 >> (64 - s0))) : w0) >> (64 - 2 * km1);
-                        const u64 x0 = packed[p1 >> 5], x1 = packed[(p1 >> 5) + 1];
-                        const u32 s1 = 2u * ((u32)p1 & 31u);
-                        const u64 b = (s1 ? ((x0 << s1) | (x1 >> (64 - s1))) : x0) >> (64 - 2 * km1);
+                    // equal (k-1)-mers at p and p1, compared 32 bases at a time (the reference keeps them in
+                    // one uint64_t for k <= 32 and one __uint128_t for k <= 64, main.cpp:230-231)
+                    kb = 1;
+                    for (u64 off = 0; off < km1 && kb; off += 32) {
+                        const u32 len = (u32)((km1 - off < 32) ? (km1 - off) : 32);
+                        const u64 q = p + off, q1 = p1 + off;
+                        const u64 w0 = packed[q >> 5], w1 = packed[(q >> 5) + 1];
+                        const u32 s0 = 2u * ((u32)q & 31u);
+                        const u64 a = (s0 ? ((w0 << s0) | (w1 >> (64 - s0))) : w0) >> (64 - 2 * len);
+                        const u64 x0 = packed[q1 >> 5], x1 = packed[(q1 >> 5) + 1];
+                        const u32 s1 = 2u * ((u32)q1 & 31u);
+                        const u64 b = (s1 ? ((x0 << s1) | (x1 >> (64 - s1))) : x0) >> (64 - 2 * len);
                         kb = a == b;
                     }
                 }
@@ -434,7 +438,7 @@ inline void build_suffix_array(const u64 *d_packed, u64 n, u32 *d_sa, uint64_t *
 inline void build_index_on_device(const char *d_ms, u64 n, int k, bool with_klcp, bool keep_planes, BuiltIndex &out, uint64_t *launches) {
     if (n == 0) throw std::runtime_error("empty masked superstring");
     if (n + 1 >= (1ull << 32)) throw std::runtime_error("GPU index builder supports superstrings shorter than 2^32 - 1");
-    if (k < 1 || k > 32) throw std::runtime_error("GPU index builder supports k <= 32");
+    if (k < 1 || k > 65536) throw std::runtime_error("GPU index builder supports 1 <= k <= 65536");
     const u64 N = n + 1, nblk = (N >> 6) + 1;
     const u64 n_words = (n + 31) / 32 + 4, n_mask_words = (n + 63) / 64 + 1;
     DevArr<u64> packed(n_words), maskbits(n_mask_words);

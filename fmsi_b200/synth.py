@@ -101,8 +101,23 @@ def contig_superstring(codes: np.ndarray, k: int, n_pieces: int, seed: int,
         piece = codes[starts[p]:min(ends[p], n)]
         parts.append(revcomp_codes(piece) if flip[p] else piece)
     s = np.concatenate(parts)
-    kset = np.unique(canonical_packed(pack_kmers(codes, k), k))
-    sk = canonical_packed(pack_kmers(s, k), k)
+    if k <= 32:
+        kset = np.unique(canonical_packed(pack_kmers(codes, k), k))
+        sk = canonical_packed(pack_kmers(s, k), k)
+    else:  # k-mers no longer fit a word: canonical k-mers as byte strings -> dense ids (small inputs only)
+        ids: dict[bytes, int] = {}
+
+        def canon_ids(c: np.ndarray) -> np.ndarray:
+            win = np.lib.stride_tricks.sliding_window_view(c.astype(np.uint8), k)
+            out = np.empty(len(win), dtype=np.uint64)
+            for r in range(len(win)):
+                f = win[r].tobytes()
+                b = (3 - win[r][::-1]).astype(np.uint8).tobytes()
+                out[r] = ids.setdefault(min(f, b), len(ids))
+            return out
+
+        kset = np.unique(canon_ids(codes))
+        sk = canon_ids(s)
     pos = np.searchsorted(kset, sk)
     pos[pos >= len(kset)] = len(kset) - 1
     member = kset[pos] == sk

@@ -10,7 +10,8 @@
  *  - plain C types only; all functions return FMSI_GPU_OK (0) or a negative error code, and
  *    fmsi_gpu_last_error() returns a thread-local message for the last failure;
  *  - k-mers are packed 2 bits per base, A=0 C=1 G=2 T=3 (reference src/kmers.h:3-20), first base
- *    in the highest used bits: kmer = sum base[t] << 2*(k-1-t), k <= 32;
+ *    in the highest used bits: kmer = sum base[t] << 2*(k-1-t), k <= 32 (longer k-mers are queried
+ *    as text through fmsi_gpu_query_chunks);
  *  - SA intervals are half-open [i, j) over [0, N], N = n+1 = sa_transformed_mask.size();
  *  - `mem` says where the query/result buffers live: FMSI_GPU_MEM_HOST (the library stages them
  *    through its own pinned/device buffers and returns when results are in host memory) or
@@ -99,7 +100,8 @@ int fmsi_gpu_index_from_bits(const uint8_t *ac_gt, size_t n_ac_gt, const uint8_t
  * on the GPU: suffix-sorts the mask-cased superstring `ms` (ACGTacgt, upper case = ON, n characters,
  * host or device memory per `mem`), and builds the device-resident index directly. The suffix
  * array is unique, so the result equals the reference's `fmsi index` output (fmsi_gpu_index_save
- * writes byte-identical files). Limits: n + 1 < 2^32, k <= 32. */
+ * writes byte-identical files; the reference itself builds no kLCP array for k > 64, src/main.cpp:225-228).
+ * Limits: n + 1 < 2^32, k <= FMSI_GPU_MAX_K. */
 int fmsi_gpu_index_build(const char *ms, size_t n, int k, int with_klcp, int mem, int device,
                          const fmsi_gpu_options *opts, fmsi_gpu_index **out);
 /* dump_index(index, fn) — reference src/fms_index.h:484-500: writes <prefix>.fmsi.{ac_gt,ac,gt,mask,
@@ -146,8 +148,14 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
  * ms_query, src/main.cpp:337-370); chunk c is bases[chunk_off[c] .. chunk_off[c]+chunk_len[c]),
  * chunk_len[c] >= k, and yields chunk_len[c]-k+1 results starting at result index res_off[c].
  * With streaming != 0 a chunk holds at most FMSI_GPU_MAX_STREAM_KMERS k-mers.
- * results layout as for fmsi_gpu_query_kmers with n = total number of k-mers. */
+ * results layout as for fmsi_gpu_query_kmers with n = total number of k-mers.
+ * k may exceed 32 here (the reference's get_range_with_pattern, src/fms_index.h:117-124, takes any k
+ * and `fmsi index` builds such indexes, src/main.cpp:225-233), up to FMSI_GPU_MAX_K: the k-mers are
+ * then searched straight from the packed text. For k > 32 `streaming` only checks that the kLCP array
+ * is loaded — kLCP interval reuse is a shortcut that never changes a per-strand value, so those
+ * chunks may hold any number of k-mers and are answered by plain backward search. */
 #define FMSI_GPU_MAX_STREAM_KMERS 64
+#define FMSI_GPU_MAX_K 65536
 int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
                           const char *bases, size_t n_bases, const uint64_t *chunk_off,
                           const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,

@@ -51,8 +51,13 @@ def run_ref(args, cwd):
     return r.stdout
 
 
+ONLY = set(sys.argv[1:])  # `make_golden.py CASE...` regenerates just those cases
+
+
 def make_case(name: str, ms: bytes, k: int, queries: bytes, klcp: bool = True, note: str = "", header: bytes = b"ms"):
     d = os.path.join(HERE, name)
+    if ONLY and name not in ONLY:
+        return
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
     with open(os.path.join(d, "ms.fa"), "wb") as f:
@@ -164,6 +169,22 @@ def main():
               note="index built with -x (no kLCP)")
     g = synth.random_codes(5000, 71)
     make_case("syn_k32", synth.genome_superstring(g, 32), 32, mixed_queries(g, 32, 200, 20, 73), note="k=32 (widest packed k-mer)")
+
+    # --- k > 32: the k-mer no longer fits one packed word (get_range_with_pattern takes any k) -------
+    g = synth.random_codes(20000, 81)
+    make_case("syn_k47_max", synth.contig_superstring(g, 47, 12, 82, "max"), 47, mixed_queries(g, 47, 300, 40, 83),
+              note="k=47 (two pattern windows per strand), max-ones mask")
+    g = synth.random_codes(20000, 91)
+    half = synth.random_codes(32, 92)
+    pal = np.concatenate([half, synth.revcomp_codes(half)])  # a self-complementary 64-mer (general mode counts it once)
+    g[4000:4064] = pal
+    g[9000:9064] = pal
+    make_case("syn_k64_min", synth.contig_superstring(g, 64, 12, 93, "min"), 64,
+              mixed_queries(g, 64, 300, 40, 94) + b">pal\n" + synth.codes_to_ascii(pal) + b"\n>palctx\n" + synth.codes_to_ascii(g[3990:4080]) + b"\n",
+              note="k=64 (largest k with kLCP), min-ones mask, a self-complementary 64-mer occurring twice")
+    g = synth.random_codes(20000, 101)
+    make_case("syn_k97_noklcp", synth.contig_superstring(g, 97, 8, 102, "max"), 97, mixed_queries(g, 97, 300, 40, 103), klcp=False,
+              note="k=97 > 64: `fmsi index` builds no kLCP array (main.cpp:225-228); four pattern windows per strand")
 
     # --- parser / record-loop quirks ----------------------------------------
     quirks = (b">q1\nACGTN\n>q2\nNNACG\n>q3\nACGNTAC\nGTA\n>q4 lower\nacgtacgt\n@fq1 c\nACGTACG\n+\nIIIIIII\n"

@@ -39,7 +39,16 @@ def test_build_reproduces_reference_index_files(case, tmp_path):
     # and the built index answers queries like the loaded one
     ref = fg.Index.load(os.path.join(d, "ms.fa"), use_klcp=meta["klcp"])
     codes = synth.ascii_to_codes(ms)
-    if len(codes) >= meta["k"]:
+    if meta["k"] > 32:  # no packed form: the k-mers of the superstring and of random text, as chunks
+        k = meta["k"]
+        text = synth.codes_to_ascii(codes[:6000]) + synth.codes_to_ascii(np.random.default_rng(1).integers(0, 4, size=3000, dtype=np.uint8))
+        offs, lens = [0, 6000], [6000, 3000]
+        for out_kind in (fg.OUT_PRESENCE, fg.OUT_ORDERS):
+            assert np.array_equal(idx.query_chunks(text, offs, lens, k, fg.MODE_OR, out_kind), ref.query_chunks(text, offs, lens, k, fg.MODE_OR, out_kind))
+        if meta["klcp"]:
+            a = idx.query_chunks(text, offs, lens, k, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_BOTH, True)
+            assert np.array_equal(a, ref.query_chunks(text, offs, lens, k, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_BOTH, False))
+    elif len(codes) >= meta["k"]:
         kmers = synth.pack_kmers(codes, meta["k"])[:5000]
         rnd = np.random.default_rng(1).integers(0, 1 << (2 * meta["k"]) - 1, size=2000, dtype=np.uint64)
         q = np.concatenate([kmers, rnd])
@@ -87,4 +96,6 @@ def test_build_rejects_bad_input():
     with pytest.raises(fg.FmsiGpuError):
         fg.Index.build(b"ACGTNACGT", 3)
     with pytest.raises(fg.FmsiGpuError):
-        fg.Index.build(b"ACGTACGT", 33)
+        fg.Index.build(b"ACGTACGT", 0)
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Index.build(b"ACGTACGT", 65537)

@@ -147,6 +147,10 @@ def test_device_matches_oracle(case, variant):
         for mo in (False, True):
             assert gi.infer_presence(s, e, mo).tolist() == [oi.infer_presence(x, y, mo) for x, y in zip(s, e)]
         assert gi.kmer_order_if_present(s, e).tolist() == [oi.kmer_order_if_present(x, y) for x, y in zip(s, e)]
+    if k > 32:  # packed k-mers stop at k = 32: the text path is test_long_k_chunks_match_oracle
+        gi.close()
+        oi.close()
+        return
     # k-mers
     ms = open(prefix, "rb").read().split(b"\n")[1]
     ms_codes = synth.ascii_to_codes(ms)
@@ -286,6 +290,70 @@ def test_chunks_streaming_and_single_match_oracle(case):
                     assert [((int(v) & 3) - 1, ((int(v) >> 2) & 3) - 1) for v in both] == wb, (case, max_kmers, mode, streaming)
                 else:
                     assert [tuple(r) for r in both.tolist()] == wb, (case, max_kmers, streaming)
+    gi.close()
+    oi.close()
+
+
+@pytest.mark.parametrize("case", ["syn_k47_max", "syn_k64_min", "syn_k97_noklcp"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide"])
+def test_long_k_chunks_match_oracle(case, variant):
+    """k > 32 (longk_kernels.cuh): k-mers are searched from the packed text, 32 pattern characters per
+    register window. Every mode, LAZY and BOTH strands, with and without `streaming`, chunks of assorted
+    sizes, against the oracle's per-strand values; packed-k-mer entry points must refuse such k."""
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    k = meta["k"]
+    prefix = os.path.join(d, "ms.fa")
+    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}}[variant]
+    gi = fg.Index.load(prefix, use_klcp=meta["klcp"], **kw)
+    oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
+    assert gi.k == k and not gi.dict
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    rng = np.random.default_rng(zlib.crc32(case.encode()) + 1)
+    seqs = []
+    for r in range(50):  # reads from the superstring with substitutions, random strand, assorted lengths
+        ln = int(rng.integers(k, k + 200))
+        p = int(rng.integers(0, len(ms_codes) - ln + 1))
+        s = ms_codes[p:p + ln].copy()
+        sub = rng.random(ln) < 0.01
+        s[sub] = (s[sub] + rng.integers(1, 4, size=int(sub.sum()))) & 3
+        if r % 2:
+            s = synth.revcomp_codes(s)
+        seqs.append(s.astype(np.uint8))
+    seqs.append(rng.integers(0, 4, size=k + 100).astype(np.uint8))
+    seqs.append(ms_codes[:k].copy())
+    seqs.append(ms_codes[len(ms_codes) - k:].copy())
+    half = rng.integers(0, 4, size=(k + 1) // 2).astype(np.uint8)
+    seqs.append(np.concatenate([half, synth.revcomp_codes(half)])[:max(k, 2 * (k // 2))])  # self-complementary when k is even
+    seqs = [s for s in seqs if len(s) >= k]
+
+    def lazy(f, r, omode, oord):  # query_kmers_single with a neutral predictor, fms_index.h:283-298
+        if oord:
+            return f if f >= 0 else r
+        if omode == MODE_OR:
+            return int((f if f == 1 else r) == 1)
+        return int((f if f != -1 else r) == 1)
+
+    for max_kmers in (64, 7, 300):
+        bases, offs, lens = _chunks_of(seqs, k, max_kmers)
+        strs = [bases[o + q:o + q + k].decode() for o, l in zip(offs.tolist(), lens.tolist()) for q in range(l - k + 1)]
+        for mode, out, omode, oord in ((fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False),
+                                       (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True)):
+            wb = [oi.kmer_both_strands(st, omode, oord) for st in strs]
+            want = [lazy(f, r, omode, oord) for f, r in wb]
+            for streaming in ((False, True) if meta["klcp"] else (False,)):
+                got = gi.query_chunks(bases, offs, lens, k, mode, out, fg.STRANDS_LAZY, streaming)
+                assert got.astype(np.int64).tolist() == want, (case, max_kmers, mode, out, streaming)
+                both = gi.query_chunks(bases, offs, lens, k, mode, out, fg.STRANDS_BOTH, streaming)
+                if out == fg.OUT_PRESENCE:
+                    assert [((int(v) & 3) - 1, ((int(v) >> 2) & 3) - 1) for v in both] == wb, (case, max_kmers, mode, streaming)
+                else:
+                    assert [tuple(r) for r in both.tolist()] == wb, (case, max_kmers, streaming)
+    with pytest.raises(fg.FmsiGpuError):
+        gi.query_kmers(np.zeros(4, np.uint64), k)
+    if not meta["klcp"]:
+        with pytest.raises(fg.FmsiGpuError):
+            gi.query_chunks(bases, offs, lens, k, fg.MODE_OR, fg.OUT_PRESENCE, fg.STRANDS_LAZY, True)
     gi.close()
     oi.close()
 
