@@ -52,9 +52,10 @@ int usage() {
     std::cerr << "Usage:   fmsi <command> [options]" << std::endl << std::endl;
     std::cerr << "Command (GPU):" << std::endl;
     std::cerr << "    query   - Queries k-mers against an index." << std::endl;
-    std::cerr << "    lookup  - Return unique hashes of present k-mers." << std::endl << std::endl;
+    std::cerr << "    lookup  - Return unique hashes of present k-mers." << std::endl;
+    std::cerr << "    index   - Creates a BWT based index of the given masked superstring (same files as the reference)." << std::endl << std::endl;
     std::cerr << "Command (forwarded to the reference binary named by $FMSI_REFERENCE_BIN):" << std::endl;
-    std::cerr << "    index export union inter diff symdiff merge compact clean" << std::endl << std::endl;
+    std::cerr << "    export union inter diff symdiff merge compact clean" << std::endl << std::endl;
     return 1;
 }
 
@@ -786,6 +787,114 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     return ok ? 0 : 1;
 }
 
+int usage_index() {
+    std::cerr << std::endl;
+    std::cerr << "Usage:   fmsi index [options] <masked-superstring-input>" << std::endl << std::endl;
+    std::cerr << "Options:" << std::endl;
+    std::cerr << "    -k INT  - size of k-mers [recommended, default: number of mask trailing zeros - 1]" << std::endl;
+    std::cerr << "    -x      - do not compute the kLCP array used for faster streaming queries." << std::endl << std::endl;
+    std::cerr << "Note: `fmsi index` accepts only masked superstrings - these can be computed e.g. by KmerCamel from any FASTA file." << std::endl
+              << std::endl;
+    return 1;
+}
+
+// `fmsi index [-k K] [-x] MS.fa` — ms_index, reference src/main.cpp:172-236: same flags, messages and files
+// (the suffix array is unique, so the GPU builder's `.fmsi.*` bytes equal the reference's; tests/test_gpu_build.py).
+// Returns -2 for inputs the GPU builder does not take (n + 1 >= 2^32) when a reference binary can be forwarded to.
+int ms_index(int argc, char *argv[]) {
+    bool usage = false;
+    std::string fn;
+    if (argc > 1 && std::string(argv[argc - 1]) != "-h") {
+        fn = argv[argc - 1];
+        argc--;
+    }
+    int k = 0, c;
+    bool no_streaming = false;
+    while ((c = getopt(argc, argv, "hk:x")) >= 0) {
+        switch (c) {
+        case 'h': usage = true; break;
+        case 'k': k = atoi(optarg); break;
+        case 'x': no_streaming = true; break;
+        default: return usage_index();
+        }
+    }
+    if (usage) {
+        usage_index();
+        return 0;
+    } else if (fn.empty()) {
+        std::cerr << "ERROR: Path to the masked superstring is a required argument." << std::endl;
+        return usage_index();
+    }
+    std::cerr << "Starting " << fn << std::endl;
+    // read_masked_superstring (parser.h:41-55): the first FASTA/FASTQ entry of a plain or gzip file / stdin
+    std::string ms, name;
+    {
+        FILE *in = fn == "-" ? stdin : std::fopen(fn.c_str(), "r");
+        if (!in) throw std::invalid_argument("couldn't open file " + fn);  // uncaught in the reference too
+        gzFile fp = gzdopen(fileno(in), "r");
+        gzbuffer(fp, 1 << 20);
+        std::vector<char> text;
+        size_t have = 0;
+        for (;;) {
+            if (text.size() < have + (1u << 24)) text.resize(std::max<size_t>(2 * text.size(), (size_t)1 << 24));
+            const int got = gzread(fp, text.data() + have, (unsigned)std::min<size_t>(text.size() - have, 1u << 30));
+            if (got <= 0) break;
+            have += (size_t)got;
+        }
+        gzclose(fp);
+        fmsi::MemRecordReader reader(text.data(), have);
+        const int64_t l = reader.next(name, ms);
+        if (l < 0)
+            throw std::invalid_argument("Error reading the fasta file. The fasta file should contain a single entry - the masked superstring.");
+        std::string other;
+        if (reader.next(name, other) >= 0)
+            std::cerr << "Warning: The fasta file contains more than one entry. Only the first entry will be used." << std::endl;
+    }
+    if (ms.size() == 0) {
+        std::cerr << "ERROR: The file '" << fn << "' is in incorrect format. It is supposed to be a fasta file with a single entry, the masked superstring"
+                  << std::endl;
+        return usage_index();
+    }
+    std::cerr << "Read masked superstring of length " << ms.size() << std::endl;
+    int inferred_k = 1;  // infer_k (parser.h:31-37)
+    while ((size_t)inferred_k < ms.size() && !(ms[ms.size() - inferred_k] >= 'A' && ms[ms.size() - inferred_k] <= 'Z')) inferred_k++;
+    if (k == 0) {
+        k = inferred_k;
+        std::cerr << "Inferred k from the masked case convention: " << k << std::endl;
+    }
+    if (k != inferred_k)
+        std::cerr << "WARNING: The provided k (" << k << ") does not match the k inferred from the mask convention (" << inferred_k
+                  << "). The provided k is used but we recommend double checking that it is correct." << std::endl;
+    if (k > 64 && !no_streaming) {
+        std::cerr << "WARNING: Construction of kLCP array for streaming support is only available for k <= 64. The index will be constructed "
+                     "without streaming support, which results in slower positive streaming queries."
+                  << std::endl;
+        no_streaming = true;
+    }
+    const char *ref_bin = std::getenv("FMSI_REFERENCE_BIN");
+    const bool can_forward = ref_bin && *ref_bin;
+    if (ms.size() + 1 >= (1ull << 32) && can_forward) return -2;
+    int device = 0;
+    if (const char *e = std::getenv("FMSI_GPU_DEVICE")) device = atoi(e);
+    fmsi_gpu_options opts;
+    std::memset(&opts, 0, sizeof opts);  // no suffix table, no dictionary: the index is only written out
+    fmsi_gpu_index *idx = nullptr;
+    int rc = fmsi_gpu_index_build(ms.data(), ms.size(), k, no_streaming ? 0 : 1, FMSI_GPU_MEM_HOST, device, &opts, &idx);
+    if (rc != FMSI_GPU_OK) {
+        std::cerr << "ERROR: " << fmsi_gpu_last_error() << std::endl;
+        return can_forward ? -2 : 1;
+    }
+    std::cerr << "Constructed index" << std::endl;
+    rc = fmsi_gpu_index_save(idx, fn.c_str());
+    fmsi_gpu_index_free(idx);
+    if (rc != FMSI_GPU_OK) {
+        std::cerr << "ERROR: " << fmsi_gpu_last_error() << std::endl;
+        return 1;
+    }
+    std::cerr << "Written index" << std::endl;
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char *argv[]) {
@@ -801,6 +910,11 @@ int main(int argc, char *argv[]) {
         if (ret == -2) return forward_to_reference(argc, argv);
         return ret;
     }
+    if (op == "index") {
+        ret = ms_index(argc - 1, argv + 1);
+        if (ret == -2) return forward_to_reference(argc, argv);
+        return ret;
+    }
     if (op == "-v") {
         std::cout << kVersion << std::endl;
         return 0;
@@ -809,7 +923,7 @@ int main(int argc, char *argv[]) {
         usage();
         return 0;
     }
-    if (op == "index" || op == "clean" || op == "merge" || op == "normalize" || op == "compact" || op == "export" || op == "union" ||
+    if (op == "clean" || op == "merge" || op == "normalize" || op == "compact" || op == "export" || op == "union" ||
         op == "inter" || op == "diff" || op == "symdiff")
         return forward_to_reference(argc, argv);
     return usage();

@@ -12,10 +12,12 @@
 //
 //   orient(q)  = q if q*C <= rc(q)*C (mod 2^64) else rc(q)   (C odd: a bijection, so ties <=> q == rc(q);
 //                a hash order, unlike the lexicographic minimum, keeps the first t bases uniform)
-//   bucket[x], x = first t bases of orient(q)  (32 B = one sector, 4^t of them):
+//   key(q)     = a bijective mix of orient(q) on 2k bits (fold_key) — a hash table, so the load of a bucket does
+//                not depend on how the index's k-mers share prefixes
+//   bucket[x], x = top 2t bits of key(q)  (32 B = one sector, 4^t of them):
 //       u32 start, end      rows [start, end) of this bucket in rows[] / ids[] (sorted by payload, distinct)
 //       u32 flags           4 bits per inline row: sf | sr << 2
-//       PAY32: u32 pay[5]       the last B = k - t <= 16 bases of the first 5 rows
+//       PAY32: u32 pay[5]       the low 2B bits (B = k - t <= 16) of the keys of the first 5 rows
 //       PAY64: u32 pad; u64 pay[2]   (16 < B <= 30) first 2 rows
 //   rows[g]  (8 B)  pay << 4 | sf | sr << 2   — read only when the bucket holds more rows than fit inline
 //   ids[g]   (8 B)  {id_f, id_r} = rank1(sa_start) of either orientation (lookup only)
@@ -52,6 +54,20 @@ struct FoldView {
 };
 
 __device__ __forceinline__ bool fold_swapped(u64 q, u64 rc) { return rc * kFoldMul < q * kFoldMul; }
+
+// The table key of an oriented k-mer: a bijection of [0, 4^k) (multiply by an odd constant, fold the upper half
+// into the lower, multiply again, all mod 4^k), so rows stay unique while the bucket index (the top 2t bits) no
+// longer follows the k-mer's first t bases. Indexes whose k-mers share long prefixes (pangenomes: thousands of
+// near-copies of one genome) would otherwise pile their rows into the few buckets of the genome's own t-mers.
+constexpr u64 kFoldMul2 = 0xD6E8FEB86659FD93ull;
+__device__ __forceinline__ u64 fold_key(u64 c, u32 k) {
+    const u64 m = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
+    c = (c * kFoldMul) & m;
+    c ^= c >> k;
+    c = (c * kFoldMul2) & m;
+    c ^= c >> k;
+    return c;
+}
 
 // ------------------------------------------------------------------------------------------- build
 // kmers[r] = the first k characters of the suffix of SA row r (padded with A past the sentinel);
@@ -116,8 +132,8 @@ __global__ void fold_entries_kernel(const DevIndex d, const u64 *__restrict__ km
         state = rj > ri ? (first ? 3 : 2) : 1;
         id = ri;
     }
-    keys[h] = sw ? rc : q;
-    vals[h] = id | (state << 32) | ((u64)sw << 34);
+    keys[h] = fold_key(sw ? rc : q, k);
+    vals[h] = id | (state << 32) | ((u64)sw << 34) | ((u64)(q == rc) << 35);
 }
 
 struct alignas(32) FoldBucket {
@@ -135,9 +151,11 @@ __global__ void fold_rows_kernel(const u64 *__restrict__ keys, const u64 *__rest
     const u64 e0 = gs[g], e1 = (g + 1 < n_groups) ? (u64)gs[g + 1] : n_entries;
     const u64 key = keys[e0];
     u32 sf = 0, sr = 0, idf = kFoldNoId, idr = kFoldNoId;
+    bool self_rc = false;
     for (u64 e = e0; e < e1; ++e) {
         const u64 v = vals[e];
         const u32 st = (u32)(v >> 32) & 3u;
+        self_rc |= (v >> 35) & 1ull;
         if (!st) continue;
         if ((v >> 34) & 1ull) {
             sr = st;
@@ -147,7 +165,7 @@ __global__ void fold_rows_kernel(const u64 *__restrict__ keys, const u64 *__rest
             idf = (u32)v;
         }
     }
-    if (revcomp_packed(key, k) == key) {
+    if (self_rc) {
         sr = sf;
         idr = idf;
     }
@@ -357,7 +375,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
                     if (k < 32) km &= (1ull << (2 * k)) - 1ull;
                     const u64 rc = revcomp_packed(km, k);
                     swapped = fold_swapped(km, rc);
-                    const u64 c = swapped ? rc : km;
+                    const u64 c = fold_key(swapped ? rc : km, k);
                     q = c & pmask;
                     bx = c >> (2 * B);
                     phase = FP_BUCKET;

@@ -119,3 +119,50 @@ def test_cli_errors_match_reference_behaviour():
     assert r.returncode == 1 and b"Path to the fasta file is a required argument" in r.stderr
     r = run_cli(["query", "-q", "/nonexistent/q.fa", os.path.join(d, "ms.fa")])
     assert r.returncode != 0  # the reference aborts on an uncaught std::invalid_argument
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_cli_index_writes_the_reference_files(case, tmp_path):
+    """`fmsi index [-k K] [-x] MS.fa` (ms_index, reference src/main.cpp:172-236) on the GPU builder: the six
+    `.fmsi.*` files next to the input are byte-identical to those the reference's `fmsi index` wrote."""
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    ms = tmp_path / "ms.fa"
+    ms.write_bytes(open(os.path.join(d, "ms.fa"), "rb").read())
+    flags = ["-k", str(meta["k"])] + ([] if meta["klcp"] else ["-x"])
+    r = run_cli(["index", *flags, str(ms)])
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"Constructed index" in r.stderr and b"Written index" in r.stderr
+    for ext in ("ac_gt", "ac", "gt", "mask", "klcp", "misc"):
+        want = os.path.join(d, f"ms.fa.fmsi.{ext}")
+        got = f"{ms}.fmsi.{ext}"
+        if not os.path.exists(want):
+            assert not os.path.exists(got), ext
+            continue
+        assert open(got, "rb").read() == open(want, "rb").read(), f"{case}: {ext}"
+
+
+def test_cli_index_infers_k_reads_gzip_and_reports_errors(tmp_path):
+    d = os.path.join(GOLDEN, "syn_k9_max")
+    text = open(os.path.join(d, "ms.fa"), "rb").read()
+    gz = tmp_path / "ms.fa.gz"
+    gz.write_bytes(gzip.compress(text + b">second\nACGT\n"))
+    r = run_cli(["index", str(gz)])
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"Inferred k from the masked case convention: 9" in r.stderr and b"more than one entry" in r.stderr
+    for ext in ("ac_gt", "ac", "gt", "mask", "klcp", "misc"):
+        assert open(f"{gz}.fmsi.{ext}", "rb").read() == open(os.path.join(d, f"ms.fa.fmsi.{ext}"), "rb").read(), ext
+    r = run_cli(["index", "-k", "7", str(gz)])
+    assert r.returncode == 0 and b"does not match the k inferred from the mask convention (9)" in r.stderr
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b">x\n\n")
+    r = run_cli(["index", str(empty)])
+    assert r.returncode == 1 and b"is in incorrect format" in r.stderr
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">x\nACGTNACGTacg\n")
+    r = run_cli(["index", str(bad)], env={"FMSI_REFERENCE_BIN": ""})
+    assert r.returncode != 0 and b"other than ACGTacgt" in r.stderr
+    r = run_cli(["index"])
+    assert r.returncode == 1 and b"Path to the masked superstring is a required argument" in r.stderr
+    r = run_cli(["index", "-h"])
+    assert r.returncode == 0 and b"Usage:   fmsi index" in r.stderr
