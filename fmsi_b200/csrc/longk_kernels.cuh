@@ -29,13 +29,9 @@ __global__ void extract_starts_kernel(const u64 *__restrict__ coff, const u32 *_
                                       const u64 *__restrict__ roff, const u64 n_chunks, const u64 n_results,
                                       const u32 k, u64 *__restrict__ starts) {
     const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r - (threadIdx.x & 31u) >= n_results) return;  // whole warp past the end
+    const u64 lo = chunk_of_slot(roff, n_chunks, r, n_results);
     if (r >= n_results) return;
-    u64 lo = 0, hi = n_chunks;  // last chunk with roff <= r
-    while (hi - lo > 1) {
-        const u64 mid = (lo + hi) >> 1;
-        if (roff[mid] <= r) lo = mid;
-        else hi = mid;
-    }
     const u64 pos = r - roff[lo];
     u64 s = kNoKmer;
     if (roff[lo] <= r && clen[lo] >= k && pos + k <= clen[lo]) s = coff[lo] + pos;

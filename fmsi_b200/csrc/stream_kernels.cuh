@@ -54,19 +54,44 @@ __device__ __forceinline__ u64 window(const u64 *__restrict__ packed, u64 s, u32
     return v >> (64 - 2 * len);
 }
 
+// The chunk that owns result slot r = the last chunk c with roff[c] <= r, for the 32 consecutive slots of a warp
+// (r = blockIdx.x * blockDim.x + threadIdx.x, blockDim.x a multiple of 32). roff[] is non-decreasing, so the
+// chunks of a warp's slots lie between the chunk of its first slot and the chunk of its last: two full binary
+// searches per warp (lanes 0 and 1) and a search over that short range per lane (a step or two for reads),
+// instead of a log2(n_chunks)-deep search per slot. Every lane of the warp must call it.
+__device__ __forceinline__ u64 chunk_of_slot(const u64 *__restrict__ roff, const u64 n_chunks, const u64 r, const u64 n_results) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 r_first = r - lane;
+    const u64 r_last = (r_first + 31 < n_results) ? r_first + 31 : n_results - 1;
+    const u64 target = lane == 0 ? r_first : r_last;
+    u64 lo = 0, hi = n_chunks;
+    if (lane < 2) {
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if (roff[mid] <= target) lo = mid;
+            else hi = mid;
+        }
+    }
+    const u64 lo0 = __shfl_sync(0xffffffffu, lo, 0), hi0 = __shfl_sync(0xffffffffu, lo, 1);
+    lo = lo0;
+    hi = hi0 + 1;
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (roff[mid] <= r) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
 // Non-streaming chunks: one thread per result slot materialises its k-mer; the single-query kernel
 // then runs over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
 __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
                                      const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks,
                                      const u64 n_results, const u32 k, u64 *__restrict__ kmers) {
     const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r - (threadIdx.x & 31u) >= n_results) return;  // whole warp past the end
+    const u64 lo = chunk_of_slot(roff, n_chunks, r, n_results);
     if (r >= n_results) return;
-    u64 lo = 0, hi = n_chunks;  // last chunk with roff <= r
-    while (hi - lo > 1) {
-        const u64 mid = (lo + hi) >> 1;
-        if (roff[mid] <= r) lo = mid;
-        else hi = mid;
-    }
     const u64 pos = r - roff[lo];
     u64 km = 0;
     if (roff[lo] <= r && clen[lo] >= k && pos + k <= clen[lo]) km = window(packed, coff[lo] + pos, k);
