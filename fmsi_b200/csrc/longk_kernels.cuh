@@ -23,19 +23,13 @@ namespace fmsi {
 
 constexpr u64 kNoKmer = ~0ull;  // start position of a result slot that belongs to no k-mer
 
-// One thread per result slot: the start position of its k-mer in the packed text (chunks overlap by
-// k-1 bases, so slot r of chunk c starts at chunk_off[c] + (r - res_off[c])).
+// The start position of every result slot's k-mer in the packed text (chunks overlap by k-1 bases, so slot r of
+// chunk c starts at chunk_off[c] + (r - res_off[c])); kNoKmer for slots that belong to no k-mer.
 __global__ void extract_starts_kernel(const u64 *__restrict__ coff, const u32 *__restrict__ clen,
                                       const u64 *__restrict__ roff, const u64 n_chunks, const u64 n_results,
-                                      const u32 k, u64 *__restrict__ starts) {
-    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (r - (threadIdx.x & 31u) >= n_results) return;  // whole warp past the end
-    const u64 lo = chunk_of_slot(roff, n_chunks, r, n_results);
-    if (r >= n_results) return;
-    const u64 pos = r - roff[lo];
-    u64 s = kNoKmer;
-    if (roff[lo] <= r && clen[lo] >= k && pos + k <= clen[lo]) s = coff[lo] + pos;
-    starts[r] = s;
+                                      const u32 k, const u32 gshift, u64 *__restrict__ starts) {
+    for_chunk_slots(coff, clen, roff, n_chunks, n_results, k, gshift, [&](u64 slot, u64 start) { starts[slot] = start; },
+                    [&](u64 slot) { starts[slot] = kNoKmer; });
 }
 
 // The next (at most 32) pattern characters of a strand search that has consumed `consumed` of its k

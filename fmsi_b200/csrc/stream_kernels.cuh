@@ -29,19 +29,38 @@ __device__ __forceinline__ u32 base_code(unsigned char ch) {
     return x ^ (x >> 1);
 }
 
+// Four ASCII bases in a 32-bit word (first base in the lowest byte) -> their 2-bit codes in one byte, first base
+// highest. Per byte: code = x ^ (x >> 1), x = (ch >> 1) & 3; the multiply gathers the four 2-bit fields (byte i's
+// field lands at bit 30 - 2i; all other partial products fall below bit 24 without overlapping, or overflow).
+__device__ __forceinline__ u32 pack4_bases(u32 w) {
+    u32 y = (w >> 1) & 0x03030303u;
+    y ^= (y >> 1) & 0x01010101u;
+    return (y * 0x40100401u) >> 24;
+}
+__device__ __forceinline__ u64 pack16_bases(const uint4 x) {
+    return ((u64)pack4_bases(x.x) << 24) | ((u64)pack4_bases(x.y) << 16) | ((u64)pack4_bases(x.z) << 8) | (u64)pack4_bases(x.w);
+}
+
 // Packed text: base b sits at bits [62 - 2(b & 31), 63 - 2(b & 31)] of word b >> 5, so that a window
-// read is already in k-mer order (first base highest).
+// read is already in k-mer order (first base highest). One thread per word: two 16-byte loads when the
+// text is 16-byte aligned (device scratch always is), bytes otherwise and at the tail.
 __global__ void pack_bases_kernel(const char *__restrict__ bases, const u64 n_bases, u64 *__restrict__ packed,
                                   const u64 n_words) {
     const u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     u64 v = 0;
     const u64 b0 = w * 32;
+    if ((reinterpret_cast<unsigned long long>(bases) & 15ull) == 0 && b0 + 32 <= n_bases) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(bases + b0);
+        const uint4 x0 = __ldg(p), x1 = __ldg(p + 1);
+        v = (pack16_bases(x0) << 32) | pack16_bases(x1);
+    } else {
 #pragma unroll 8
-    for (u32 t = 0; t < 32; ++t) {
-        const u64 b = b0 + t;
-        const u32 code = (b < n_bases) ? base_code((unsigned char)bases[b]) : 0u;
-        v = (v << 2) | code;
+        for (u32 t = 0; t < 32; ++t) {
+            const u64 b = b0 + t;
+            const u32 code = (b < n_bases) ? base_code((unsigned char)bases[b]) : 0u;
+            v = (v << 2) | code;
+        }
     }
     packed[w] = v;
 }
@@ -54,48 +73,48 @@ __device__ __forceinline__ u64 window(const u64 *__restrict__ packed, u64 s, u32
     return v >> (64 - 2 * len);
 }
 
-// The chunk that owns result slot r = the last chunk c with roff[c] <= r, for the 32 consecutive slots of a warp
-// (r = blockIdx.x * blockDim.x + threadIdx.x, blockDim.x a multiple of 32). roff[] is non-decreasing, so the
-// chunks of a warp's slots lie between the chunk of its first slot and the chunk of its last: two full binary
-// searches per warp (lanes 0 and 1) and a search over that short range per lane (a step or two for reads),
-// instead of a log2(n_chunks)-deep search per slot. Every lane of the warp must call it.
-__device__ __forceinline__ u64 chunk_of_slot(const u64 *__restrict__ roff, const u64 n_chunks, const u64 r, const u64 n_results) {
-    const u32 lane = threadIdx.x & 31u;
-    const u64 r_first = r - lane;
-    const u64 r_last = (r_first + 31 < n_results) ? r_first + 31 : n_results - 1;
-    const u64 target = lane == 0 ? r_first : r_last;
-    u64 lo = 0, hi = n_chunks;
-    if (lane < 2) {
-        while (hi - lo > 1) {
-            const u64 mid = (lo + hi) >> 1;
-            if (roff[mid] <= target) lo = mid;
-            else hi = mid;
-        }
-    }
-    const u64 lo0 = __shfl_sync(0xffffffffu, lo, 0), hi0 = __shfl_sync(0xffffffffu, lo, 1);
-    lo = lo0;
-    hi = hi0 + 1;
-    while (hi - lo > 1) {
-        const u64 mid = (lo + hi) >> 1;
-        if (roff[mid] <= r) lo = mid;
-        else hi = mid;
-    }
-    return lo;
+// Chunk-driven slot fill shared by extract_kmers_kernel / extract_starts_kernel (longk_kernels.cuh): a group of
+// 2^gshift consecutive threads owns chunk c and strides over its k-mers, so nobody searches res_off[] for the chunk
+// of a slot (a log2(n_chunks)-deep chain of dependent loads per warp made that search the slowest kernel of the
+// reads path). res_off[] is non-decreasing; a chunk's slots end where the next chunk's begin; slots that belong
+// to no k-mer (before the first chunk, between chunks, after the last) are filled with `gap`.
+// f(slot, start_base) stores the k-mer that starts at base `start_base`; g(slot) stores the gap value.
+template <typename Fill, typename Gap>
+__device__ __forceinline__ void for_chunk_slots(const u64 *__restrict__ coff, const u32 *__restrict__ clen, const u64 *__restrict__ roff,
+                                                const u64 n_chunks, const u64 n_results, const u32 k, const u32 gshift, Fill f, Gap g) {
+    const u64 tid = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    const u64 c = tid >> gshift;
+    if (c >= n_chunks) return;
+    const u64 G = 1ull << gshift, sub = tid & (G - 1);
+    const u64 r0 = roff[c];
+    u64 r_next = (c + 1 < n_chunks) ? roff[c + 1] : n_results;
+    if (r_next > n_results) r_next = n_results;
+    const u32 len = clen[c];
+    u64 nk = len >= k ? (u64)(len - k + 1) : 0;
+    if (r0 >= r_next) nk = 0;
+    else if (nk > r_next - r0) nk = r_next - r0;
+    const u64 s0 = coff[c];
+    for (u64 pos = sub; pos < nk; pos += G) f(r0 + pos, s0 + pos);
+    for (u64 r = r0 + nk + sub; r < r_next; r += G) g(r);
+    if (c == 0)
+        for (u64 r = sub; r < r0 && r < n_results; r += G) g(r);
 }
 
-// Non-streaming chunks: one thread per result slot materialises its k-mer; the single-query kernel
-// then runs over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
+// Host side: threads per chunk (log2) for the kernels above, from the mean number of k-mers per chunk.
+inline u32 chunk_group_shift(u64 n_chunks, u64 n_results) {
+    const u64 avg = n_chunks ? n_results / n_chunks : 1;
+    u32 g = 0;
+    while (g < 5 && (1ull << g) < avg) ++g;
+    return g;
+}
+
+// Non-streaming chunks: the k-mer of every result slot, materialised for the single-query kernels, which
+// then run over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
 __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
                                      const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks,
-                                     const u64 n_results, const u32 k, u64 *__restrict__ kmers) {
-    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (r - (threadIdx.x & 31u) >= n_results) return;  // whole warp past the end
-    const u64 lo = chunk_of_slot(roff, n_chunks, r, n_results);
-    if (r >= n_results) return;
-    const u64 pos = r - roff[lo];
-    u64 km = 0;
-    if (roff[lo] <= r && clen[lo] >= k && pos + k <= clen[lo]) km = window(packed, coff[lo] + pos, k);
-    kmers[r] = km;
+                                     const u64 n_results, const u32 k, const u32 gshift, u64 *__restrict__ kmers) {
+    for_chunk_slots(coff, clen, roff, n_chunks, n_results, k, gshift,
+                    [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); }, [&](u64 slot) { kmers[slot] = 0; });
 }
 
 enum { SP_TABLE = 0, SP_STEP = 1, SP_MX = 2 };
