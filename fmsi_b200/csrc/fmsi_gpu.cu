@@ -4,9 +4,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -506,6 +508,8 @@ struct RawIndex {
     int k = 0;
 };
 
+std::chrono::steady_clock::time_point g_load_start;  // $FMSI_GPU_TIMING stage clock of the running fmsi_gpu_index_load
+
 int convert_and_setup(fmsi_gpu_index *idx, const RawIndex &raw, const fmsi_gpu_options *opts) {
     int rc = select_device(idx);
     if (rc) return rc;
@@ -534,6 +538,9 @@ int convert_and_setup(fmsi_gpu_index *idx, const RawIndex &raw, const fmsi_gpu_o
         convert_on_device(N, d_acgt, d_ac, raw.ac.nbits, d_gt, raw.gt.nbits, d_mask.p, raw.has_klcp ? d_klcp.p : nullptr, raw.counts,
                           opts ? (unsigned)opts->sb_shift_log2 : 0u, cv, &launches);
         BCU(cudaDeviceSynchronize());
+        if (std::getenv("FMSI_GPU_TIMING"))
+            fprintf(stderr, "[fmsi timing] load: uploaded + converted on the device: %.3f s\n",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - g_load_start).count());
         g_launches.fetch_add(launches);
         h.mask_ones = cv.mask_ones;
         h.sb_shift = cv.sb_shift;
@@ -562,26 +569,35 @@ void read_raw_index_files(const std::string &prefix, bool use_klcp, RawIndex &ra
     const std::string base = prefix + ".fmsi";
     for (const char *ext : {".ac_gt", ".ac", ".gt", ".mask", ".misc"})
         if (!file_exists(base + ext)) throw std::runtime_error("index not correctly loaded: missing " + base + ext);
-    {
-        ByteReader r(base + ".ac_gt");
-        r.read_bitvec(raw.ac_gt);
-    }
-    {
-        ByteReader r(base + ".ac");
-        r.read_bitvec(raw.ac);
-    }
-    {
-        ByteReader r(base + ".gt");
-        r.read_bitvec(raw.gt);
-    }
-    raw.rrr = read_rrr(base + ".mask");
-    raw.has_rrr = true;
+    // the four bit vectors are read concurrently, each straight into its word array (a human-scale index is
+    // 4 x 388 MB; one thread copying file after file through a staging buffer took most of the load time)
     raw.has_klcp = false;
-    if (use_klcp && file_exists(base + ".klcp")) {
-        ByteReader r(base + ".klcp");
-        r.read_bitvec(raw.klcp);
-        raw.has_klcp = raw.klcp.nbits > 0;
+    const bool want_klcp = use_klcp && file_exists(base + ".klcp");
+    std::string errors[4];
+    auto reader = [&](int slot, const char *ext, BitVec *dst) {
+        try {
+            read_bitvec_file(base + ext, *dst);
+        } catch (const std::exception &e) {
+            errors[slot] = e.what();
+        }
+    };
+    std::vector<std::thread> readers;
+    readers.emplace_back(reader, 0, ".ac_gt", &raw.ac_gt);
+    readers.emplace_back(reader, 1, ".ac", &raw.ac);
+    readers.emplace_back(reader, 2, ".gt", &raw.gt);
+    if (want_klcp) readers.emplace_back(reader, 3, ".klcp", &raw.klcp);
+    std::string rrr_error;
+    try {
+        raw.rrr = read_rrr(base + ".mask");
+    } catch (const std::exception &e) {
+        rrr_error = e.what();
     }
+    for (auto &t : readers) t.join();
+    for (const std::string &e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+    if (!rrr_error.empty()) throw std::runtime_error(rrr_error);
+    raw.has_rrr = true;
+    if (want_klcp) raw.has_klcp = raw.klcp.nbits > 0;
     std::ifstream in(base + ".misc");
     if (!(in >> raw.dollar >> raw.counts[0] >> raw.counts[1] >> raw.counts[2] >> raw.counts[3] >> raw.k))
         throw std::runtime_error("malformed " + base + ".misc");
@@ -638,13 +654,27 @@ int fmsi_gpu_index_load(const char *prefix, int use_klcp, int device, const fmsi
     std::unique_ptr<fmsi_gpu_index> idx(new fmsi_gpu_index());
     idx->device = device;
     RawIndex raw;
+    // the CUDA context of the device (hundreds of ms in a fresh process) comes up while the files are read
+    std::thread warm([device] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && device >= 0 && device < ndev && cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr);
+        cudaGetLastError();
+    });
+    const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
+    const auto t0 = g_load_start = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     try {
         read_raw_index_files(prefix, use_klcp != 0, raw);
+        if (timing) fprintf(stderr, "[fmsi timing] load: files read: %.3f s\n", since());
+        warm.join();
+        if (timing) fprintf(stderr, "[fmsi timing] load: CUDA context up: %.3f s\n", since());
         if (raw.rrr.size == 0) return fail(FMSI_GPU_ERR_IO, "index not correctly loaded (empty mask)");
     } catch (const std::exception &e) {
+        if (warm.joinable()) warm.join();
         return fail(FMSI_GPU_ERR_IO, e.what());
     }
     int rc = convert_and_setup(idx.get(), raw, opts);
+    if (timing) fprintf(stderr, "[fmsi timing] load: converted, table / dictionary built: %.3f s\n", since());
     if (rc) {
         fmsi_gpu_index_free(idx.release());
         return rc;
@@ -753,56 +783,89 @@ int fmsi_gpu_index_save(const fmsi_gpu_index *idx, const char *prefix) {
         const HostIndex &h = idx->meta;
         const uint64_t N = h.n, nw = (N + 63) >> 6;
         const std::string base = std::string(prefix) + ".fmsi";
-        BitVec ac_gt, ac, gt, mask, klcp;
-        ac_gt.resize_bits(N);
-        mask.resize_bits(N);
-        std::memcpy(ac_gt.w.data(), idx->plane_hi.data(), nw * 8);
-        std::memcpy(mask.w.data(), idx->plane_mask.data(), nw * 8);
-        // counts = {1, #A+1, #A+#C+1, ...} -> |ac| = counts[2], |gt| = N - counts[2] (fms_index.h:434-451)
+        // counts = {1, #A+1, #A+#C+1, ...} -> |ac| = counts[2], |gt| = N - counts[2] (fms_index.h:434-451).
+        // ac / gt = the low plane compacted to the A/C/$ slots and to the G/T slots, in row order: per 1024-block
+        // granule the slot counts, a prefix sum over granules, then all host threads append their ranges.
+        BitVec ac, gt;
         ac.resize_bits(h.counts[2]);
         gt.resize_bits(N - h.counts[2]);
-        uint64_t ap = 0, gp = 0;
-        for (uint64_t b = 0; b < nw; ++b) {
+        const uint64_t kGran = 1024, ngran = (nw + kGran - 1) / kGran;
+        auto block_hi = [&](uint64_t b) {
             const unsigned valid = (unsigned)std::min<uint64_t>(64, N - b * 64);
-            const uint64_t vmask = valid == 64 ? ~0ull : ((1ull << valid) - 1);
-            const uint64_t hi = idx->plane_hi[b] & vmask, lo = idx->plane_lo[b];
-            uint64_t sel = ~hi & vmask;
-            while (sel) {  // A/C/$ slots in order
-                const unsigned t = (unsigned)__builtin_ctzll(sel);
-                if ((lo >> t) & 1) ac.set(ap);
-                ++ap;
-                sel &= sel - 1;
+            return idx->plane_hi[b] & (valid == 64 ? ~0ull : ((1ull << valid) - 1));
+        };
+        auto block_valid = [&](uint64_t b) { return (uint64_t)std::min<uint64_t>(64, N - b * 64); };
+        std::vector<uint64_t> g_start(ngran + 1, 0);  // G/T slots before granule g
+        parallel_ranges(ngran, 1, [&](uint64_t g0, uint64_t g1) {
+            for (uint64_t g = g0; g < g1; ++g) {
+                uint64_t c = 0;
+                for (uint64_t b = g * kGran; b < std::min(nw, (g + 1) * kGran); ++b) c += (uint64_t)__builtin_popcountll(block_hi(b));
+                g_start[g + 1] = c;
             }
-            sel = hi;
-            while (sel) {
-                const unsigned t = (unsigned)__builtin_ctzll(sel);
-                if ((lo >> t) & 1) gt.set(gp);
-                ++gp;
-                sel &= sel - 1;
+        });
+        for (uint64_t g = 0; g < ngran; ++g) g_start[g + 1] += g_start[g];
+        if (g_start[ngran] != gt.nbits) throw std::runtime_error("plane sizes inconsistent with counts");
+        parallel_ranges(ngran, 1, [&](uint64_t g0, uint64_t g1) {
+            uint64_t gp = g_start[g0], ap = g0 * kGran * 64 - gp;
+            for (uint64_t b = g0 * kGran; b < std::min(nw, g1 * kGran); ++b) {
+                const uint64_t hi = block_hi(b), lo = idx->plane_lo[b];
+                const uint64_t vmask = block_valid(b) == 64 ? ~0ull : ((1ull << block_valid(b)) - 1);
+                uint64_t sel = ~hi & vmask, bits = 0;
+                unsigned cnt = 0;
+                while (sel) {  // A/C/$ slots in order
+                    bits |= ((lo >> __builtin_ctzll(sel)) & 1ull) << cnt++;
+                    sel &= sel - 1;
+                }
+                ac.set_int_atomic(ap, bits, cnt);
+                ap += cnt;
+                sel = hi;
+                bits = 0;
+                cnt = 0;
+                while (sel) {
+                    bits |= ((lo >> __builtin_ctzll(sel)) & 1ull) << cnt++;
+                    sel &= sel - 1;
+                }
+                gt.set_int_atomic(gp, bits, cnt);
+                gp += cnt;
             }
-        }
-        if (ap != ac.nbits || gp != gt.nbits) throw std::runtime_error("plane sizes inconsistent with counts");
-        {
-            ByteWriter w(base + ".ac_gt");
-            w.bitvec(ac_gt);
-        }
-        {
+        });
+        // the five files are written concurrently (the mask's RRR<63> coder runs on all threads first)
+        BitVec mask;
+        mask.resize_bits(N);
+        std::memcpy(mask.w.data(), idx->plane_mask.data(), nw * 8);
+        const RrrFile rrr = rrr_encode(mask);
+        mask = BitVec();
+        std::vector<std::thread> writers;
+        std::string werr[5];
+        auto guarded = [&](int slot, std::function<void()> fn) {
+            writers.emplace_back([&werr, slot, fn] {
+                try {
+                    fn();
+                } catch (const std::exception &e) {
+                    werr[slot] = e.what();
+                }
+            });
+        };
+        auto write_plane = [&](const std::string &path, const std::vector<uint64_t> &plane) {
+            ByteWriter w(path);
+            w.u64(N);
+            w.bytes(plane.data(), nw * 8);
+        };
+        guarded(0, [&] { write_plane(base + ".ac_gt", idx->plane_hi); });
+        guarded(1, [&] {
             ByteWriter w(base + ".ac");
             w.bitvec(ac);
-        }
-        {
+        });
+        guarded(2, [&] {
             ByteWriter w(base + ".gt");
             w.bitvec(gt);
-        }
-        write_rrr(base + ".mask", rrr_encode(mask));
-        if (h.has_klcp) {
-            klcp.resize_bits(N);
-            std::memcpy(klcp.w.data(), idx->plane_klcp.data(), nw * 8);
-            ByteWriter w(base + ".klcp");
-            w.bitvec(klcp);
-        } else {
-            std::remove((base + ".klcp").c_str());
-        }
+        });
+        guarded(3, [&] { write_rrr(base + ".mask", rrr); });
+        if (h.has_klcp) guarded(4, [&] { write_plane(base + ".klcp", idx->plane_klcp); });
+        else std::remove((base + ".klcp").c_str());
+        for (auto &t : writers) t.join();
+        for (const std::string &e : werr)
+            if (!e.empty()) throw std::runtime_error(e);
         FILE *f = std::fopen((base + ".misc").c_str(), "w");
         if (!f) throw std::runtime_error("cannot create " + base + ".misc");
         std::fprintf(f, "%llu\n%llu\n%llu\n%llu\n%llu\n%d\n", (unsigned long long)h.dollar, (unsigned long long)h.counts[0],

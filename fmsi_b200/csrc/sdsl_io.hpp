@@ -14,9 +14,12 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace fmsi {
@@ -40,11 +43,80 @@ struct BitVec {
         if (len < 64) x &= (1ull << len) - 1;
         return x;
     }
+    // ORs the low `len` (<= 64) bits of x into bits [pos, pos + len)
     void set_int(uint64_t pos, uint64_t x, unsigned len) {
-        for (unsigned t = 0; t < len; ++t)
-            if ((x >> t) & 1) set(pos + t);
+        if (len == 0) return;
+        if (len < 64) x &= (1ull << len) - 1;
+        const uint64_t wi = pos >> 6;
+        const unsigned off = pos & 63;
+        w[wi] |= x << off;
+        if (off + len > 64) w[wi + 1] |= x >> (64 - off);
+    }
+    // the same, for writers on different threads whose fields may share a word
+    void set_int_atomic(uint64_t pos, uint64_t x, unsigned len) {
+        if (len == 0) return;
+        if (len < 64) x &= (1ull << len) - 1;
+        const uint64_t wi = pos >> 6;
+        const unsigned off = pos & 63;
+        __atomic_fetch_or(&w[wi], x << off, __ATOMIC_RELAXED);
+        if (off + len > 64) __atomic_fetch_or(&w[wi + 1], x >> (64 - off), __ATOMIC_RELAXED);
     }
 };
+
+// fn(begin, end) over [0, n) cut into contiguous ranges whose boundaries are multiples of `granule`, one host
+// thread per range ($FMSI_GPU_THREADS, else the machine's hardware threads, at most 32). Exceptions propagate.
+inline void parallel_ranges(uint64_t n, uint64_t granule, const std::function<void(uint64_t, uint64_t)> &fn) {
+    unsigned T = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("FMSI_GPU_THREADS")) T = (unsigned)std::atoi(e);
+    if (T < 1) T = 1;
+    if (T > 32) T = 32;
+    const uint64_t units = (n + granule - 1) / granule;
+    if (T > units) T = units ? (unsigned)units : 1;
+    if (T == 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::string> err(T);
+    for (unsigned t = 0; t < T; ++t) {
+        const uint64_t a = std::min(n, units * t / T * granule), b = std::min(n, units * (t + 1) / T * granule);
+        th.emplace_back([&, t, a, b] {
+            try {
+                if (a < b) fn(a, b);
+            } catch (const std::exception &e) {
+                err[t] = e.what();
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    for (const std::string &e : err)
+        if (!e.empty()) throw std::runtime_error(e);
+}
+
+// A file that holds exactly one int_vector<1> (.ac_gt / .ac / .gt / .klcp): the words are read straight into the
+// vector (no intermediate copy of the file), so several files can be read by concurrent threads at disk / page
+// cache speed.
+inline void read_bitvec_file(const std::string &path, BitVec &b) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    uint64_t nbits = 0;
+    bool ok = std::fread(&nbits, 8, 1, f) == 1;
+    if (ok) {
+        std::fseek(f, 0, SEEK_END);
+        const uint64_t size = (uint64_t)std::ftell(f);
+        const uint64_t n_words = (nbits >> 6) + ((nbits & 63) ? 1 : 0);
+        ok = size >= 8 && (size - 8) / 8 >= n_words;
+        if (ok) {
+            std::fseek(f, 8, SEEK_SET);
+            b.nbits = nbits;
+            b.w.resize(n_words + 1);
+            b.w[n_words] = 0;
+            ok = n_words == 0 || std::fread(b.w.data(), 8, n_words, f) == n_words;
+        }
+    }
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("truncated file " + path);
+}
 
 struct IntVec {
     BitVec bits;
@@ -266,6 +338,8 @@ inline unsigned bit_length_or_one(uint64_t x) { return x ? 64 - (unsigned)__buil
 // 63-bit blocks stored as (class, offset in class); every 32 blocks one sample of the offset-stream
 // position and of the running rank; a full superblock in which more than half of the blocks have
 // more than 31 ones is stored complemented (classes only) and flagged in `invert`.
+// Two passes over superblocks on all host threads (a human-scale mask has 49 M blocks): classes and per-superblock
+// totals first, then — once the prefix sums give every superblock its offset-stream position and rank — the fields.
 inline RrrFile rrr_encode(const BitVec &bv) {
     const Binomials &B = Binomials::get();
     RrrFile f;
@@ -273,44 +347,65 @@ inline RrrFile rrr_encode(const BitVec &bv) {
     const uint64_t nblocks = (bv.nbits + kRrrBlock) / kRrrBlock;  // incl. a dummy block when size % 63 == 0
     const uint64_t nsuper = (nblocks + kRrrSample - 1) / kRrrSample;
     std::vector<uint8_t> cls(nblocks, 0);
-    std::vector<uint64_t> word(nblocks, 0);
-    uint64_t total_ones = 0, stream_bits = 0;
-    for (uint64_t b = 0; b < nblocks; ++b) {
+    std::vector<uint64_t> sb_off(nsuper + 1, 0), sb_ones(nsuper + 1, 0);  // per superblock, then exclusive prefix sums
+    auto block_word = [&](uint64_t b) {
         const uint64_t pos = b * kRrrBlock;
-        if (pos >= bv.nbits) break;
-        const unsigned len = (unsigned)std::min<uint64_t>(kRrrBlock, bv.nbits - pos);
-        word[b] = bv.get_int(pos, len);
-        cls[b] = (uint8_t)__builtin_popcountll(word[b]);
-        total_ones += cls[b];
-        stream_bits += B.space[cls[b]];
+        return bv.get_int(pos, (unsigned)std::min<uint64_t>(kRrrBlock, bv.nbits - pos));
+    };
+    // ranges are multiples of 64 superblocks: bt fields (32 x 6 bits = 3 words per superblock) and invert bits of
+    // different threads then never share a word
+    parallel_ranges(nsuper, 64, [&](uint64_t s0, uint64_t s1) {
+        for (uint64_t sb = s0; sb < s1; ++sb) {
+            const uint64_t b0 = sb * kRrrSample, b1 = std::min<uint64_t>(b0 + kRrrSample, nblocks);
+            uint64_t bits = 0, ones = 0;
+            for (uint64_t b = b0; b < b1 && b * kRrrBlock < bv.nbits; ++b) {
+                cls[b] = (uint8_t)__builtin_popcountll(block_word(b));
+                ones += cls[b];
+                bits += B.space[cls[b]];
+            }
+            sb_off[sb] = bits;
+            sb_ones[sb] = ones;
+        }
+    });
+    uint64_t total_ones = 0, stream_bits = 0;
+    for (uint64_t sb = 0; sb < nsuper; ++sb) {
+        const uint64_t bits = sb_off[sb], ones = sb_ones[sb];
+        sb_off[sb] = stream_bits;
+        sb_ones[sb] = total_ones;
+        stream_bits += bits;
+        total_ones += ones;
     }
     f.bt.alloc(nblocks, 6);
     f.btnr.resize_bits(std::max<uint64_t>(stream_bits, 64));
     f.btnrp.alloc(nsuper, bit_length_or_one(stream_bits));
     f.rank.alloc(nsuper + ((bv.nbits % ((uint64_t)kRrrSample * kRrrBlock)) > 0 ? 1 : 0), bit_length_or_one(total_ones));
     f.invert.resize_bits(nsuper);
-    uint64_t off = 0, ones = 0;
-    for (uint64_t sb = 0; sb < nsuper; ++sb) {
-        const uint64_t b0 = sb * kRrrSample, b1 = std::min<uint64_t>(b0 + kRrrSample, nblocks);
-        if (b0 * kRrrBlock >= bv.nbits) break;  // superblock made only of the dummy block: no sample written
-        f.btnrp.set(sb, off);
-        f.rank.set(sb, ones);
-        bool inv = false;
-        if (b0 + kRrrSample <= nblocks) {  // only complete superblocks may be complemented
-            unsigned heavy = 0;
-            for (uint64_t b = b0; b < b1; ++b) heavy += cls[b] > kRrrBlock / 2;
-            inv = heavy > kRrrSample / 2;
+    parallel_ranges(nsuper, 64, [&](uint64_t s0, uint64_t s1) {
+        for (uint64_t sb = s0; sb < s1; ++sb) {
+            const uint64_t b0 = sb * kRrrSample, b1 = std::min<uint64_t>(b0 + kRrrSample, nblocks);
+            if (b0 * kRrrBlock >= bv.nbits) break;  // superblock made only of the dummy block
+            bool inv = false;
+            if (b0 + kRrrSample <= nblocks) {  // only complete superblocks may be complemented
+                unsigned heavy = 0;
+                for (uint64_t b = b0; b < b1; ++b) heavy += cls[b] > kRrrBlock / 2;
+                inv = heavy > kRrrSample / 2;
+            }
+            if (inv) f.invert.set(sb);
+            uint64_t off = sb_off[sb];
+            for (uint64_t b = b0; b < b1; ++b) {
+                const unsigned stored = inv ? kRrrBlock - cls[b] : cls[b];
+                f.bt.set(b, stored);
+                if (b * kRrrBlock >= bv.nbits) continue;  // dummy block: class only
+                const unsigned len = B.space[stored];
+                if (len) f.btnr.set_int_atomic(off, rrr_rank_of_word(block_word(b)), len);
+                off += len;
+            }
         }
-        if (inv) f.invert.set(sb);
-        for (uint64_t b = b0; b < b1; ++b) {
-            const unsigned stored = inv ? kRrrBlock - cls[b] : cls[b];
-            f.bt.set(b, stored);
-            if (b * kRrrBlock >= bv.nbits) continue;  // dummy block: class only
-            const unsigned len = B.space[stored];
-            if (len) f.btnr.set_int(off, rrr_rank_of_word(word[b]), len);
-            off += len;
-            ones += cls[b];
-        }
+    });
+    for (uint64_t sb = 0; sb < nsuper; ++sb) {  // samples: narrow fields that share words, written by one thread
+        if (sb * kRrrSample * kRrrBlock >= bv.nbits) break;  // no sample for a superblock made only of the dummy block
+        f.btnrp.set(sb, sb_off[sb]);
+        f.rank.set(sb, sb_ones[sb]);
     }
     f.rank.set(f.rank.n - 1, total_ones);
     return f;

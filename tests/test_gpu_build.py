@@ -59,7 +59,7 @@ def test_build_reproduces_reference_index_files(case, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/fmsi not shipped")
-@pytest.mark.parametrize("name", ["polyA", "tandem", "repeats", "random300k", "two_letters"])
+@pytest.mark.parametrize("name", ["polyA", "tandem", "repeats", "random300k", "random2M", "two_letters"])
 def test_build_on_repetitive_inputs(name, tmp_path):
     rng = np.random.default_rng(5)
     if name == "polyA":
@@ -76,8 +76,8 @@ def test_build_on_repetitive_inputs(name, tmp_path):
             parts.append(bytes(u))
         s = b"".join(parts)
         ms, k = s[:-30] + s[-30:].lower(), 31
-    elif name == "random300k":
-        g = synth.random_codes(300_000, 77)
+    elif name in ("random300k", "random2M"):  # several granules / thread ranges of the save path's ac / gt compaction
+        g = synth.random_codes(300_000 if name == "random300k" else 2_000_000, 77)
         ms, k = synth.contig_superstring(g, 23, 50, 78, "max"), 23
     else:
         s = synth.codes_to_ascii(rng.integers(0, 2, size=5000, dtype=np.uint8) * 3)  # only A and T
