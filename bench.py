@@ -267,10 +267,12 @@ def reference_cpu_rate(wl: dict, per_proc: int, seed: int, procs: int | None = N
         shutil.rmtree(tmp, ignore_errors=True)
     total = P * per_proc
     query_wall = max(wall - load_s, 1e-9)
-    return dict(value=total / wall, unit=UNIT, cores=P, kind="reference", wall_s=round(wall, 3), index_load_s=round(load_s, 3),
-                value_excluding_load=total / query_wall,
+    # `value` is the steady-state query rate: the per-process index load is subtracted, as the GPU arm's
+    # numbers exclude its index set-up too; the rate over the whole wall time is reported beside it.
+    return dict(value=total / query_wall, unit=UNIT, cores=P, kind="reference", wall_s=round(wall, 3), index_load_s=round(load_s, 3),
+                query_wall_s=round(query_wall, 3), value_including_load=total / wall,
                 sample=f"{P} concurrent `fmsi query -O` processes x {per_proc} single 31-mer FASTA records (50% present), "
-                       f"same index; wall {wall:.2f}s incl. per-process index load {load_s:.2f}s")
+                       f"same index; wall {wall:.2f}s of which per-process index load {load_s:.2f}s (subtracted)")
 
 
 def algorithmic_bytes_per_kmer(wl: dict, sample: int, seed: int) -> dict:
@@ -344,7 +346,7 @@ def main():
             r = reference_cpu_rate(wl, cpu_sample, seed=5000 + 100 * s_)
             if s_ >= args.warmup:
                 vals.append(r)
-        wall = sum(v["wall_s"] for v in vals)
+        wall = sum(v["query_wall_s"] for v in vals)
         total = sum(v["cores"] * cpu_sample for v in vals)
         value = total / wall
         cb = dict(vals[-1])
