@@ -1037,12 +1037,15 @@ int query_kmers_impl(fmsi_gpu_index *idx, int mode, int output, int strands, con
     }
     if (mem != FMSI_GPU_MEM_HOST) return fail(FMSI_GPU_ERR_ARG, "bad mem");
 
-    // Host buffers: double-buffered batches so H2D, kernel and D2H of neighbouring batches overlap.
+    // Host buffers: double-buffered batches so H2D, kernel and D2H of neighbouring batches overlap. The call is
+    // bound by the H2D copies (8 B per k-mer over PCIe); what is not overlapped is the kernel + D2H of the last
+    // batch, so a call is cut into ~16 batches (at least 2 Mi k-mers each: 16 MB copies still run at link speed).
+    const size_t batch = std::min(kBatchKmers, std::max<size_t>((size_t)1 << 21, (n + 15) / 16));
     size_t done = 0;
     int b = 0;
     while (done < n) {
         Slot &s = idx->slots[b % kSlots];
-        const size_t m = std::min(kBatchKmers, n - done);
+        const size_t m = std::min(batch, n - done);
         CU(cudaEventSynchronize(s.done));
         int rc;
         if ((rc = ensure(&s.d_in, &s.in_cap, m * 8)) || (rc = ensure(&s.d_out, &s.out_cap, m * rbytes))) return rc;

@@ -146,7 +146,8 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
  * query_kmers_streaming (:181-254) when `streaming` != 0 (needs kLCP) else query_kmers_single.
  * bases: ASCII ACGTacgt only (the caller splits records at other characters like
  * ms_query, src/main.cpp:337-370); chunk c is bases[chunk_off[c] .. chunk_off[c]+chunk_len[c]),
- * chunk_len[c] >= k, and yields chunk_len[c]-k+1 results starting at result index res_off[c].
+ * chunk_len[c] >= k, and yields chunk_len[c]-k+1 results starting at result index res_off[c]
+ * (res_off[] non-decreasing; result slots that no chunk covers are left unspecified).
  * With streaming != 0 a chunk holds at most FMSI_GPU_MAX_STREAM_KMERS k-mers.
  * results layout as for fmsi_gpu_query_kmers with n = total number of k-mers.
  * k may exceed 32 here (the reference's get_range_with_pattern, src/fms_index.h:117-124, takes any k
