@@ -1,10 +1,10 @@
-// fmsi_cli.cpp — `fmsi query` / `fmsi lookup` front end over libfmsi_gpu.so.
+// fmsi_cli.cpp — `fmsi query` / `fmsi lookup` / `fmsi index` front end over libfmsi_gpu.so.
 //
 // Drop-in for the query path of the reference CLI (reference src/main.cpp: ms_query :238-375,
-// usage texts :102-130, dispatch :668-699): same flags, same index files, byte-identical stdout.
-// Everything else the reference CLI does (index, export, merge, set operations, -f functions other
-// than or/all) is out of scope for the GPU engine and is forwarded to the unchanged reference
-// binary when $FMSI_REFERENCE_BIN points at one.
+// usage texts :102-130, dispatch :668-699): same flags (incl. -f and|xor|INT-INT), same index files,
+// byte-identical stdout; and for `fmsi index` (ms_index :172-236) on the GPU builder, byte-identical files.
+// Everything else the reference CLI does (export, merge, set operations, compact, clean) is out of scope
+// for the GPU engine and is forwarded to the unchanged reference binary when $FMSI_REFERENCE_BIN points at one.
 //
 // Flow per block of records:  record-boundary scan (fasta_blocks.hpp; the only serial input step)
 //   -> kseq-exact parse -> valid ACGT runs -> GPU chunks -> fmsi_gpu_query_chunks (both strands)
