@@ -1129,8 +1129,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
 
     if (longk) {
         u64 *d_starts = (u64 *)((char *)s.d_aux + kmers_off);
-        const u32 gshift = chunk_group_shift(n_chunks, n_results);
-        extract_starts_kernel<<<blocks_for((u64)n_chunks << gshift), 256, 0, st>>>(d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, gshift, d_starts);
+        extract_starts_kernel<<<slot_blocks(n_results), 256, 0, st>>>(d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_starts);
         CU(cudaGetLastError());
         if ((rc = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_starts, n_results, d_results,
                                 on_host ? s.ls.ctr : idx->user.ctr, st)))
@@ -1138,8 +1137,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         g_launches.fetch_add(2);
     } else if (via_kmers) {
         u64 *d_kmers = (u64 *)((char *)s.d_aux + kmers_off);
-        const u32 gshift = chunk_group_shift(n_chunks, n_results);
-        extract_kmers_kernel<<<blocks_for((u64)n_chunks << gshift), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, gshift, d_kmers);
+        extract_kmers_kernel<<<slot_blocks(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
         CU(cudaGetLastError());
         g_launches.fetch_add(1);
         if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.ls : idx->user, st, gf))) return rc;

@@ -73,48 +73,63 @@ __device__ __forceinline__ u64 window(const u64 *__restrict__ packed, u64 s, u32
     return v >> (64 - 2 * len);
 }
 
-// Chunk-driven slot fill shared by extract_kmers_kernel / extract_starts_kernel (longk_kernels.cuh): a group of
-// 2^gshift consecutive threads owns chunk c and strides over its k-mers, so nobody searches res_off[] for the chunk
-// of a slot (a log2(n_chunks)-deep chain of dependent loads per warp made that search the slowest kernel of the
-// reads path). res_off[] is non-decreasing; a chunk's slots end where the next chunk's begin; slots that belong
-// to no k-mer (before the first chunk, between chunks, after the last) are filled with `gap`.
-// f(slot, start_base) stores the k-mer that starts at base `start_base`; g(slot) stores the gap value.
+// Slot -> chunk resolution shared by extract_kmers_kernel / extract_starts_kernel (longk_kernels.cuh): result slot r
+// belongs to the last chunk c with res_off[c] <= r (res_off[] non-decreasing). A binary search per slot is a
+// log2(n_chunks)-deep chain of dependent loads per warp and made this the slowest kernel of the reads path
+// (2.5 ms for 120 M slots). Here a warp owns kSlotsPerWarp = 31 * 32 consecutive slots: its 32 lanes search the 32
+// sub-block boundaries at once (one deep chain per 992 slots, 32 of them in flight per warp), then every slot
+// only searches between the chunks of its sub-block's two boundaries — a step or two, whatever the chunk sizes
+// (one 5 Mbp chunk or ten million single-k-mer chunks). f(slot, start_base) stores the k-mer that starts at base
+// `start_base`; g(slot) stores the value of slots that belong to no k-mer.
+constexpr u32 kSlotsPerWarp = 31 * 32;
+
 template <typename Fill, typename Gap>
-__device__ __forceinline__ void for_chunk_slots(const u64 *__restrict__ coff, const u32 *__restrict__ clen, const u64 *__restrict__ roff,
-                                                const u64 n_chunks, const u64 n_results, const u32 k, const u32 gshift, Fill f, Gap g) {
-    const u64 tid = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    const u64 c = tid >> gshift;
-    if (c >= n_chunks) return;
-    const u64 G = 1ull << gshift, sub = tid & (G - 1);
-    const u64 r0 = roff[c];
-    u64 r_next = (c + 1 < n_chunks) ? roff[c + 1] : n_results;
-    if (r_next > n_results) r_next = n_results;
-    const u32 len = clen[c];
-    u64 nk = len >= k ? (u64)(len - k + 1) : 0;
-    if (r0 >= r_next) nk = 0;
-    else if (nk > r_next - r0) nk = r_next - r0;
-    const u64 s0 = coff[c];
-    for (u64 pos = sub; pos < nk; pos += G) f(r0 + pos, s0 + pos);
-    for (u64 r = r0 + nk + sub; r < r_next; r += G) g(r);
-    if (c == 0)
-        for (u64 r = sub; r < r0 && r < n_results; r += G) g(r);
+__device__ __forceinline__ void for_result_slots(const u64 *__restrict__ coff, const u32 *__restrict__ clen, const u64 *__restrict__ roff,
+                                                 const u64 n_chunks, const u64 n_results, const u32 k, Fill f, Gap g) {
+    const unsigned FULL = 0xffffffffu;
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warp = (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5;
+    const u64 base = warp * kSlotsPerWarp;
+    if (base >= n_results) return;  // uniform per warp
+    u64 target = base + 32ull * lane;
+    if (target >= n_results) target = n_results - 1;
+    u64 lo = 0, hi = n_chunks;
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (__ldg(roff + mid) <= target) lo = mid;
+        else hi = mid;
+    }
+    const u64 bound = lo;  // chunk of the first slot of sub-block `lane`
+#pragma unroll 4
+    for (u32 j = 0; j < 31; ++j) {
+        u64 c0 = __shfl_sync(FULL, bound, j), c1 = __shfl_sync(FULL, bound, j + 1) + 1;
+        const u64 r = base + 32ull * j + lane;
+        if (r >= n_results) continue;  // no shuffles below this point
+        while (c1 - c0 > 1) {
+            const u64 mid = (c0 + c1) >> 1;
+            if (__ldg(roff + mid) <= r) c0 = mid;
+            else c1 = mid;
+        }
+        const u64 r0 = __ldg(roff + c0);
+        const u32 len = __ldg(clen + c0);
+        const u64 pos = r - r0;
+        if (r0 <= r && len >= k && pos + k <= len) f(r, __ldg(coff + c0) + pos);
+        else g(r);
+    }
 }
 
-// Host side: threads per chunk (log2) for the kernels above, from the mean number of k-mers per chunk.
-inline u32 chunk_group_shift(u64 n_chunks, u64 n_results) {
-    const u64 avg = n_chunks ? n_results / n_chunks : 1;
-    u32 g = 0;
-    while (g < 5 && (1ull << g) < avg) ++g;
-    return g;
+inline unsigned slot_blocks(u64 n_results, int block = 256) {
+    const u64 warps = (n_results + kSlotsPerWarp - 1) / kSlotsPerWarp;
+    return (unsigned)((warps * 32 + block - 1) / block);
 }
 
 // Non-streaming chunks: the k-mer of every result slot, materialised for the single-query kernels, which
 // then run over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
 __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
                                      const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks,
-                                     const u64 n_results, const u32 k, const u32 gshift, u64 *__restrict__ kmers) {
-    for_chunk_slots(coff, clen, roff, n_chunks, n_results, k, gshift,
-                    [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); }, [&](u64 slot) { kmers[slot] = 0; });
+                                     const u64 n_results, const u32 k, u64 *__restrict__ kmers) {
+    for_result_slots(coff, clen, roff, n_chunks, n_results, k, [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); },
+                     [&](u64 slot) { kmers[slot] = 0; });
 }
 
 enum { SP_TABLE = 0, SP_STEP = 1, SP_MX = 2 };
