@@ -503,6 +503,12 @@ def main():
                 req = tj["l1_sectors_per_launch"] * (batch / tj["batch"]) / (launch_ms / 1e3) / 1e9
                 hw.update(requests_per_kmer=round(tj["l1_sectors_per_launch"] / tj["batch"], 3), grequests_s=round(req, 1),
                           random_request_ceiling_grequests_s=tj.get("random_request_ceiling_grequests_s"))
+                if tj.get("query_stream_sectors_per_launch"):
+                    # requested sectors minus the coalesced read of the queries themselves = dependent random probes
+                    # (bucket / rows sectors); the ceiling is what tools/randbw2 measured for pure L2 misses on this part
+                    probes = (tj["l1_sectors_per_launch"] - tj["query_stream_sectors_per_launch"]) / tj["batch"]
+                    hw.update(random_probes_per_kmer=round(probes, 3), grandom_probes_s=round(probes * batch / (launch_ms / 1e3) / 1e9, 1),
+                              l2_hit_rate=tj.get("l2_hit_rate"))
         roofline = dict(bound="hbm", achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=traffic,
                         kernel=kernel_name, launch_ms=round(launch_ms, 4), peak_source=peak_src, hardware=hw,
                         algorithmic=dict(bytes_per_kmer=round(alg["bytes"], 1), lf_steps_per_kmer=round(alg["lf_steps"], 2),
