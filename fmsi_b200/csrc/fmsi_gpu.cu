@@ -77,6 +77,8 @@ struct fmsi_gpu_index {
     DictView dict{};
     FoldView fold{};
     Slot slots[kSlots];
+    cudaStream_t aux_stream = nullptr;       // second query stream of pipelined host-mode chunk calls
+    std::vector<cudaEvent_t> piece_events;   // "text piece uploaded and packed" events of those calls
     LaunchScratch user;  // scratch for MEM_DEVICE launches
     // host copies of the BWT/mask/kLCP planes, kept only for indexes made by fmsi_gpu_index_build
     std::vector<uint64_t> plane_lo, plane_hi, plane_mask, plane_klcp;
@@ -883,6 +885,8 @@ int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, idx->d_fbuckets, idx->d_frows, idx->d_fids,
                     (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
+    if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
+    for (cudaEvent_t ev : idx->piece_events) cudaEventDestroy(ev);
     for (auto &s : idx->slots) {
         for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.ls.ctr, s.ls.ovf})
             if (p) cudaFree(p);
@@ -1097,61 +1101,149 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     size_t aux_need = n_words * 8;
     const size_t kmers_off = aux_need;
     if (via_kmers) aux_need += n_results * 8;
+    // Host mode, large ordered inputs: the text goes up in pieces on one stream while the chunks that are complete
+    // run (and their results come back) on two others, so H2D, kernels and D2H overlap within the call.
+    const size_t kPiece = (size_t)8 << 20;  // bases per piece (a multiple of 32)
+    const bool pipelined = on_host && n_bases > 2 * kPiece;
+    auto bad_stream_chunk = [&](size_t c) { return chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS; };
+    const char *kBadStreamChunk = "streaming chunks must hold between 1 and FMSI_GPU_MAX_STREAM_KMERS k-mers";
     if (on_host) {
-        CU(cudaEventSynchronize(s.done));
-        if (streaming && !longk) {
-            // host-side validation of the per-chunk k-mer bound
-            for (size_t c = 0; c < n_chunks; ++c)
-                if (chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS)
-                    return fail(FMSI_GPU_ERR_ARG, "streaming chunks must hold between 1 and FMSI_GPU_MAX_STREAM_KMERS k-mers");
-        }
-        const size_t in_need = ((n_bases + 7) & ~size_t(7)) + n_chunks * (8 + 8 + 4) + 64;
+        for (auto &sl : idx->slots) CU(cudaEventSynchronize(sl.done));
+        if (pipelined && !idx->aux_stream) CU(cudaStreamCreateWithFlags(&idx->aux_stream, cudaStreamNonBlocking));
+        const size_t in_need = ((n_bases + 15) & ~size_t(15)) + n_chunks * (8 + 8 + 4) + 64;
         if ((rc = ensure(&s.d_in, &s.in_cap, in_need)) || (rc = ensure(&s.d_out, &s.out_cap, n_results * rbytes))) return rc;
         char *p = (char *)s.d_in;
-        CU(cudaMemcpyAsync(p, bases, n_bases, cudaMemcpyHostToDevice, st));
         d_bases = p;
-        p += (n_bases + 7) & ~size_t(7);
-        CU(cudaMemcpyAsync(p, chunk_off, n_chunks * 8, cudaMemcpyHostToDevice, st));
+        p += (n_bases + 15) & ~size_t(15);
         d_off = (const u64 *)p;
         p += n_chunks * 8;
-        CU(cudaMemcpyAsync(p, res_off, n_chunks * 8, cudaMemcpyHostToDevice, st));
         d_res = (const u64 *)p;
         p += n_chunks * 8;
-        CU(cudaMemcpyAsync(p, chunk_len, n_chunks * 4, cudaMemcpyHostToDevice, st));
         d_len = (const u32 *)p;
         d_results = s.d_out;
     }
+    // chunk metadata [c0, c1) to the device (host mode)
+    auto upload_chunks = [&](size_t c0, size_t c1, cudaStream_t q) -> int {
+        if (c1 <= c0) return FMSI_GPU_OK;
+        CU(cudaMemcpyAsync((void *)(d_off + c0), chunk_off + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, q));
+        CU(cudaMemcpyAsync((void *)(d_res + c0), res_off + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, q));
+        CU(cudaMemcpyAsync((void *)(d_len + c0), chunk_len + c0, (c1 - c0) * 4, cudaMemcpyHostToDevice, q));
+        return FMSI_GPU_OK;
+    };
     if ((rc = ensure(&s.d_aux, &s.aux_cap, aux_need))) return rc;
     u64 *d_packed = (u64 *)s.d_aux;
-    pack_bases_kernel<<<blocks_for(n_words), 256, 0, st>>>(d_bases, (u64)n_bases, d_packed, (u64)n_words);
-    CU(cudaGetLastError());
-    g_launches.fetch_add(1);
+    u64 *d_slots = (u64 *)((char *)s.d_aux + kmers_off);  // k-mers (or, for k > 32, start positions) of the result slots
 
-    if (longk) {
-        u64 *d_starts = (u64 *)((char *)s.d_aux + kmers_off);
-        extract_starts_kernel<<<slot_blocks(n_results), 256, 0, st>>>(d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_starts);
-        CU(cudaGetLastError());
-        if ((rc = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_starts, n_results, d_results,
-                                on_host ? s.ls.ctr : idx->user.ctr, st)))
-            return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-        g_launches.fetch_add(2);
-    } else if (via_kmers) {
-        u64 *d_kmers = (u64 *)((char *)s.d_aux + kmers_off);
-        extract_kmers_kernel<<<slot_blocks(n_results), 256, 0, st>>>(d_packed, d_off, d_len, d_res, (u64)n_chunks, (u64)n_results, (u32)k, d_kmers);
+    // The queries of chunks [c0, c1) = result slots [r0, r1), on stream `q` with launch scratch `ls`.
+    auto copy_back = [&](size_t r0, size_t r1, cudaStream_t q) -> int {
+        if (r1 > r0) CU(cudaMemcpyAsync((char *)results + r0 * rbytes, (char *)d_results + r0 * rbytes, (r1 - r0) * rbytes, cudaMemcpyDeviceToHost, q));
+        return FMSI_GPU_OK;
+    };
+    auto run_span = [&](size_t c0, size_t c1, size_t r0, size_t r1, cudaStream_t q, LaunchScratch &ls) -> int {
+        if (c1 <= c0 || r1 <= r0) return FMSI_GPU_OK;
+        void *out_span = (char *)d_results + r0 * rbytes;
+        if (longk) {
+            extract_starts_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, d_slots);
+            CU(cudaGetLastError());
+            int e = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_slots + r0, r1 - r0, out_span, ls.ctr, q);
+            if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+            g_launches.fetch_add(2);
+        } else if (via_kmers) {
+            extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, d_slots);
+            CU(cudaGetLastError());
+            g_launches.fetch_add(1);
+            int e = dispatch_query(idx, d, mode, output, strands, d_slots + r0, r1 - r0, out_span, ls, q, gf);
+            if (e) return e;
+        } else {
+            int e = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off + c0, d_len + c0, d_res + c0, c1 - c0, d_results,
+                                    ls.ctr, q);
+            if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("streaming kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+            g_launches.fetch_add(1);
+        }
+        return FMSI_GPU_OK;
+    };
+
+    auto single_batch = [&]() -> int {
+        if (on_host) {
+            if (streaming && !longk)
+                for (size_t c = 0; c < n_chunks; ++c)
+                    if (bad_stream_chunk(c)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
+            int e = upload_chunks(0, n_chunks, st);
+            if (e) return e;
+            CU(cudaMemcpyAsync((void *)d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+        }
+        pack_bases_kernel<<<blocks_for(n_words), 256, 0, st>>>(d_bases, (u64)n_bases, d_packed, (u64)n_words);
         CU(cudaGetLastError());
         g_launches.fetch_add(1);
-        if ((rc = dispatch_query(idx, d, mode, output, strands, d_kmers, n_results, d_results, on_host ? s.ls : idx->user, st, gf))) return rc;
-    } else {
-        if ((rc = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off, d_len, d_res, n_chunks, d_results,
-                                  on_host ? s.ls.ctr : idx->user.ctr, st)))
-            return fail(FMSI_GPU_ERR_CUDA, std::string("streaming kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+        int e = run_span(0, n_chunks, 0, n_results, st, on_host ? s.ls : idx->user);
+        if (e) return e;
+        if (on_host) {
+            if ((e = copy_back(0, n_results, st))) return e;
+            CU(cudaEventRecord(s.done, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return FMSI_GPU_OK;
+    };
+    if (!pipelined) return single_batch();
+
+    // Pieces [p0, p1) of the text (32-base aligned, so no packed word is written twice) on the copy stream `st`,
+    // each followed by the metadata of the chunks that now lie wholly inside the uploaded prefix; those chunks go
+    // to one of two query streams. The results of a span are copied back after the NEXT span has been launched:
+    // with pageable host buffers both copies block the calling thread, and this order keeps the GPU busy meanwhile.
+    // Chunks are validated as they are scheduled; chunks out of text order end the pipeline and the call starts
+    // over as a single batch (same results).
+    cudaStream_t qs[2] = {idx->slots[1].stream, idx->aux_stream};
+    LaunchScratch *qls[2] = {&idx->slots[1].ls, &s.ls};
+    size_t c_done = 0, r_done = 0, span = 0;
+    size_t back_r0 = 0, back_r1 = 0;  // span whose results are still on the device
+    cudaStream_t back_q = nullptr;
+    bool ordered = true;
+    for (size_t p0 = 0; p0 < n_bases && ordered; p0 += kPiece) {
+        const size_t p1 = std::min(n_bases, p0 + kPiece);
+        const bool last = p1 == n_bases;
+        CU(cudaMemcpyAsync((char *)d_bases + p0, bases + p0, p1 - p0, cudaMemcpyHostToDevice, st));
+        const size_t w0 = p0 / 32, w1 = last ? n_words : p1 / 32;
+        pack_bases_kernel<<<blocks_for(w1 - w0), 256, 0, st>>>(d_bases + 32 * w0, (u64)(n_bases - 32 * w0), d_packed + w0, (u64)(w1 - w0));
+        CU(cudaGetLastError());
         g_launches.fetch_add(1);
+        size_t c1 = c_done;
+        for (; c1 < n_chunks; ++c1) {
+            const uint64_t end = chunk_off[c1] + chunk_len[c1];
+            if (c1 > 0 && (chunk_off[c1] < chunk_off[c1 - 1] || end < chunk_off[c1 - 1] + chunk_len[c1 - 1] || res_off[c1] < res_off[c1 - 1])) {
+                ordered = false;
+                break;
+            }
+            if (end > n_bases) return fail(FMSI_GPU_ERR_ARG, "chunk exceeds the text");
+            if (!last && end > 32 * w1) break;
+            if (streaming && !longk && bad_stream_chunk(c1)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
+        }
+        if (!ordered || c1 == c_done) continue;
+        if ((rc = upload_chunks(c_done, c1, st))) return rc;
+        const size_t r1 = std::max(r_done, c1 < n_chunks ? (size_t)std::min<uint64_t>(res_off[c1], n_results) : n_results);
+        if (idx->piece_events.size() <= span) {
+            cudaEvent_t ev;
+            CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            idx->piece_events.push_back(ev);
+        }
+        CU(cudaEventRecord(idx->piece_events[span], st));
+        cudaStream_t q = qs[span & 1];
+        CU(cudaStreamWaitEvent(q, idx->piece_events[span], 0));
+        if ((rc = run_span(c_done, c1, r_done, r1, q, *qls[span & 1]))) return rc;
+        if (back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
+        back_r0 = r_done;
+        back_r1 = r1;
+        back_q = q;
+        c_done = c1;
+        r_done = r1;
+        ++span;
     }
-    if (on_host) {
-        CU(cudaMemcpyAsync(results, d_results, n_results * rbytes, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(s.done, st));
-        CU(cudaStreamSynchronize(st));
-    }
+    if (ordered && back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
+    CU(cudaEventRecord(s.done, st));
+    CU(cudaEventRecord(idx->slots[1].done, qs[0]));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(qs[0]));
+    CU(cudaStreamSynchronize(qs[1]));
+    if (!ordered) return single_batch();
     return FMSI_GPU_OK;
 }
 

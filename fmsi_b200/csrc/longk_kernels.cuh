@@ -26,9 +26,9 @@ constexpr u64 kNoKmer = ~0ull;  // start position of a result slot that belongs 
 // The start position of every result slot's k-mer in the packed text (chunks overlap by k-1 bases, so slot r of
 // chunk c starts at chunk_off[c] + (r - res_off[c])); kNoKmer for slots that belong to no k-mer.
 __global__ void extract_starts_kernel(const u64 *__restrict__ coff, const u32 *__restrict__ clen,
-                                      const u64 *__restrict__ roff, const u64 n_chunks, const u64 n_results,
-                                      const u32 k, u64 *__restrict__ starts) {
-    for_result_slots(coff, clen, roff, n_chunks, n_results, k, [&](u64 slot, u64 start) { starts[slot] = start; },
+                                      const u64 *__restrict__ roff, const u64 chunk_begin, const u64 n_chunks,
+                                      const u64 slot_begin, const u64 n_results, const u32 k, u64 *__restrict__ starts) {
+    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, [&](u64 slot, u64 start) { starts[slot] = start; },
                      [&](u64 slot) { starts[slot] = kNoKmer; });
 }
 

@@ -85,15 +85,18 @@ constexpr u32 kSlotsPerWarp = 31 * 32;
 
 template <typename Fill, typename Gap>
 __device__ __forceinline__ void for_result_slots(const u64 *__restrict__ coff, const u32 *__restrict__ clen, const u64 *__restrict__ roff,
-                                                 const u64 n_chunks, const u64 n_results, const u32 k, Fill f, Gap g) {
+                                                 const u64 chunk_begin, const u64 n_chunks, const u64 slot_begin, const u64 n_results,
+                                                 const u32 k, Fill f, Gap g) {
+    // slots [slot_begin, n_results), which belong to chunks [chunk_begin, n_chunks) (a pipelined host call resolves
+    // its result spans one after the other, each with the chunk range uploaded so far)
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const u64 warp = (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5;
-    const u64 base = warp * kSlotsPerWarp;
+    const u64 base = slot_begin + warp * kSlotsPerWarp;
     if (base >= n_results) return;  // uniform per warp
     u64 target = base + 32ull * lane;
     if (target >= n_results) target = n_results - 1;
-    u64 lo = 0, hi = n_chunks;
+    u64 lo = chunk_begin, hi = n_chunks;
     while (hi - lo > 1) {
         const u64 mid = (lo + hi) >> 1;
         if (__ldg(roff + mid) <= target) lo = mid;
@@ -126,9 +129,10 @@ inline unsigned slot_blocks(u64 n_results, int block = 256) {
 // Non-streaming chunks: the k-mer of every result slot, materialised for the single-query kernels, which
 // then run over the flat array. Slots that belong to no k-mer (gaps) get the k-mer 0.
 __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
-                                     const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks,
-                                     const u64 n_results, const u32 k, u64 *__restrict__ kmers) {
-    for_result_slots(coff, clen, roff, n_chunks, n_results, k, [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); },
+                                     const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 chunk_begin,
+                                     const u64 n_chunks, const u64 slot_begin, const u64 n_results, const u32 k,
+                                     u64 *__restrict__ kmers) {
+    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); },
                      [&](u64 slot) { kmers[slot] = 0; });
 }
 

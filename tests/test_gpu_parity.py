@@ -495,3 +495,34 @@ def test_midsize_parity_and_properties(midsize):
     assert np.array_equal(a[:len(allk)].astype(np.int64), oi.query_packed(allk, k, MODE_ALL, False))
     gi.close()
     oi.close()
+
+
+@pytest.mark.parametrize("tier", ["backward", "fold"])
+def test_large_host_chunk_calls_are_pipelined_and_identical(midsize, tier):
+    """A host-mode fmsi_gpu_query_chunks call with more than 16 MiB of text is cut into text pieces whose H2D copies
+    overlap the queries and result copies of the chunks already complete (query_chunks_impl). Its results must
+    equal those of small (single-batch) calls over the same chunks, for streamed and single queries, presence and
+    ids, both strand policies; gaps in the text between chunks and a tail after the last chunk included."""
+    g, fa = midsize
+    k = 31
+    gi = fg.Index.load(fa, use_klcp=True, dict=2 if tier == "fold" else 0)
+    reads = synth.read_queries(g, 150, 130_000, 21)  # 19.5 M bases
+    bases, offs, lens = _chunks_of(list(reads), k, 64)
+    bases = bases + b"ACGT" * 1000  # text after the last chunk
+    assert len(bases) > (16 << 20)
+    oi = OracleIndex.load(fa, use_klcp=True)
+    sample = np.concatenate([synth.pack_kmers(synth.ascii_to_codes(bases[o:o + l]), k) for o, l in zip(offs.tolist()[-300:], lens.tolist()[-300:])])
+    for mode, out, strands, streaming in ((fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY, True), (fg.MODE_OR, fg.OUT_PRESENCE, fg.STRANDS_BOTH, False),
+                                          (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_LAZY, True), (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_BOTH, False)):
+        big = gi.query_chunks(bases, offs, lens, k, mode, out, strands, streaming)
+        parts = []
+        step = 40_000  # chunks per small call: ~3.4 MiB of text each, below the pipelining threshold
+        for c in range(0, len(offs), step):
+            o, l = offs[c:c + step], lens[c:c + step]
+            lo, hi = int(o[0]), int(o[-1] + l[-1])
+            parts.append(gi.query_chunks(bases[lo:hi], o - np.uint64(lo), l, k, mode, out, strands, streaming))
+        assert np.array_equal(big, np.concatenate(parts)), (tier, mode, out, strands, streaming)
+        if out == fg.OUT_PRESENCE and strands == fg.STRANDS_LAZY:
+            assert np.array_equal(big[-len(sample):].astype(np.int64), oi.query_packed(sample, k, MODE_ALL, False))
+    gi.close()
+    oi.close()
