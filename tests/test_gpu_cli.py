@@ -154,6 +154,16 @@ def test_cli_index_infers_k_reads_gzip_and_reports_errors(tmp_path):
         assert open(f"{gz}.fmsi.{ext}", "rb").read() == open(os.path.join(d, f"ms.fa.fmsi.{ext}"), "rb").read(), ext
     r = run_cli(["index", "-k", "7", str(gz)])
     assert r.returncode == 0 and b"does not match the k inferred from the mask convention (9)" in r.stderr
+    # multi-line FASTA with CRLF line ends and a FASTQ record hold the same superstring (kseq semantics, parser.h:41-55)
+    name, seq = text.split(b"\n")[:2]
+    for fn, body in (("multi.fa", name + b" comment\r\n" + b"\r\n".join(seq[i:i + 61] for i in range(0, len(seq), 61)) + b"\r\n"),
+                     ("one.fq", b"@" + name[1:] + b"\n" + seq + b"\n+\n" + b"I" * len(seq) + b"\n")):
+        alt = tmp_path / fn
+        alt.write_bytes(body)
+        r = run_cli(["index", str(alt)])
+        assert r.returncode == 0, r.stderr.decode()
+        for ext in ("ac_gt", "ac", "gt", "mask", "klcp", "misc"):
+            assert open(f"{alt}.fmsi.{ext}", "rb").read() == open(os.path.join(d, f"ms.fa.fmsi.{ext}"), "rb").read(), (fn, ext)
     empty = tmp_path / "empty.fa"
     empty.write_bytes(b">x\n\n")
     r = run_cli(["index", str(empty)])
