@@ -361,7 +361,15 @@ def main():
 
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # Bookkeeping only (barriers, max of the elapsed time): the query path has no collective, so the group runs
+        # over gloo. Merely initialising NCCL (peer mappings; no collective in flight) slowed the random-probe kernel
+        # by 5.5 % on every rank (1.6875 vs 1.600 ms per step at N = 2, profiles/r01v_* vs r01w_*);
+        # FMSI_BENCH_DIST_BACKEND=nccl selects it anyway.
+        backend = os.environ.get("FMSI_BENCH_DIST_BACKEND", "gloo")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
 
     # ---- workload: index replica on this GPU ----------------------------------------------------
     t0 = time.time()
@@ -412,7 +420,7 @@ def main():
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        t = torch.tensor([x], dtype=torch.float64, device=dev if dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
