@@ -362,7 +362,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         # Bookkeeping only (barriers, max of the elapsed time): the query path has no collective, so the group runs
-        # over gloo. Merely initialising NCCL (peer mappings; no collective in flight) slowed the random-probe kernel
+        # over gloo. Merely initialising NCCL (no collective in flight) slowed the random-probe kernel
         # by 5.5 % on every rank (1.6875 vs 1.600 ms per step at N = 2, profiles/r01v_* vs r01w_*);
         # FMSI_BENCH_DIST_BACKEND=nccl selects it anyway.
         backend = os.environ.get("FMSI_BENCH_DIST_BACKEND", "gloo")
