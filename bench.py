@@ -369,7 +369,16 @@ def main():
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=dev)
         else:
-            dist.init_process_group(backend)
+            try:
+                dist.init_process_group(backend)
+            except Exception as ex:  # e.g. a host name that does not resolve: loopback, then NCCL (same on every rank of the box)
+                log(f"[bench] {backend} process group failed ({ex}); retrying over the loopback interface")
+                os.environ["GLOO_SOCKET_IFNAME"] = "lo"
+                try:
+                    dist.init_process_group(backend)
+                except Exception as ex2:
+                    log(f"[bench] {backend} failed again ({ex2}); falling back to nccl")
+                    dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: index replica on this GPU ----------------------------------------------------
     t0 = time.time()
