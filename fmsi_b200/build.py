@@ -73,6 +73,10 @@ def build_tools(force: bool = False, verbose: bool = True) -> None:
     exe = os.path.join(BIN, "fasta_dump")
     if force or _newer(exe, [src, os.path.join(CSRC, "fasta_blocks.hpp")]):
         _run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-lz"], verbose)
+    src = os.path.join(CSRC, "tools", "predictor_check.cpp")  # replay-split test tool (tests/test_predictor.py)
+    exe = os.path.join(BIN, "predictor_check")
+    if force or _newer(exe, [src, os.path.join(CSRC, "predictor.hpp")]):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src], verbose)
     src = os.path.join(CSRC, "tools", "rrr_roundtrip.cpp")  # sdsl format code test tool (tests/test_sdsl_io.py)
     exe = os.path.join(BIN, "rrr_roundtrip")
     if force or _newer(exe, [src, os.path.join(CSRC, "sdsl_io.hpp")]):

@@ -230,6 +230,7 @@ struct Job {
     Batch b;
     std::vector<uint8_t> raw8, fin8;
     std::vector<int64_t> raw64, fin64;
+    std::vector<fmsi::ChunkSummary> summaries;  // per reference chunk (exact -S mode), made by a worker
     std::string out;
 };
 
@@ -320,8 +321,13 @@ class Pipeline {
                 cv_.notify_all();
             } else {
                 const bool ok = query(*t.job, members_[member]);
+                {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    member_busy_[member] = false;
+                    cv_.notify_all();
+                }
+                if (ok && !cfg_.lazy && cfg_.streaming) summarize(*t.job);  // the part of the replay that needs no predictor state
                 std::unique_lock<std::mutex> lk(mu_);
-                member_busy_[member] = false;
                 if (ok) queried_[t.job->seq] = t.job;
                 cv_.notify_all();
             }
@@ -416,32 +422,78 @@ class Pipeline {
         return true;
     }
 
-    // final values in query order from the both-strand results (exact mode)
-    void replay(Job &j) {
+    // Exact -S mode, on a worker: the merged values of every reference chunk for the unswapped strand order, the
+    // predictor inputs for either order, and whether the order changes any value (predictor.hpp: ChunkSummary).
+    void summarize(Job &j) {
         Batch &b = j.b;
         const uint64_t n = b.n_results;
         const bool orders = cfg_.orders;
         if (orders) j.fin64.resize(n);
         else j.fin8.resize(n);
+        j.summaries.resize(b.ref_chunks.size());
         const int64_t *r64 = j.raw64.data();
         const uint8_t *r8 = j.raw8.data();
         auto f_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q] : (int64_t)(r8[q] & 3) - 1; };
         auto r_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q + 1] : (int64_t)((r8[q] >> 2) & 3) - 1; };
         uint64_t q0 = 0;
-        for (uint32_t m : b.ref_chunks) {
-            if (cfg_.streaming) {
-                fmsi::replay_streaming_chunk(
-                    predictor_, cfg_.mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
-                    [&](size_t q, int64_t v) {
-                        if (orders) j.fin64[q0 + q] = v;
-                        else j.fin8[q0 + q] = v == 1;
-                    });
-            } else {
-                for (uint32_t q = 0; q < m; ++q) {
-                    const int64_t v = fmsi::replay_single(predictor_, cfg_.mode, orders, f_of(q0 + q), r_of(q0 + q));
+        for (size_t c = 0; c < b.ref_chunks.size(); ++c) {
+            const uint32_t m = b.ref_chunks[c];
+            fmsi::ChunkSummary &cs = j.summaries[c];
+            fmsi::streaming_chunk_with_order(
+                false, cfg_.mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
+                [&](size_t q, int64_t v) {
                     if (orders) j.fin64[q0 + q] = v;
                     else j.fin8[q0 + q] = v == 1;
+                },
+                cs.fpr[0], cs.bpr[0]);
+            bool differs = false;
+            fmsi::streaming_chunk_with_order(
+                true, cfg_.mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
+                [&](size_t q, int64_t v) { differs |= orders ? j.fin64[q0 + q] != v : j.fin8[q0 + q] != (uint8_t)(v == 1); }, cs.fpr[1], cs.bpr[1]);
+            cs.differs = differs;
+            q0 += m;
+        }
+    }
+
+    // final values in query order from the both-strand results (exact mode), strictly in block order
+    void replay(Job &j) {
+        Batch &b = j.b;
+        const uint64_t n = b.n_results;
+        const bool orders = cfg_.orders;
+        const int64_t *r64 = j.raw64.data();
+        const uint8_t *r8 = j.raw8.data();
+        auto f_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q] : (int64_t)(r8[q] & 3) - 1; };
+        auto r_of = [&](uint64_t q) -> int64_t { return orders ? r64[2 * q + 1] : (int64_t)((r8[q] >> 2) & 3) - 1; };
+        uint64_t q0 = 0;
+        if (cfg_.streaming) {
+            // per chunk: the predictor picks the order, the summary supplies what that order logs; values were
+            // merged for the unswapped order and are redone only where the other order changes them
+            for (size_t c = 0; c < b.ref_chunks.size(); ++c) {
+                const uint32_t m = b.ref_chunks[c];
+                const fmsi::ChunkSummary &cs = j.summaries[c];
+                const bool swap = predictor_.predict_swap();
+                if (swap && cs.differs) {
+                    int fpr, bpr;
+                    fmsi::streaming_chunk_with_order(
+                        true, cfg_.mode, orders, m, [&](size_t q) { return f_of(q0 + q); }, [&](size_t q) { return r_of(q0 + q); },
+                        [&](size_t q, int64_t v) {
+                            if (orders) j.fin64[q0 + q] = v;
+                            else j.fin8[q0 + q] = v == 1;
+                        },
+                        fpr, bpr);
                 }
+                predictor_.log_result(cs.fpr[swap], cs.bpr[swap]);
+                q0 += m;
+            }
+            return;
+        }
+        if (orders) j.fin64.resize(n);
+        else j.fin8.resize(n);
+        for (uint32_t m : b.ref_chunks) {
+            for (uint32_t q = 0; q < m; ++q) {
+                const int64_t v = fmsi::replay_single(predictor_, cfg_.mode, orders, f_of(q0 + q), r_of(q0 + q));
+                if (orders) j.fin64[q0 + q] = v;
+                else j.fin8[q0 + q] = v == 1;
             }
             q0 += m;
         }

@@ -61,11 +61,11 @@ inline int64_t replay_single(StrandPredictor &p, QueryMode mode, bool orders, in
     return got;
 }
 
-// query_kmers_streaming for ONE reference chunk of m k-mers (fms_index.h:181-254): f[q], r[q] are
-// the strand values of the k-mer at chunk position q; out[q] receives the merged value.
+// query_kmers_streaming for ONE reference chunk of m k-mers (fms_index.h:181-254) with the strand order given:
+// f[q], r[q] are the strand values of the k-mer at chunk position q; out[q] receives the merged value; (fpr, bpr)
+// are the predictor inputs the reference passes to log_result for this chunk.
 template <typename GetF, typename GetR, typename Put>
-inline void replay_streaming_chunk(StrandPredictor &p, QueryMode mode, bool orders, size_t m, GetF f, GetR r, Put out) {
-    const bool swap = p.predict_swap();
+inline void streaming_chunk_with_order(bool swap, QueryMode mode, bool orders, size_t m, GetF f, GetR r, Put out, int &fpr_out, int &bpr_out) {
     const bool max_ones = mode == QueryMode::All;
     int fpr = 0, bpr = 0;
     for (size_t q = 0; q < m; ++q) {
@@ -80,7 +80,24 @@ inline void replay_streaming_chunk(StrandPredictor &p, QueryMode mode, bool orde
         out(q, res);
     }
     if (swap) std::swap(fpr, bpr);
+    fpr_out = fpr;
+    bpr_out = bpr;
+}
+
+// The same chunk under the predictor: its state picks the order, the chunk's totals update it.
+template <typename GetF, typename GetR, typename Put>
+inline void replay_streaming_chunk(StrandPredictor &p, QueryMode mode, bool orders, size_t m, GetF f, GetR r, Put out) {
+    int fpr, bpr;
+    streaming_chunk_with_order(p.predict_swap(), mode, orders, m, f, r, out, fpr, bpr);
     p.log_result(fpr, bpr);
 }
+
+// What the predictor needs from a chunk, computed ahead of the in-order replay (by any thread): the log_result
+// inputs under either strand order, and whether the merged values depend on the order at all (they do only where
+// a k-mer is decided differently by its two strands). The in-order pass is then O(1) per chunk unless `differs`.
+struct ChunkSummary {
+    int32_t fpr[2], bpr[2];  // [swap]
+    bool differs;
+};
 
 }  // namespace fmsi
