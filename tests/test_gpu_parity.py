@@ -526,3 +526,36 @@ def test_large_host_chunk_calls_are_pipelined_and_identical(midsize, tier):
             assert np.array_equal(big[-len(sample):].astype(np.int64), oi.query_packed(sample, k, MODE_ALL, False))
     gi.close()
     oi.close()
+
+
+def test_large_host_chunk_calls_with_long_k():
+    """The pipelined host path for k > 32 (queries are start positions in the packed text): 17 MiB of text against the
+    k = 47 golden index, chunks that embed the superstring's own k-mers every so often; one big call == small calls."""
+    d = os.path.join(GOLDEN, "syn_k47_max")
+    k = json.load(open(os.path.join(d, "meta.json")))["k"]
+    gi = fg.Index.load(os.path.join(d, "ms.fa"), use_klcp=True)
+    ms = open(os.path.join(d, "ms.fa"), "rb").read().split(b"\n")[1].upper()
+    rng = np.random.default_rng(3)
+    L, R = 200, 90_000
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L * R, dtype=np.uint8)].copy()
+    msa = np.frombuffer(ms, dtype=np.uint8)
+    for r in range(0, R, 50):  # every 50th chunk carries a piece of the superstring: present k-mers
+        p = int(rng.integers(0, len(msa) - 120))
+        text[r * L + 30:r * L + 150] = msa[p:p + 120]
+    bases = text.tobytes()
+    assert len(bases) > (16 << 20)
+    offs = np.arange(R, dtype=np.uint64) * L
+    lens = np.full(R, L, dtype=np.uint32)
+    for out, strands in ((fg.OUT_PRESENCE, fg.STRANDS_BOTH), (fg.OUT_ORDERS, fg.STRANDS_LAZY)):
+        big = gi.query_chunks(bases, offs, lens, k, fg.MODE_OR, out, strands, True)
+        parts = []
+        step = 15_000  # 3 MB of text per call: single batch
+        for c in range(0, R, step):
+            o, l = offs[c:c + step], lens[c:c + step]
+            lo, hi = int(o[0]), int(o[-1] + l[-1])
+            parts.append(gi.query_chunks(bases[lo:hi], o - np.uint64(lo), l, k, fg.MODE_OR, out, strands, False))
+        small = np.concatenate(parts)
+        assert np.array_equal(big, small)
+        hits = (big.reshape(-1, 2)[:, 0] if out == fg.OUT_ORDERS and strands == fg.STRANDS_BOTH else big)
+        assert (hits >= 0).any() if out == fg.OUT_ORDERS else big.any()  # the embedded superstring pieces are found
+    gi.close()
