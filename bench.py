@@ -369,6 +369,10 @@ def main():
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=dev)
         else:
+            # one node: gloo over the loopback interface (its default picks the interface the host name resolves to,
+            # and a container's host name may not resolve)
+            if backend == "gloo" and os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost", "::1"):
+                os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
             try:
                 dist.init_process_group(backend)
             except Exception as ex:  # e.g. a host name that does not resolve: loopback, then NCCL (same on every rank of the box)
