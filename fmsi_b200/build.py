@@ -73,6 +73,11 @@ def build_tools(force: bool = False, verbose: bool = True) -> None:
     exe = os.path.join(BIN, "fasta_dump")
     if force or _newer(exe, [src, os.path.join(CSRC, "fasta_blocks.hpp")]):
         _run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-lz"], verbose)
+    src = os.path.join(CSRC, "tools", "layout_dump.cpp")  # record-layout test tool (tests/test_layout.py); includes fmsi_cli.cpp
+    exe = os.path.join(BIN, "layout_dump")
+    if os.path.exists(LIB) and (force or _newer(exe, [src, os.path.join(CSRC, "fmsi_cli.cpp"), os.path.join(CSRC, "fasta_blocks.hpp"), LIB])):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+              "-L", HERE, "-lfmsi_gpu", "-lz", "-Wl,-rpath,$ORIGIN/.."], verbose)
     src = os.path.join(CSRC, "tools", "predictor_check.cpp")  # replay-split test tool (tests/test_predictor.py)
     exe = os.path.join(BIN, "predictor_check")
     if force or _newer(exe, [src, os.path.join(CSRC, "predictor.hpp")]):
