@@ -107,8 +107,15 @@ int persistent_grid(const fmsi_gpu_index *idx, Kernel kern, int block) {
 }
 
 u32 pick_chunk(size_t n, int grid, int block) {
+    static const int forced = [] {  // $FMSI_GPU_CHUNK: k-mers a warp takes per grab (design experiment switch)
+        const char *e = std::getenv("FMSI_GPU_CHUNK");
+        return e ? std::atoi(e) : 0;
+    }();
+    if (forced >= 32) return (u32)(forced / 32 * 32);
+    // ~32 grabs per warp: at the end of a launch warps run dry within one grab's duration of each other, and that
+    // ramp-down is idle memory system (256 / 512 / 1408 k-mers per grab: 42.6 / 42.5 / 42.1 G k-mers/s at human scale)
     const size_t warps = (size_t)grid * (block / 32);
-    size_t c = n / (warps * 8 + 1);
+    size_t c = n / (warps * 32 + 1);
     c = (c / 32) * 32;
     if (c < 32) c = 32;
     if (c > 2048) c = 2048;
