@@ -9,10 +9,11 @@ works without a GPU, any call needs the library and a device.
 from .api import (  # noqa: F401
     FmsiGpuError, Function, Index, Pool, load_index, lib, lib_path, MODE_OR, MODE_ALL, OUT_PRESENCE, OUT_ORDERS,
     STRANDS_LAZY, STRANDS_BOTH, MEM_HOST, MEM_DEVICE, EXPORTED_SYMBOLS, launch_count, device_count,
+    OUT_PRESENCE_BITS, TEXT_ASCII, TEXT_PACKED2, pack_text,
 )
 
 __all__ = [
     "FmsiGpuError", "Function", "Index", "Pool", "load_index", "lib", "lib_path", "MODE_OR", "MODE_ALL", "OUT_PRESENCE",
     "OUT_ORDERS", "STRANDS_LAZY", "STRANDS_BOTH", "MEM_HOST", "MEM_DEVICE", "EXPORTED_SYMBOLS",
-    "launch_count", "device_count",
+    "launch_count", "device_count", "OUT_PRESENCE_BITS", "TEXT_ASCII", "TEXT_PACKED2", "pack_text",
 ]

@@ -13,7 +13,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 MODE_OR, MODE_ALL = 0, 1
-OUT_PRESENCE, OUT_ORDERS = 0, 1
+OUT_PRESENCE, OUT_ORDERS, OUT_PRESENCE_BITS = 0, 1, 2
+TEXT_ASCII, TEXT_PACKED2 = 0, 1
 STRANDS_LAZY, STRANDS_BOTH = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 MAX_STREAM_KMERS = 64
@@ -26,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
     "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_member", "fmsi_gpu_pool_free",
     "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks", "fmsi_gpu_query_kmers_general", "fmsi_gpu_query_chunks_general",
+    "fmsi_gpu_query_chunks_packed", "fmsi_gpu_count_probes",
 ]
 F_OR, F_AND, F_XOR, F_RANGE = 0, 1, 2, 3
 
@@ -37,7 +39,7 @@ class FmsiGpuError(RuntimeError):
 
 
 class Options(C.Structure):
-    _fields_ = [("prefix_t", C.c_int32), ("sb_shift_log2", C.c_int32), ("dict", C.c_int32), ("reserved32", C.c_int32),
+    _fields_ = [("prefix_t", C.c_int32), ("sb_shift_log2", C.c_int32), ("dict", C.c_int32), ("multistep", C.c_int32),
                 ("reserved", C.c_int64 * 5)]
 
 
@@ -58,7 +60,7 @@ class IndexInfo(C.Structure):
         ("n_bwt", C.c_uint64), ("counts", C.c_uint64 * 4), ("dollar_position", C.c_uint64),
         ("mask_ones", C.c_uint64), ("hbm_bytes", C.c_uint64), ("k", C.c_int32), ("has_klcp", C.c_int32),
         ("prefix_t", C.c_int32), ("wide", C.c_int32), ("device", C.c_int32), ("dict", C.c_int32),
-        ("dict_t", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("dict_t", C.c_int32), ("multistep", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -100,6 +102,8 @@ def lib() -> C.CDLL:
     L.fmsi_gpu_query_kmers.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp,
                                         C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    L.fmsi_gpu_query_chunks_packed.argtypes = L.fmsi_gpu_query_chunks.argtypes
+    L.fmsi_gpu_count_probes.argtypes = [vp, C.c_int, u64p]
     L.fmsi_gpu_query_kmers_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int,
                                                 vp, C.c_int, vp]
@@ -143,6 +147,8 @@ def _ptr(a: np.ndarray, ty):
 def result_dtype_shape(output: int, strands: int, n: int):
     if output == OUT_PRESENCE:
         return np.uint8, (n,)
+    if output == OUT_PRESENCE_BITS:
+        return np.uint8, ((n + 7) // 8,)
     return np.int64, ((n, 2) if strands == STRANDS_BOTH else (n,))
 
 
@@ -164,27 +170,28 @@ class Index:
         self.dict = bool(info.dict)
         self.dict_kind = int(info.dict)   # 0 none, 1 SA-ordered dictionary, 2 strand-folded dictionary
         self.dict_t = int(info.dict_t)
+        self.multistep = int(info.multistep)
         self.hbm_bytes = int(info.hbm_bytes)
         self.mask_ones = int(info.mask_ones)
 
     # ---- construction -------------------------------------------------------------------------
     @staticmethod
     def load(prefix: str, use_klcp: bool = True, device: int = 0, prefix_t: int = -1, sb_shift_log2: int = 0,
-             dict: int = -1) -> "Index":
+             dict: int = -1, multistep: int = -1) -> "Index":
         """load_index(fn, use_klcp) — reference src/fms_index.h:502."""
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep)
         h = C.c_void_p()
         _check(lib().fmsi_gpu_index_load(os.fsencode(prefix), int(use_klcp), device, C.byref(opts), C.byref(h)))
         return Index(h)
 
     @staticmethod
     def from_bits(ac_gt, ac, gt, mask, counts, dollar_position, klcp=None, k=31, device=0, prefix_t=-1,
-                  sb_shift_log2=0, dict=-1) -> "Index":
+                  sb_shift_log2=0, dict=-1, multistep=-1) -> "Index":
         """In-memory fixture, the form of tests/fms_index_test.h:10-69."""
         arrs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (ac_gt, ac, gt, mask)]
         kl = np.ascontiguousarray(klcp if klcp is not None else [], dtype=np.uint8)
         cnt = _u64(counts)
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep)
         h = C.c_void_p()
         _check(lib().fmsi_gpu_index_from_bits(
             _ptr(arrs[0], C.c_uint8), arrs[0].size, _ptr(arrs[1], C.c_uint8), arrs[1].size,
@@ -195,10 +202,10 @@ class Index:
 
     @staticmethod
     def build(ms, k: int, with_klcp: bool = True, device: int = 0, prefix_t: int = -1, n: int | None = None,
-              mem: int = MEM_HOST, dict: int = -1) -> "Index":
+              mem: int = MEM_HOST, dict: int = -1, multistep: int = -1) -> "Index":
         """construct(ms, k, use_klcp) on the GPU (reference src/fms_index.h:397). ms: mask-cased ASCII
         bytes (host) or a raw device pointer (int) with n and mem=MEM_DEVICE."""
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=0, dict=dict)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=0, dict=dict, multistep=multistep)
         h = C.c_void_p()
         if isinstance(ms, int):
             ptr, length = ms, int(n)
@@ -222,6 +229,12 @@ class Index:
             self.close()
         except Exception:
             pass
+
+    def count_probes(self, on: bool) -> int:
+        """Switch the kernels' probe accounting on / off; returns the running total of dependent requests so far."""
+        total = C.c_uint64(0)
+        _check(lib().fmsi_gpu_count_probes(self._h, int(on), C.byref(total)))
+        return int(total.value)
 
     # ---- building blocks (reference names) ----------------------------------------------------
     def rank(self, i, c) -> np.ndarray:
@@ -296,10 +309,13 @@ class Index:
         _check(lib().fmsi_gpu_query_kmers(self._h, mode, output, strands, kmers_ptr, n, k, out_ptr, mem, stream or None))
 
     def query_chunks(self, bases: bytes | np.ndarray, chunk_off, chunk_len, k: int | None = None, mode: int = MODE_OR,
-                     output: int = OUT_PRESENCE, strands: int = STRANDS_LAZY, streaming: bool = False) -> np.ndarray:
-        """query_kmers<mode>() over chunks of ACGT text in host memory; results concatenated chunk by chunk."""
+                     output: int = OUT_PRESENCE, strands: int = STRANDS_LAZY, streaming: bool = False, packed: bool = False) -> np.ndarray:
+        """query_kmers<mode>() over chunks of ACGT text in host memory; results concatenated chunk by chunk.
+        packed=True sends the text 2-bit packed (fmsi_gpu_query_chunks_packed); the packing is done here, on the host."""
         k = self.k if k is None else k
         b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.ascontiguousarray(bases, dtype=np.uint8)
+        if packed:
+            return self._query_chunks_packed(pack_text(b), b.size, chunk_off, chunk_len, k, mode, output, strands, streaming)
         off = _u64(chunk_off)
         ln = np.ascontiguousarray(chunk_len, dtype=np.uint32)
         cnt = ln.astype(np.int64) - k + 1
@@ -315,6 +331,36 @@ class Index:
                                           off.ctypes.data, ln.ctypes.data, res_off.ctypes.data, off.size, n_res, k,
                                           out.ctypes.data, MEM_HOST, None))
         return out
+
+
+    def _query_chunks_packed(self, words: np.ndarray, n_bases: int, chunk_off, chunk_len, k, mode, output, strands, streaming) -> np.ndarray:
+        off = _u64(chunk_off)
+        ln = np.ascontiguousarray(chunk_len, dtype=np.uint32)
+        cnt = ln.astype(np.int64) - k + 1
+        if (cnt < 1).any():
+            raise ValueError("every chunk must hold at least one k-mer")
+        res_off = np.zeros(off.size, dtype=np.uint64)
+        if off.size:
+            res_off[1:] = np.cumsum(cnt)[:-1].astype(np.uint64)
+        n_res = int(cnt.sum())
+        dt, shape = result_dtype_shape(output, strands, n_res)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_query_chunks_packed(self._h, mode, output, strands, int(streaming), words.ctypes.data, n_bases,
+                                                 off.ctypes.data, ln.ctypes.data, res_off.ctypes.data, off.size, n_res, k,
+                                                 out.ctypes.data, MEM_HOST, None))
+        return out
+
+
+def pack_text(ascii_bases: np.ndarray) -> np.ndarray:
+    """ASCII ACGTacgt -> FMSI_GPU_TEXT_PACKED2 words (32 bases per uint64, first base in the highest bits)."""
+    b = np.ascontiguousarray(ascii_bases, dtype=np.uint8)
+    x = (b >> 1) & 3
+    codes = (x ^ (x >> 1)).astype(np.uint64)
+    n_words = (b.size + 31) // 32
+    pad = np.zeros(n_words * 32, dtype=np.uint64)
+    pad[:b.size] = codes
+    shifts = (62 - 2 * np.arange(32, dtype=np.uint64)).astype(np.uint64)
+    return np.bitwise_or.reduce(pad.reshape(n_words, 32) << shifts[None, :], axis=1)
 
 
 class Pool:

@@ -11,9 +11,23 @@ namespace fmsi {
 typedef uint64_t u64;
 typedef unsigned int u32;
 
+// Multi-step rank sector (multistep.cuh): 224 SA rows of ONE m-mer x of preceding bases.
+//   cnt  : C_m[x] + #{rows r < 224 b whose suffix is preceded by x}   (C_m[x] = #suffixes smaller than x)
+//   bits : bit r % 224 set iff row r's suffix is preceded by x (first bit = lowest bit of bits[0])
+// so m LF-steps (m applications of update_range, reference src/fms_index.h:98-103) cost one sector.
+struct alignas(32) MultiBlock {
+    uint32_t cnt;
+    uint32_t bits[7];
+};
+static_assert(sizeof(MultiBlock) == 32, "one sector");
+constexpr uint32_t kMultiRows = 224;
+
 struct DevIndex {
     const RankBlock *rank;
     const AuxBlock *aux;
+    const MultiBlock *multi;  // [4^m][multi_nblk], x-major; null when the tier is not built
+    u32 multi_m;              // bases per multi-step probe (0 = off, else 2 or 3)
+    u32 multi_nblk;           // N / 224 + 1
     const void *table;    // 4^t entries, 1 << tshift bytes apart, each starting with {i, j}: u32 pairs
                           // (narrow; 32-byte dictionary buckets when tshift == 5) or u64 pairs (wide)
     const u64 *sb_base;   // [n_superblocks][4]
@@ -29,17 +43,37 @@ struct DevIndex {
 template <bool WIDE> struct PosT { typedef u32 type; };
 template <> struct PosT<true> { typedef u64 type; };
 
+// L2 fill granularity of the random probes. A plain load makes L2 fetch the whole 128-byte line from DRAM for a
+// 32-byte probe (ncu, r01b: 3.7x the requested bytes, DRAM at 0.89 of peak); `.L2::64B` asks for a 64-byte fill.
+// -DFMSI_LD_PLAIN builds the A/B variant without the qualifier.
+#ifdef FMSI_LD_PLAIN
+#define FMSI_L2_HINT ""
+#else
+#define FMSI_L2_HINT ".L2::64B"
+#endif
+
 // One sector, bypassing L1 allocation (no reuse inside an SM for random probes).
 __device__ __forceinline__ void ld_sector(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate" FMSI_L2_HINT ".v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                  : "l"(p));
 }
 // One sector through L1 (streaming path: consecutive probes revisit the same block).
 __device__ __forceinline__ void ld_sector_l1(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc" FMSI_L2_HINT ".v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                  : "l"(p));
+}
+// 8 / 16 bytes of a random table entry
+__device__ __forceinline__ uint2 ld_pair32(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate" FMSI_L2_HINT ".v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ ulonglong2 ld_pair64(const void *p) {
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate" FMSI_L2_HINT ".v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
 }
 
 __device__ __forceinline__ u64 low_mask(u32 nbits) {  // nbits in [0, 63]
@@ -63,6 +97,23 @@ __device__ __forceinline__ typename PosT<WIDE>::type lf_map(const DevIndex &d, u
     // '$' is stored as A: ranks of A past the dollar slot are one too high (fms_index.h:81).
     r -= (pos_t)((c == 0) & ((u64)i > d.dollar));
     return r;
+}
+
+// ones among the first n bits of a 64-bit (32-bit) word, n any integer: 0 for n <= 0, all for n >= 64 (32)
+__device__ __forceinline__ u32 popc_upto64(u64 w, int n) {
+    if (n <= 0) return 0u;
+    return (u32)__popcll(n >= 64 ? w : (w & ((1ull << n) - 1ull)));
+}
+__device__ __forceinline__ u32 popc_upto32(u32 w, int n) {
+    if (n <= 0) return 0u;
+    return (u32)__popc(n >= 32 ? w : (w & ((1u << n) - 1u)));
+}
+
+// m LF-steps at once from one multi-step sector (a = cnt | bits[0] << 32, b..d = bits[1..6]):
+// cnt + #{set bits before offset i % 224}.
+__device__ __forceinline__ u32 lf_multi(u64 a, u64 b, u64 c, u64 d, u32 off) {
+    const int o = (int)off;
+    return (u32)a + popc_upto32((u32)(a >> 32), o) + popc_upto64(b, o - 32) + popc_upto64(c, o - 96) + popc_upto64(d, o - 160);
 }
 
 // 2-bit reverse complement of a packed k-mer (first base in the highest used bits).

@@ -21,6 +21,7 @@
 #include "index_convert.cuh"
 #include "index_layout.hpp"
 #include "longk_kernels.cuh"
+#include "multistep.cuh"
 #include "query_kernels.cuh"
 #include "stream_kernels.cuh"
 
@@ -70,6 +71,8 @@ struct fmsi_gpu_index {
     DevIndex dev{};
     void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr, *d_rows = nullptr;
     void *d_fbuckets = nullptr, *d_frows = nullptr, *d_fids = nullptr;  // strand-folded dictionary (fold.cuh)
+    void *d_multi = nullptr;                                            // multi-step rank arrays (multistep.cuh)
+    size_t b_multi = 0;
     size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
     size_t b_fbuckets = 0, b_frows = 0, b_fids = 0;
     uint64_t hbm_bytes = 0;
@@ -80,6 +83,10 @@ struct fmsi_gpu_index {
     cudaStream_t aux_stream = nullptr;       // second query stream of pipelined host-mode chunk calls
     std::vector<cudaEvent_t> piece_events;   // "text piece uploaded and packed" events of those calls
     LaunchScratch user;  // scratch for MEM_DEVICE launches
+    unsigned long long *d_probes = nullptr;  // fmsi_gpu_count_probes: running total of the kernels' dependent requests
+    bool count_probes = false;
+    void *d_user_bytes = nullptr;  // MEM_DEVICE calls with bit-packed output: the byte results before packing
+    size_t user_bytes_cap = 0;
     // host copies of the BWT/mask/kLCP planes, kept only for indexes made by fmsi_gpu_index_build
     std::vector<uint64_t> plane_lo, plane_hi, plane_mask, plane_klcp;
 };
@@ -96,6 +103,8 @@ int ensure(void **p, size_t *cap, size_t need) {
     *cap = want;
     return FMSI_GPU_OK;
 }
+
+inline unsigned long long *probe_ctr(const fmsi_gpu_index *idx) { return idx->count_probes ? idx->d_probes : nullptr; }
 
 inline unsigned blocks_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
 
@@ -130,7 +139,7 @@ int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers,
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     const u32 chunk = pick_chunk(n, grid, kQueryBlock);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr, GenF{0, 0, 0});
+    kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr, GenF{0, 0, 0}, probe_ctr(idx));
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
@@ -142,11 +151,11 @@ int launch_general(const fmsi_gpu_index *idx, const DevIndex &d, const GenF &gf,
     if (idx->wide) {
         auto kern = query_kmers_kernel<K_MODE_GENERAL, K_OUT_PRESENCE, K_STRANDS_LAZY, true, false>;
         const int grid = persistent_grid(idx, kern, kQueryBlock);
-        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf, probe_ctr(idx));
     } else {
         auto kern = query_kmers_kernel<K_MODE_GENERAL, K_OUT_PRESENCE, K_STRANDS_LAZY, false, false>;
         const int grid = persistent_grid(idx, kern, kQueryBlock);
-        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf);
+        kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), nullptr, nullptr, gf, probe_ctr(idx));
     }
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
@@ -175,7 +184,7 @@ int launch_dict(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, 
     CU(cudaGetLastError());
     auto fix = query_kmers_kernel<MODE, OUT, STRANDS, false, true>;
     const int fgrid = persistent_grid(idx, fix, kQueryBlock);
-    fix<<<fgrid, kQueryBlock, 0, st>>>(d, kmers, 0, out, ls.ctr + 2, 32u, (const u32 *)ls.ovf, ls.ctr + 1, GenF{0, 0, 0});
+    fix<<<fgrid, kQueryBlock, 0, st>>>(d, kmers, 0, out, ls.ctr + 2, 32u, (const u32 *)ls.ovf, ls.ctr + 1, GenF{0, 0, 0}, probe_ctr(idx));
     CU(cudaGetLastError());
     g_launches.fetch_add(2);
     return FMSI_GPU_OK;
@@ -195,7 +204,7 @@ int launch_fold_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *o
     auto kern = fold_query_kernel<MODE, OUT, STRANDS, PAY64, LD64>;
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(idx->fold, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock));
+    kern<<<grid, kQueryBlock, 0, st>>>(idx->fold, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), probe_ctr(idx));
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
@@ -410,6 +419,48 @@ int alloc_slots(fmsi_gpu_index *idx) {
     return alloc_scratch(idx->user);
 }
 
+// Multi-step rank arrays for the backward-search kernels (multistep.cuh). opts->multistep / $FMSI_GPU_MULTISTEP:
+// 0 = off, 2 / 3 = bases per probe, -1 = auto: 2 for narrow indexes when no dictionary tier is resident (the
+// dictionary tiers answer single k-mers themselves) and the arrays fit in a quarter of the free memory.
+int setup_multistep(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
+    int want = opts ? opts->multistep : -1;
+    if (const char *e = std::getenv("FMSI_GPU_MULTISTEP")) want = std::atoi(e);
+    if (want == 0) return FMSI_GPU_OK;
+    if (want != -1 && want != 2 && want != 3) return fail(FMSI_GPU_ERR_ARG, "multistep must be -1, 0, 2 or 3");
+    const HostIndex &h = idx->meta;
+    const bool narrow = !idx->wide && h.n < (1ull << 32) - 256;
+    if (!narrow) return FMSI_GPU_OK;  // wide indexes keep single steps
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    u32 m = 2;
+    if (want == -1) {
+        if (idx->fold.enabled || idx->dict.enabled) return FMSI_GPU_OK;
+        if (multi_bytes(h.n, 2) + multi_build_scratch_bytes(h.n, 2) > free_b / 4) return FMSI_GPU_OK;
+    } else {
+        m = (u32)want;
+        if (multi_bytes(h.n, m) + multi_build_scratch_bytes(h.n, m) > free_b - free_b / 16)
+            return fail(FMSI_GPU_ERR_NOMEM, "multi-step rank arrays do not fit in device memory");
+    }
+    MultiBlock *multi = nullptr;
+    u32 nblk = 0;
+    uint64_t launches = 0;
+    try {
+        build_multi_on_device(idx->dev, m, &multi, &nblk, &launches);
+    } catch (const std::exception &e) {
+        const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || std::string(e.what()).find("out of memory") != std::string::npos;
+        if (oom && want == -1) return FMSI_GPU_OK;
+        return fail(oom ? FMSI_GPU_ERR_NOMEM : FMSI_GPU_ERR_CUDA, std::string("multi-step rank arrays: ") + e.what());
+    }
+    g_launches.fetch_add(launches);
+    idx->d_multi = multi;
+    idx->b_multi = multi_bytes(h.n, m);
+    idx->hbm_bytes += idx->b_multi;
+    idx->dev.multi = multi;
+    idx->dev.multi_m = m;
+    idx->dev.multi_nblk = nblk;
+    return FMSI_GPU_OK;
+}
+
 // Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table or dictionary,
 // streams, launch scratch.
 int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
@@ -418,6 +469,9 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     d.rank = reinterpret_cast<const RankBlock *>(idx->d_rank);
     d.aux = reinterpret_cast<const AuxBlock *>(idx->d_aux);
     d.table = nullptr;
+    d.multi = nullptr;
+    d.multi_m = 0;
+    d.multi_nblk = 0;
     d.sb_base = reinterpret_cast<const u64 *>(idx->d_sb);
     d.n = h.n;
     d.dollar = h.dollar;
@@ -503,6 +557,7 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
         rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
     }
     if (rc) return rc;
+    if ((rc = setup_multistep(idx, opts))) return rc;
     return alloc_slots(idx);
 }
 
@@ -655,6 +710,23 @@ int fmsi_gpu_device_count(void) {
     return n;
 }
 uint64_t fmsi_gpu_launch_count(void) { return g_launches.load(); }
+
+int fmsi_gpu_count_probes(fmsi_gpu_index *idx, int on, uint64_t *total) {
+    if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
+    CU(cudaSetDevice(idx->device));
+    if (!idx->d_probes) {
+        CU(cudaMalloc(&idx->d_probes, sizeof(unsigned long long)));
+        CU(cudaMemset(idx->d_probes, 0, sizeof(unsigned long long)));
+    }
+    CU(cudaDeviceSynchronize());
+    if (total) {
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, idx->d_probes, sizeof v, cudaMemcpyDeviceToHost));
+        *total = v;
+    }
+    idx->count_probes = on != 0;
+    return FMSI_GPU_OK;
+}
 
 int fmsi_gpu_index_load(const char *prefix, int use_klcp, int device, const fmsi_gpu_options *opts,
                         fmsi_gpu_index **out) {
@@ -890,7 +962,7 @@ int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     if (!idx) return FMSI_GPU_OK;
     cudaSetDevice(idx->device);
     for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, idx->d_fbuckets, idx->d_frows, idx->d_fids,
-                    (void *)idx->user.ctr, idx->user.ovf})
+                    idx->d_multi, idx->d_user_bytes, (void *)idx->d_probes, (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
     for (cudaEvent_t ev : idx->piece_events) cudaEventDestroy(ev);
@@ -919,6 +991,7 @@ int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info
     info->dict_t = idx->fold.enabled ? (int32_t)idx->fold.t : idx->dict.enabled ? (int32_t)idx->dev.t : 0;
     info->wide = idx->wide;
     info->device = idx->device;
+    info->multistep = (int32_t)idx->dev.multi_m;
     return FMSI_GPU_OK;
 }
 
@@ -1034,35 +1107,53 @@ int query_kmers_impl(fmsi_gpu_index *idx, int mode, int output, int strands, con
                      const uint64_t *kmers, size_t n, int k, void *results, int mem, void *stream) {
     if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
     if (k < 1 || k > 32) return fail(FMSI_GPU_ERR_K, "k must be in [1, 32] for packed k-mers");
+    const bool bits = output == FMSI_GPU_OUT_PRESENCE_BITS;  // presence bytes, then packed 8 per byte on the device
+    if (bits) output = FMSI_GPU_OUT_PRESENCE;
     if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL && !(mode == FMSI_GPU_MODE_GENERAL_ && gf)) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
-        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH) || (bits && strands != FMSI_GPU_STRANDS_LAZY))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
     if (n == 0) return FMSI_GPU_OK;
     if (!kmers || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
     const DevIndex d = dev_for_k(idx, k);
     const size_t rbytes = result_bytes(output, strands);
+    int rc;
 
     if (mem == FMSI_GPU_MEM_DEVICE) {
-        return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->user, (cudaStream_t)stream, gf);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!bits) return dispatch_query(idx, d, mode, output, strands, kmers, n, results, idx->user, st, gf);
+        if ((rc = ensure(&idx->d_user_bytes, &idx->user_bytes_cap, n))) return rc;
+        if ((rc = dispatch_query(idx, d, mode, output, strands, kmers, n, idx->d_user_bytes, idx->user, st, gf))) return rc;
+        pack_presence_bits_kernel<<<blocks_for((n + 7) / 8), 256, 0, st>>>((const unsigned char *)idx->d_user_bytes, (u64)n, (unsigned char *)results);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return FMSI_GPU_OK;
     }
     if (mem != FMSI_GPU_MEM_HOST) return fail(FMSI_GPU_ERR_ARG, "bad mem");
 
     // Host buffers: double-buffered batches so H2D, kernel and D2H of neighbouring batches overlap. The call is
     // bound by the H2D copies (8 B per k-mer over PCIe); what is not overlapped is the kernel + D2H of the last
-    // batch, so a call is cut into ~16 batches (at least 2 Mi k-mers each: 16 MB copies still run at link speed).
-    const size_t batch = std::min(kBatchKmers, std::max<size_t>((size_t)1 << 21, (n + 15) / 16));
+    // batch, so a call is cut into ~16 batches (at least 2 Mi k-mers each: 16 MB copies still run at link speed;
+    // a multiple of 64 k-mers, so that bit-packed results of a batch start on a byte boundary).
+    const size_t batch = (std::min(kBatchKmers, std::max<size_t>((size_t)1 << 21, (n + 15) / 16)) + 63) & ~size_t(63);
     size_t done = 0;
     int b = 0;
     while (done < n) {
         Slot &s = idx->slots[b % kSlots];
         const size_t m = std::min(batch, n - done);
         CU(cudaEventSynchronize(s.done));
-        int rc;
         if ((rc = ensure(&s.d_in, &s.in_cap, m * 8)) || (rc = ensure(&s.d_out, &s.out_cap, m * rbytes))) return rc;
+        if (bits && (rc = ensure(&s.d_aux, &s.aux_cap, (m + 7) / 8))) return rc;
         CU(cudaMemcpyAsync(s.d_in, kmers + done, m * 8, cudaMemcpyHostToDevice, s.stream));
         if ((rc = dispatch_query(idx, d, mode, output, strands, (const u64 *)s.d_in, m, s.d_out, s.ls, s.stream, gf))) return rc;
-        CU(cudaMemcpyAsync((char *)results + done * rbytes, s.d_out, m * rbytes, cudaMemcpyDeviceToHost, s.stream));
+        if (bits) {
+            pack_presence_bits_kernel<<<blocks_for((m + 7) / 8), 256, 0, s.stream>>>((const unsigned char *)s.d_out, (u64)m, (unsigned char *)s.d_aux);
+            CU(cudaGetLastError());
+            g_launches.fetch_add(1);
+            CU(cudaMemcpyAsync((char *)results + done / 8, s.d_aux, (m + 7) / 8, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            CU(cudaMemcpyAsync((char *)results + done * rbytes, s.d_out, m * rbytes, cudaMemcpyDeviceToHost, s.stream));
+        }
         CU(cudaEventRecord(s.done, s.stream));
         done += m;
         ++b;
@@ -1072,22 +1163,31 @@ int query_kmers_impl(fmsi_gpu_index *idx, int mode, int output, int strands, con
 }
 
 int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming, const GenF *gf,
-                      const char *bases, size_t n_bases, const uint64_t *chunk_off,
+                      const void *text, int text_format, size_t n_bases, const uint64_t *chunk_off,
                       const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                       size_t n_results, int k, void *results, int mem, void *stream) {
     if (!idx) return fail(FMSI_GPU_ERR_ARG, "null index");
     if (k < 1 || k > FMSI_GPU_MAX_K) return fail(FMSI_GPU_ERR_K, "k must be in [1, FMSI_GPU_MAX_K]");
+    const bool bits = output == FMSI_GPU_OUT_PRESENCE_BITS;  // presence bytes, packed 8 per byte once all are in
+    if (bits) output = FMSI_GPU_OUT_PRESENCE;
     if ((mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL && !(mode == FMSI_GPU_MODE_GENERAL_ && gf)) || (output != FMSI_GPU_OUT_PRESENCE && output != FMSI_GPU_OUT_ORDERS) ||
-        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH))
+        (strands != FMSI_GPU_STRANDS_LAZY && strands != FMSI_GPU_STRANDS_BOTH) || (bits && strands != FMSI_GPU_STRANDS_LAZY))
         return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    if (text_format != FMSI_GPU_TEXT_ASCII && text_format != FMSI_GPU_TEXT_PACKED2) return fail(FMSI_GPU_ERR_ARG, "bad text format");
     if (streaming && !idx->meta.has_klcp) return fail(FMSI_GPU_ERR_KLCP, "kLCP array was not loaded for the given index");
+    // the kLCP array describes (k-1)-mers of the index's own k (construct_klcp, fms_index.h:357-385)
+    if (streaming && k <= 32 && k != idx->meta.k) return fail(FMSI_GPU_ERR_K, "streaming queries need k equal to the index's k");
     if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
-    if (!bases || !chunk_off || !chunk_len || !res_off || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    if (!text || !chunk_off || !chunk_len || !res_off || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
     const DevIndex d = dev_for_k(idx, k);
     const size_t rbytes = result_bytes(output, strands);
     const bool on_host = mem == FMSI_GPU_MEM_HOST;
     if (!on_host && mem != FMSI_GPU_MEM_DEVICE) return fail(FMSI_GPU_ERR_ARG, "bad mem");
+    const bool packed_in = text_format == FMSI_GPU_TEXT_PACKED2;
+    const char *bases = packed_in ? nullptr : (const char *)text;
+    const u64 *words_in = packed_in ? (const u64 *)text : nullptr;
+    const size_t n_words_in = (n_bases + 31) / 32;
 
     Slot &s = idx->slots[0];
     cudaStream_t st = on_host ? s.stream : (cudaStream_t)stream;
@@ -1104,7 +1204,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     const bool longk = k > 32;
     const bool via_kmers = longk || !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k) ||
                                                          (idx->dict.enabled && (u32)k == idx->dict.k && d.t && n_results < (1ull << 32))));
-    const size_t n_words = (n_bases + 31) / 32 + 4;
+    const size_t n_words = n_words_in + 4;
     size_t aux_need = n_words * 8;
     const size_t kmers_off = aux_need;
     if (via_kmers) aux_need += n_results * 8;
@@ -1117,17 +1217,23 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     if (on_host) {
         for (auto &sl : idx->slots) CU(cudaEventSynchronize(sl.done));
         if (pipelined && !idx->aux_stream) CU(cudaStreamCreateWithFlags(&idx->aux_stream, cudaStreamNonBlocking));
-        const size_t in_need = ((n_bases + 15) & ~size_t(15)) + n_chunks * (8 + 8 + 4) + 64;
-        if ((rc = ensure(&s.d_in, &s.in_cap, in_need)) || (rc = ensure(&s.d_out, &s.out_cap, n_results * rbytes))) return rc;
+        const size_t text_stage = packed_in ? 0 : ((n_bases + 15) & ~size_t(15));
+        const size_t in_need = text_stage + n_chunks * (8 + 8 + 4) + 64;
+        // bit-packed output: the packed bits sit behind the byte results
+        const size_t out_need = n_results * rbytes + (bits ? ((n_results + 7) / 8 + 64) : 0);
+        if ((rc = ensure(&s.d_in, &s.in_cap, in_need)) || (rc = ensure(&s.d_out, &s.out_cap, out_need))) return rc;
         char *p = (char *)s.d_in;
         d_bases = p;
-        p += (n_bases + 15) & ~size_t(15);
+        p += text_stage;
         d_off = (const u64 *)p;
         p += n_chunks * 8;
         d_res = (const u64 *)p;
         p += n_chunks * 8;
         d_len = (const u32 *)p;
         d_results = s.d_out;
+    } else if (bits) {
+        if ((rc = ensure(&idx->d_user_bytes, &idx->user_bytes_cap, n_results))) return rc;
+        d_results = idx->d_user_bytes;
     }
     // chunk metadata [c0, c1) to the device (host mode)
     auto upload_chunks = [&](size_t c0, size_t c1, cudaStream_t q) -> int {
@@ -1141,29 +1247,59 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     u64 *d_packed = (u64 *)s.d_aux;
     u64 *d_slots = (u64 *)((char *)s.d_aux + kmers_off);  // k-mers (or, for k > 32, start positions) of the result slots
 
+    // Packed words [w0, w1) of the text on stream q: ASCII text is uploaded (host mode) and packed on the device,
+    // 2-bit text (FMSI_GPU_TEXT_PACKED2: the same layout) is copied as it is; words past the text are zeroed.
+    auto stage_words = [&](size_t w0, size_t w1, cudaStream_t q) -> int {
+        if (w1 <= w0) return FMSI_GPU_OK;
+        if (packed_in) {
+            const size_t e = std::min(w1, n_words_in);
+            if (e > w0) CU(cudaMemcpyAsync(d_packed + w0, words_in + w0, (e - w0) * 8, on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, q));
+            if (w1 > std::max(e, w0)) CU(cudaMemsetAsync(d_packed + std::max(e, w0), 0, (w1 - std::max(e, w0)) * 8, q));
+            return FMSI_GPU_OK;
+        }
+        if (on_host) {
+            const size_t b0 = 32 * w0, b1 = std::min(n_bases, 32 * w1);
+            if (b1 > b0) CU(cudaMemcpyAsync((char *)d_bases + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, q));
+        }
+        pack_bases_kernel<<<blocks_for(w1 - w0), 256, 0, q>>>(d_bases + 32 * w0, (u64)(n_bases - std::min(n_bases, 32 * w0)), d_packed + w0, (u64)(w1 - w0));
+        CU(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return FMSI_GPU_OK;
+    };
+
     // The queries of chunks [c0, c1) = result slots [r0, r1), on stream `q` with launch scratch `ls`.
     auto copy_back = [&](size_t r0, size_t r1, cudaStream_t q) -> int {
-        if (r1 > r0) CU(cudaMemcpyAsync((char *)results + r0 * rbytes, (char *)d_results + r0 * rbytes, (r1 - r0) * rbytes, cudaMemcpyDeviceToHost, q));
+        if (r1 > r0 && !bits) CU(cudaMemcpyAsync((char *)results + r0 * rbytes, (char *)d_results + r0 * rbytes, (r1 - r0) * rbytes, cudaMemcpyDeviceToHost, q));
+        return FMSI_GPU_OK;
+    };
+    // bit-packed output: all byte results are in d_results (stream q ordered after them) -> bits -> caller
+    auto finish_bits = [&](cudaStream_t q) -> int {
+        if (!bits) return FMSI_GPU_OK;
+        unsigned char *d_bits = on_host ? (unsigned char *)d_results + ((n_results + 63) & ~size_t(63)) : (unsigned char *)results;
+        pack_presence_bits_kernel<<<blocks_for((n_results + 7) / 8), 256, 0, q>>>((const unsigned char *)d_results, (u64)n_results, d_bits);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(1);
+        if (on_host) CU(cudaMemcpyAsync(results, d_bits, (n_results + 7) / 8, cudaMemcpyDeviceToHost, q));
         return FMSI_GPU_OK;
     };
     auto run_span = [&](size_t c0, size_t c1, size_t r0, size_t r1, cudaStream_t q, LaunchScratch &ls) -> int {
         if (c1 <= c0 || r1 <= r0) return FMSI_GPU_OK;
         void *out_span = (char *)d_results + r0 * rbytes;
         if (longk) {
-            extract_starts_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, d_slots);
+            extract_starts_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, (u64)n_bases, d_slots);
             CU(cudaGetLastError());
             int e = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_slots + r0, r1 - r0, out_span, ls.ctr, q);
             if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)e));
             g_launches.fetch_add(2);
         } else if (via_kmers) {
-            extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, d_slots);
+            extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, (u64)n_bases, d_slots);
             CU(cudaGetLastError());
             g_launches.fetch_add(1);
             int e = dispatch_query(idx, d, mode, output, strands, d_slots + r0, r1 - r0, out_span, ls, q, gf);
             if (e) return e;
         } else {
-            int e = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, d_off + c0, d_len + c0, d_res + c0, c1 - c0, d_results,
-                                    ls.ctr, q);
+            int e = dispatch_stream(idx->wide, idx->sm_count, d, mode, output, strands, d_packed, (u64)n_bases, d_off + c0, d_len + c0, d_res + c0, c1 - c0,
+                                    d_results, ls.ctr, q, probe_ctr(idx));
             if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("streaming kernel launch: ") + cudaGetErrorString((cudaError_t)e));
             g_launches.fetch_add(1);
         }
@@ -1172,18 +1308,18 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
 
     auto single_batch = [&]() -> int {
         if (on_host) {
-            if (streaming && !longk)
-                for (size_t c = 0; c < n_chunks; ++c)
-                    if (bad_stream_chunk(c)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
+            for (size_t c = 0; c < n_chunks; ++c) {
+                if (chunk_off[c] + chunk_len[c] > n_bases) return fail(FMSI_GPU_ERR_ARG, "chunk exceeds the text");
+                if (streaming && !longk && bad_stream_chunk(c)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
+            }
             int e = upload_chunks(0, n_chunks, st);
             if (e) return e;
-            CU(cudaMemcpyAsync((void *)d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
         }
-        pack_bases_kernel<<<blocks_for(n_words), 256, 0, st>>>(d_bases, (u64)n_bases, d_packed, (u64)n_words);
-        CU(cudaGetLastError());
-        g_launches.fetch_add(1);
-        int e = run_span(0, n_chunks, 0, n_results, st, on_host ? s.ls : idx->user);
+        int e = stage_words(0, n_words, st);
         if (e) return e;
+        e = run_span(0, n_chunks, 0, n_results, st, on_host ? s.ls : idx->user);
+        if (e) return e;
+        if ((e = finish_bits(st))) return e;
         if (on_host) {
             if ((e = copy_back(0, n_results, st))) return e;
             CU(cudaEventRecord(s.done, st));
@@ -1208,11 +1344,8 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     for (size_t p0 = 0; p0 < n_bases && ordered; p0 += kPiece) {
         const size_t p1 = std::min(n_bases, p0 + kPiece);
         const bool last = p1 == n_bases;
-        CU(cudaMemcpyAsync((char *)d_bases + p0, bases + p0, p1 - p0, cudaMemcpyHostToDevice, st));
         const size_t w0 = p0 / 32, w1 = last ? n_words : p1 / 32;
-        pack_bases_kernel<<<blocks_for(w1 - w0), 256, 0, st>>>(d_bases + 32 * w0, (u64)(n_bases - 32 * w0), d_packed + w0, (u64)(w1 - w0));
-        CU(cudaGetLastError());
-        g_launches.fetch_add(1);
+        if ((rc = stage_words(w0, w1, st))) return rc;
         size_t c1 = c_done;
         for (; c1 < n_chunks; ++c1) {
             const uint64_t end = chunk_off[c1] + chunk_len[c1];
@@ -1251,6 +1384,10 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     CU(cudaStreamSynchronize(qs[0]));
     CU(cudaStreamSynchronize(qs[1]));
     if (!ordered) return single_batch();
+    if (bits) {  // every span's byte results are on the device: pack and fetch them
+        if ((rc = finish_bits(st))) return rc;
+        CU(cudaStreamSynchronize(st));
+    }
     return FMSI_GPU_OK;
 }
 
@@ -1268,8 +1405,16 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
                           size_t n_bases, const uint64_t *chunk_off, const uint32_t *chunk_len, const uint64_t *res_off,
                           size_t n_chunks, size_t n_results, int k, void *results, int mem, void *stream) {
     if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
-    return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, bases, n_bases, chunk_off, chunk_len, res_off, n_chunks,
+    return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, bases, FMSI_GPU_TEXT_ASCII, n_bases, chunk_off, chunk_len, res_off, n_chunks,
                              n_results, k, results, mem, stream);
+}
+
+int fmsi_gpu_query_chunks_packed(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming, const uint64_t *text2,
+                                 size_t n_bases, const uint64_t *chunk_off, const uint32_t *chunk_len, const uint64_t *res_off,
+                                 size_t n_chunks, size_t n_results, int k, void *results, int mem, void *stream) {
+    if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, text2, FMSI_GPU_TEXT_PACKED2, n_bases, chunk_off, chunk_len, res_off,
+                             n_chunks, n_results, k, results, mem, stream);
 }
 
 int fmsi_gpu_query_kmers_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const uint64_t *kmers, size_t n, int k,
@@ -1284,15 +1429,16 @@ int fmsi_gpu_query_chunks_general(fmsi_gpu_index *idx, const fmsi_gpu_function *
                                   size_t n_results, int k, uint8_t *results, int mem, void *stream) {
     GenF gf;
     if (!to_genf(f, gf)) return fail(FMSI_GPU_ERR_ARG, "bad demasking function");
-    return query_chunks_impl(idx, FMSI_GPU_MODE_GENERAL_, FMSI_GPU_OUT_PRESENCE, FMSI_GPU_STRANDS_LAZY, 0, &gf, bases, n_bases, chunk_off, chunk_len,
-                             res_off, n_chunks, n_results, k, results, mem, stream);
+    return query_chunks_impl(idx, FMSI_GPU_MODE_GENERAL_, FMSI_GPU_OUT_PRESENCE, FMSI_GPU_STRANDS_LAZY, 0, &gf, bases, FMSI_GPU_TEXT_ASCII, n_bases, chunk_off,
+                             chunk_len, res_off, n_chunks, n_results, k, results, mem, stream);
 }
 
 // ---------------------------------------------------------------------------------- multi-GPU pool
 }  // extern "C"
 
 struct fmsi_gpu_pool {
-    std::vector<fmsi_gpu_index *> members;  // members[0] is the caller's primary (not owned)
+    std::vector<fmsi_gpu_index *> members;  // members[0] is the caller's primary
+    fmsi_gpu_index *primary = nullptr;      // not owned: fmsi_gpu_pool_free releases every other member
 };
 
 namespace {
@@ -1336,6 +1482,7 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->b_table = src->b_table;
     r->b_sb = src->b_sb;
     r->b_rows = src->b_rows;
+    r->b_multi = src->b_multi;
     auto bail = [&](int code) {
         fmsi_gpu_index_free(r.release());
         return code;
@@ -1348,11 +1495,13 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
         (rc = replicate_array(&r->d_rows, dev, src->d_rows, src->device, src->b_rows)) ||
         (rc = replicate_array(&r->d_fbuckets, dev, src->d_fbuckets, src->device, src->b_fbuckets)) ||
         (rc = replicate_array(&r->d_frows, dev, src->d_frows, src->device, src->b_frows)) ||
-        (rc = replicate_array(&r->d_fids, dev, src->d_fids, src->device, src->b_fids)))
+        (rc = replicate_array(&r->d_fids, dev, src->d_fids, src->device, src->b_fids)) ||
+        (rc = replicate_array(&r->d_multi, dev, src->d_multi, src->device, src->b_multi)))
         return bail(rc);
     r->dev.rank = reinterpret_cast<const RankBlock *>(r->d_rank);
     r->dev.aux = reinterpret_cast<const AuxBlock *>(r->d_aux);
     r->dev.table = r->d_table;
+    r->dev.multi = reinterpret_cast<const MultiBlock *>(r->d_multi);
     r->dev.sb_base = reinterpret_cast<const u64 *>(r->d_sb);
     r->dict.rows = reinterpret_cast<const u64 *>(r->d_rows);
     r->fold.buckets = r->d_fbuckets;
@@ -1389,6 +1538,7 @@ int fmsi_gpu_pool_create(fmsi_gpu_index *primary, const int *devices, int n_devi
     if (!primary || !devices || n_devices < 1 || !out) return fail(FMSI_GPU_ERR_ARG, "bad pool arguments");
     *out = nullptr;
     std::unique_ptr<fmsi_gpu_pool> pool(new fmsi_gpu_pool());
+    pool->primary = primary;  // ownership is by identity, not by position: a failure below may come before the rotation
     bool primary_used = false;
     for (int m = 0; m < n_devices; ++m) {
         if (devices[m] == primary->device && !primary_used) {
@@ -1424,7 +1574,8 @@ fmsi_gpu_index *fmsi_gpu_pool_member(fmsi_gpu_pool *pool, int m) {
 
 int fmsi_gpu_pool_free(fmsi_gpu_pool *pool) {
     if (!pool) return FMSI_GPU_OK;
-    for (size_t m = 1; m < pool->members.size(); ++m) fmsi_gpu_index_free(pool->members[m]);
+    for (fmsi_gpu_index *m : pool->members)
+        if (m != pool->primary) fmsi_gpu_index_free(m);
     delete pool;
     return FMSI_GPU_OK;
 }

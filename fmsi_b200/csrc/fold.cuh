@@ -319,7 +319,7 @@ __device__ __forceinline__ int fold_presence(u32 st) {
 template <int MODE, int OUT, int STRANDS, bool PAY64, bool LD64>
 __global__ void __launch_bounds__(kQueryBlock)
 fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n, void *__restrict__ out,
-                  unsigned long long *__restrict__ cursor, const u32 chunk) {
+                  unsigned long long *__restrict__ cursor, const u32 chunk, unsigned long long *__restrict__ probe_ctr) {
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -333,6 +333,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
     u32 lo = 0, hi = 0, row = 0, st = 0;
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
     bool exhausted = false;
+    u32 nprobe = 0;  // dependent memory requests issued by this lane (reported when probe_ctr is given)
 
     for (;;) {
         // ---------------------------------------------------------------- refill idle lanes
@@ -396,6 +397,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
         if (isB) ld_fold_sector<LD64>(reinterpret_cast<const char *>(fv.buckets) + (bx << 5), a0, a1, a2, a3);
         if (isS) ld_fold_sector<LD64>(fv.rows + r0, a0, a1, a2, a3);
         if (isI) a0 = __ldg(reinterpret_cast<const u64 *>(fv.ids) + row);
+        nprobe += (u32)(isB || isS || isI);
 
         // ---------------------------------------------------------------- consume
         bool done = false;  // (st, row) final
@@ -489,6 +491,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
             }
         }
     }
+    count_probes(probe_ctr, nprobe);
 }
 
 }  // namespace fmsi

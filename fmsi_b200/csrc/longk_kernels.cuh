@@ -27,8 +27,9 @@ constexpr u64 kNoKmer = ~0ull;  // start position of a result slot that belongs 
 // chunk c starts at chunk_off[c] + (r - res_off[c])); kNoKmer for slots that belong to no k-mer.
 __global__ void extract_starts_kernel(const u64 *__restrict__ coff, const u32 *__restrict__ clen,
                                       const u64 *__restrict__ roff, const u64 chunk_begin, const u64 n_chunks,
-                                      const u64 slot_begin, const u64 n_results, const u32 k, u64 *__restrict__ starts) {
-    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, [&](u64 slot, u64 start) { starts[slot] = start; },
+                                      const u64 slot_begin, const u64 n_results, const u32 k, const u64 n_bases,
+                                      u64 *__restrict__ starts) {
+    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, n_bases, [&](u64 slot, u64 start) { starts[slot] = start; },
                      [&](u64 slot) { starts[slot] = kNoKmer; });
 }
 
@@ -64,6 +65,8 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
     const u32 t = d.t, k = d.k;  // t <= 16 < 32 < k
     const u64 tmask = t ? ((1ull << (2 * t)) - 1ull) : 0ull;
     const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
+    const u32 mm = WIDE ? 0u : d.multi_m;
+    const u64 xmask = (1ull << (2 * mm)) - 1ull;
 
     // lane state
     bool active = false;
@@ -158,19 +161,29 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
         const bool isT = active && phase == PH_TABLE;
         const bool isS = active && phase == PH_STEP;
         const bool isM = active && phase == PH_MASK;
-        const u64 bi = (u64)i >> 6;
-        const u64 bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+        // multi-step probe (multistep.cuh) while the register window still holds mm bases
+        const bool isX = !WIDE && isS && mm && steps >= mm && navail >= mm;
+        u64 bi, bj;
+        const void *pa, *pb;
+        if (isX) {
+            bi = (u32)i / kMultiRows;
+            bj = (u32)j / kMultiRows;
+            const MultiBlock *base = d.multi + (pat & xmask) * (u64)d.multi_nblk;
+            pa = base + bi;
+            pb = base + bj;
+        } else {
+            bi = (u64)i >> 6;
+            bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+            pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
+            pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
+        }
         const bool two = (isS || (isM && need_j)) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         pos_t ti = 0, tj = 0;
         if (isT) ld_table<WIDE>(d, pat & tmask, ti, tj);
         if (isS || isM) {
-            const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
             ld_sector(pa, a0, a1, a2, a3);
-            if (two) {
-                const void *pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
-                ld_sector(pb, b0, b1, b2, b3);
-            }
+            if (two) ld_sector(pb, b0, b1, b2, b3);
         }
 
         // ---------------------------------------------------------------- consume
@@ -185,17 +198,26 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
             if (i == j) done = true;
             else phase = PH_STEP;  // k > t always
         } else if (isS) {
-            const u32 c = (u32)pat & 3u;
-            pat >>= 2;
-            --navail;
             if (!two) {
                 b0 = a0; b1 = a1; b2 = a2; b3 = a3;
             }
-            const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
-            const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
-            i = ni;
-            j = nj;
-            --steps;
+            if (isX) {
+                const u32 oi = (u32)i - (u32)bi * kMultiRows, oj = (u32)j - (u32)bj * kMultiRows;
+                i = (pos_t)lf_multi(a0, a1, a2, a3, oi);
+                j = (pos_t)lf_multi(b0, b1, b2, b3, oj);
+                pat >>= 2 * mm;
+                navail -= mm;
+                steps -= mm;
+            } else {
+                const u32 c = (u32)pat & 3u;
+                pat >>= 2;
+                --navail;
+                const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
+                const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
+                i = ni;
+                j = nj;
+                --steps;
+            }
             if (i == j) done = true;
             else if (steps == 0) phase = PH_MASK;
             else if (navail == 0) pat = long_window(text, s, k, strand, k - steps, navail);

@@ -14,7 +14,9 @@
 //
 // A lane is in one of three phases, each costing one memory round trip:
 //   TABLE : read {i, j} of the k-mer's last t bases from the suffix table (replaces t LF-steps)
-//   STEP  : one LF-step = rank sector of i and, if j lies in another block, of j
+//   STEP  : m LF-steps from one multi-step sector (multistep.cuh; m = 2 or 3 bases per probe) while at least m
+//           steps remain, else one LF-step = rank sector of i; in either case a second sector when j lies in
+//           another block
 //   MASK  : probe the aux sector of the final interval (mask bit / mask rank)
 // All loads of an iteration are issued before any is consumed, so the lanes of a warp overlap
 // their misses even when they are in different phases.
@@ -46,6 +48,14 @@ enum { K_STRANDS_LAZY = 0, K_STRANDS_BOTH = 1 };
 
 constexpr int kQueryBlock = 256;
 
+// Probe accounting (fmsi_gpu_count_probes): the lanes' request counts, one atomic per warp at kernel exit.
+__device__ __forceinline__ void count_probes(unsigned long long *probe_ctr, u32 nprobe) {
+    if (!probe_ctr) return;
+    u32 v = nprobe;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0) atomicAdd(probe_ctr, (unsigned long long)v);
+}
+
 template <bool WIDE> struct TableEntry { u32 i, j; };
 template <> struct TableEntry<true> { u64 i, j; };
 
@@ -54,11 +64,11 @@ __device__ __forceinline__ void ld_table(const DevIndex &d, u64 slot, typename P
                                          typename PosT<WIDE>::type &j) {
     const char *p = reinterpret_cast<const char *>(d.table) + (slot << d.tshift);
     if (WIDE) {
-        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+        const ulonglong2 e = ld_pair64(p);
         i = (typename PosT<WIDE>::type)e.x;
         j = (typename PosT<WIDE>::type)e.y;
     } else {
-        const uint2 e = __ldg(reinterpret_cast<const uint2 *>(p));
+        const uint2 e = ld_pair32(p);
         i = (typename PosT<WIDE>::type)e.x;
         j = (typename PosT<WIDE>::type)e.y;
     }
@@ -87,7 +97,8 @@ template <int MODE, int OUT, int STRANDS, bool WIDE, bool INDIRECT = false>
 __global__ void __launch_bounds__(kQueryBlock)
 query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_arg, void *__restrict__ out,
                    unsigned long long *__restrict__ cursor, const u32 chunk, const u32 *__restrict__ sel = nullptr,
-                   const unsigned long long *__restrict__ n_dev = nullptr, const GenF gf = GenF{0, 0, 0}) {
+                   const unsigned long long *__restrict__ n_dev = nullptr, const GenF gf = GenF{0, 0, 0},
+                   unsigned long long *__restrict__ probe_ctr = nullptr) {
     typedef typename PosT<WIDE>::type pos_t;
     const u64 n = INDIRECT ? (u64)*n_dev : n_arg;
     const unsigned FULL = 0xffffffffu;
@@ -96,6 +107,8 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
     const u32 t = d.t, k = d.k;
     const u64 tmask = t ? ((t >= 32) ? ~0ull : ((1ull << (2 * t)) - 1ull)) : 0ull;
     const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
+    const u32 mm = WIDE ? 0u : d.multi_m;
+    const u64 xmask = (1ull << (2 * mm)) - 1ull;
 
     // lane state
     bool active = false;
@@ -108,6 +121,7 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
     u32 selA = 0, selB = 0;  // INDIRECT: result slots of the register tiles
     bool exhausted = false;
+    u32 nprobe = 0;  // dependent memory requests issued by this lane (reported when probe_ctr is given)
     auto fetch = [&](u64 q, u64 &km, u32 &sl) {
         km = 0;
         sl = 0;
@@ -189,20 +203,31 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
         const bool isT = active && phase == PH_TABLE;
         const bool isS = active && phase == PH_STEP;
         const bool isM = active && phase == PH_MASK;
-        const u64 bi = (u64)i >> 6;
-        const u64 bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+        // multi-step probe: the next mm bases in one sector of the array of that mm-mer (multistep.cuh)
+        const bool isX = !WIDE && isS && mm && steps >= mm;
+        u64 bi, bj;
+        const void *pa, *pb;
+        if (isX) {
+            bi = (u32)i / kMultiRows;
+            bj = (u32)j / kMultiRows;
+            const MultiBlock *base = d.multi + (pat & xmask) * (u64)d.multi_nblk;
+            pa = base + bi;
+            pb = base + bj;
+        } else {
+            bi = (u64)i >> 6;
+            bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+            pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
+            pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
+        }
         const bool two = (isS || (isM && need_j)) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         pos_t ti = 0, tj = 0;
         if (isT) ld_table<WIDE>(d, pat & tmask, ti, tj);
         if (isS || isM) {
-            const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
             ld_sector(pa, a0, a1, a2, a3);
-            if (two) {
-                const void *pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
-                ld_sector(pb, b0, b1, b2, b3);
-            }
+            if (two) ld_sector(pb, b0, b1, b2, b3);
         }
+        nprobe += (u32)isT + (u32)(isS || isM) + (u32)two;
 
         // ---------------------------------------------------------------- consume
         bool done = false;       // this strand's search ended
@@ -215,16 +240,24 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
             if (i == j) done = true;
             else phase = steps ? PH_STEP : PH_MASK;
         } else if (isS) {
-            const u32 c = (u32)pat & 3u;
-            pat >>= 2;
             if (!two) {
                 b0 = a0; b1 = a1; b2 = a2; b3 = a3;
             }
-            const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
-            const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
-            i = ni;
-            j = nj;
-            --steps;
+            if (isX) {
+                const u32 oi = (u32)i - (u32)bi * kMultiRows, oj = (u32)j - (u32)bj * kMultiRows;
+                i = (pos_t)lf_multi(a0, a1, a2, a3, oi);
+                j = (pos_t)lf_multi(b0, b1, b2, b3, oj);
+                pat >>= 2 * mm;
+                steps -= mm;
+            } else {
+                const u32 c = (u32)pat & 3u;
+                pat >>= 2;
+                const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
+                const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
+                i = ni;
+                j = nj;
+                --steps;
+            }
             if (i == j) done = true;
             else if (steps == 0) phase = PH_MASK;
         } else if (isM) {
@@ -284,6 +317,7 @@ query_kmers_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u64 n_
             }
         }
     }
+    count_probes(probe_ctr, nprobe);
 }
 
 // ------------------------------------------------------------------------------------------------

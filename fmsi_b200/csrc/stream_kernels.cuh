@@ -65,6 +65,21 @@ __global__ void pack_bases_kernel(const char *__restrict__ bases, const u64 n_ba
     packed[w] = v;
 }
 
+// Presence results, one byte (0 / 1) per k-mer -> one bit per k-mer, bit q & 7 of byte q >> 3 (the characters the
+// reference prints, 8 per byte): FMSI_GPU_OUT_PRESENCE_BITS. One thread per output byte.
+__global__ void pack_presence_bits_kernel(const unsigned char *__restrict__ res, const u64 n, unsigned char *__restrict__ bits) {
+    const u64 b = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    const u64 q0 = b * 8;
+    if (q0 >= n) return;
+    u64 v = 0;
+    if (q0 + 8 <= n && (reinterpret_cast<unsigned long long>(res) & 7ull) == 0) {
+        v = *reinterpret_cast<const u64 *>(res + q0);
+    } else {
+        for (u32 t = 0; t < 8 && q0 + t < n; ++t) v |= (u64)res[q0 + t] << (8 * t);
+    }
+    bits[b] = (unsigned char)(((v & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+
 // len (<= 32) bases starting at base s, as a packed k-mer.
 __device__ __forceinline__ u64 window(const u64 *__restrict__ packed, u64 s, u32 len) {
     const u64 w0 = __ldg(packed + (s >> 5)), w1 = __ldg(packed + (s >> 5) + 1);
@@ -86,7 +101,7 @@ constexpr u32 kSlotsPerWarp = 31 * 32;
 template <typename Fill, typename Gap>
 __device__ __forceinline__ void for_result_slots(const u64 *__restrict__ coff, const u32 *__restrict__ clen, const u64 *__restrict__ roff,
                                                  const u64 chunk_begin, const u64 n_chunks, const u64 slot_begin, const u64 n_results,
-                                                 const u32 k, Fill f, Gap g) {
+                                                 const u32 k, const u64 n_bases, Fill f, Gap g) {
     // slots [slot_begin, n_results), which belong to chunks [chunk_begin, n_chunks) (a pipelined host call resolves
     // its result spans one after the other, each with the chunk range uploaded so far)
     const unsigned FULL = 0xffffffffu;
@@ -116,7 +131,9 @@ __device__ __forceinline__ void for_result_slots(const u64 *__restrict__ coff, c
         const u64 r0 = __ldg(roff + c0);
         const u32 len = __ldg(clen + c0);
         const u64 pos = r - r0;
-        if (r0 <= r && len >= k && pos + k <= len) f(r, __ldg(coff + c0) + pos);
+        const u64 cs = __ldg(coff + c0);
+        // a chunk that runs past the text (device-mode callers are not validated on the host) yields no k-mers
+        if (r0 <= r && len >= k && pos + k <= len && cs + len <= n_bases) f(r, cs + pos);
         else g(r);
     }
 }
@@ -131,8 +148,8 @@ inline unsigned slot_blocks(u64 n_results, int block = 256) {
 __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *__restrict__ coff,
                                      const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 chunk_begin,
                                      const u64 n_chunks, const u64 slot_begin, const u64 n_results, const u32 k,
-                                     u64 *__restrict__ kmers) {
-    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); },
+                                     const u64 n_bases, u64 *__restrict__ kmers) {
+    for_result_slots(coff, clen, roff, chunk_begin, n_chunks, slot_begin, n_results, k, n_bases, [&](u64 slot, u64 start) { kmers[slot] = window(packed, start, k); },
                      [&](u64 slot) { kmers[slot] = 0; });
 }
 
@@ -142,9 +159,9 @@ __device__ __forceinline__ u64 sel3(u32 w, u64 w0, u64 w1, u64 w2) { return w ==
 
 template <int MODE, int OUT, int STRANDS, bool WIDE>
 __global__ void __launch_bounds__(kStreamBlock)
-stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__restrict__ coff,
+stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 n_bases, const u64 *__restrict__ coff,
               const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks, void *out,
-              unsigned long long *__restrict__ cursor, const u32 grab) {
+              unsigned long long *__restrict__ cursor, const u32 grab, unsigned long long *__restrict__ probe_ctr) {
     typedef typename PosT<WIDE>::type pos_t;
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
@@ -152,6 +169,8 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
     const u32 t = d.t, k = d.k;
     const u64 tmask = t ? ((t >= 32) ? ~0ull : ((1ull << (2 * t)) - 1ull)) : 0ull;
     const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
+    const u32 mm = WIDE ? 0u : d.multi_m;
+    const u64 xmask = (1ull << (2 * mm)) - 1ull;
 
     bool active = false;
     u32 phase = SP_TABLE, pass = 0, p = 0, nk = 0, steps = 0;
@@ -159,6 +178,7 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
     pos_t i = 0, j = 0;
     u64 cnext = 0, cend = 0;
     bool exhausted = false;
+    u32 nprobe = 0;  // dependent memory requests issued by this lane (reported when probe_ctr is given)
 
     // k-mer at chunk position q from the register-resident bases
     auto kmer_at = [&](u32 q) -> u64 {
@@ -208,7 +228,7 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
                     const u32 len = clen[my];
                     ro = roff[my];
                     nk = len - k + 1;
-                    if (len >= k && nk <= kMaxStreamKmers) {
+                    if (len >= k && nk <= kMaxStreamKmers && cs + len <= n_bases) {
                         // bases cs .. cs+95 as three aligned-to-chunk words
                         const u64 *pw = packed + (cs >> 5);
                         const u64 q0 = __ldg(pw), q1 = __ldg(pw + 1), q2 = __ldg(pw + 2);
@@ -247,20 +267,32 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
             if (pass == 0) will_cont = p > 0;
             else will_cont = (p + 1 < nk) && (STRANDS == K_STRANDS_BOTH || !((decided >> (p + 1)) & 1ull));
         }
-        const u64 bi = (u64)i >> 6;
-        const u64 bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+        // a fresh search (after a miss) takes multi-step probes like a single query (multistep.cuh); the one
+        // step that continues a neighbour's interval is a plain LF-step
+        const bool isX = !WIDE && isS && mm && steps >= mm;
+        u64 bi, bj;
+        const void *pa, *pb;
+        if (isX) {
+            bi = (u32)i / kMultiRows;
+            bj = (u32)j / kMultiRows;
+            const MultiBlock *base = d.multi + (pat & xmask) * (u64)d.multi_nblk;
+            pa = base + bi;
+            pb = base + bj;
+        } else {
+            bi = (u64)i >> 6;
+            bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
+            pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
+            pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
+        }
         const bool two = (isS || (isM && (need_j || will_cont))) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         pos_t ti = 0, tj = 0;
         if (isT) ld_table<WIDE>(d, pat & tmask, ti, tj);
         if (isS || isM) {
-            const void *pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
             ld_sector_l1(pa, a0, a1, a2, a3);
-            if (two) {
-                const void *pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
-                ld_sector_l1(pb, b0, b1, b2, b3);
-            }
+            if (two) ld_sector_l1(pb, b0, b1, b2, b3);
         }
+        nprobe += (u32)isT + (u32)(isS || isM) + (u32)two;
 
         // ---------------------------------------------------------------- consume
         bool finished = false;  // the k-mer at position p got its value for this pass
@@ -274,16 +306,24 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
             if (i == j) finished = true;
             else phase = steps ? SP_STEP : SP_MX;
         } else if (isS) {
-            const u32 c = (u32)pat & 3u;
-            pat >>= 2;
             if (!two) {
                 b0 = a0; b1 = a1; b2 = a2; b3 = a3;
             }
-            const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
-            const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
-            i = ni;
-            j = nj;
-            --steps;
+            if (isX) {
+                const u32 oi = (u32)i - (u32)bi * kMultiRows, oj = (u32)j - (u32)bj * kMultiRows;
+                i = (pos_t)lf_multi(a0, a1, a2, a3, oi);
+                j = (pos_t)lf_multi(b0, b1, b2, b3, oj);
+                pat >>= 2 * mm;
+                steps -= mm;
+            } else {
+                const u32 c = (u32)pat & 3u;
+                pat >>= 2;
+                const pos_t ni = lf_map<WIDE>(d, a0, a1, a2, a3, i, c);
+                const pos_t nj = lf_map<WIDE>(d, b0, b1, b2, b3, j, c);
+                i = ni;
+                j = nj;
+                --steps;
+            }
             if (i == j) finished = true;
             else if (steps == 0) phase = SP_MX;
         } else if (isM) {
@@ -389,11 +429,12 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 *__res
             }
         }
     }
+    count_probes(probe_ctr, nprobe);
 }
 
 template <int MODE, int OUT, int STRANDS, bool WIDE>
-int launch_stream(int sm_count, const DevIndex &d, const u64 *packed, const u64 *coff, const u32 *clen, const u64 *roff,
-                  size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st) {
+int launch_stream(int sm_count, const DevIndex &d, const u64 *packed, u64 n_bases, const u64 *coff, const u32 *clen, const u64 *roff,
+                  size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st, unsigned long long *probe_ctr) {
     auto kern = stream_kernel<MODE, OUT, STRANDS, WIDE>;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -404,31 +445,31 @@ int launch_stream(int sm_count, const DevIndex &d, const u64 *packed, const u64 
     if (grab > 512) grab = 512;
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kStreamBlock, 0, st>>>(d, packed, coff, clen, roff, (u64)n_chunks, out, cursor, (u32)grab);
+    kern<<<grid, kStreamBlock, 0, st>>>(d, packed, n_bases, coff, clen, roff, (u64)n_chunks, out, cursor, (u32)grab, probe_ctr);
     return (int)cudaGetLastError();
 }
 
 template <int MODE, int OUT, int STRANDS>
-int launch_stream_w(bool wide, int sm_count, const DevIndex &d, const u64 *packed, const u64 *coff, const u32 *clen,
-                    const u64 *roff, size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st) {
-    if (wide) return launch_stream<MODE, OUT, STRANDS, true>(sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
-    return launch_stream<MODE, OUT, STRANDS, false>(sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+int launch_stream_w(bool wide, int sm_count, const DevIndex &d, const u64 *packed, u64 n_bases, const u64 *coff, const u32 *clen,
+                    const u64 *roff, size_t n_chunks, void *out, unsigned long long *cursor, cudaStream_t st, unsigned long long *probe_ctr) {
+    if (wide) return launch_stream<MODE, OUT, STRANDS, true>(sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
+    return launch_stream<MODE, OUT, STRANDS, false>(sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
 }
 
 // returns a cudaError_t as int (0 = ok)
 inline int dispatch_stream(bool wide, int sm_count, const DevIndex &d, int mode, int output, int strands,
-                           const u64 *packed, const u64 *coff, const u32 *clen, const u64 *roff, size_t n_chunks,
-                           void *out, unsigned long long *cursor, cudaStream_t st) {
+                           const u64 *packed, u64 n_bases, const u64 *coff, const u32 *clen, const u64 *roff, size_t n_chunks,
+                           void *out, unsigned long long *cursor, cudaStream_t st, unsigned long long *probe_ctr = nullptr) {
     if (output == K_OUT_ORDERS) {
-        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
-        return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
+        return launch_stream_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
     }
     if (mode == K_MODE_ALL) {
-        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
-        return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+        if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
+        return launch_stream_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
     }
-    if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
-    return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, coff, clen, roff, n_chunks, out, cursor, st);
+    if (strands == K_STRANDS_BOTH) return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
+    return launch_stream_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(wide, sm_count, d, packed, n_bases, coff, clen, roff, n_chunks, out, cursor, st, probe_ctr);
 }
 
 }  // namespace fmsi

@@ -80,6 +80,17 @@ def genome_superstring(codes: np.ndarray, k: int) -> bytes:
     return codes_to_ascii(codes, mask)
 
 
+def random_masked_superstring(n: int, seed: int, k: int, off: float) -> bytes:
+    """n i.i.d. bases (seed) with a random mask: every position OFF with probability `off` (seed + 1), the last k-1
+    OFF. Platform-independent (numpy PCG64), so that hashes of the reference's index of it can be committed
+    (tests/golden/make_ref_index_hashes.py) and the input regenerated anywhere."""
+    codes = random_codes(n, seed)
+    rng = np.random.default_rng(seed + 1)
+    mask = rng.random(n) >= off
+    mask[n - (k - 1):] = False
+    return codes_to_ascii(codes, mask.astype(np.uint8))
+
+
 def contig_superstring(codes: np.ndarray, k: int, n_pieces: int, seed: int,
                        ones: str = "max") -> bytes:
     """Cut the genome into n_pieces contigs (consecutive contigs overlap by k-1 so no k-mer is

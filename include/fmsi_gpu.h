@@ -43,7 +43,18 @@ enum {
 /* query_mode, reference src/fms_index.h:256-260 (`general`: see fmsi_gpu_query_kmers_general). */
 enum { FMSI_GPU_MODE_OR = 0, FMSI_GPU_MODE_ALL = 1 };
 /* output_orders of query_kmers(): presence bits (`fmsi query`) or mask-rank ids (`fmsi lookup`). */
-enum { FMSI_GPU_OUT_PRESENCE = 0, FMSI_GPU_OUT_ORDERS = 1 };
+enum {
+    FMSI_GPU_OUT_PRESENCE = 0,
+    FMSI_GPU_OUT_ORDERS = 1,
+    /* presence, one BIT per k-mer: bit q & 7 of byte q >> 3 is 1 iff the reference prints '1' for k-mer q (the
+     * characters of the reference's output line, 8 per byte). STRANDS_LAZY only. results: uint8[(n + 7) / 8].
+     * The device packs the bits, so a result crosses PCIe as 1/8 byte per k-mer. */
+    FMSI_GPU_OUT_PRESENCE_BITS = 2
+};
+/* Text of fmsi_gpu_query_chunks*: ASCII ACGTacgt, or 2 bits per base (A=0 C=1 G=2 T=3, src/kmers.h:3-20), 32 bases per
+ * 64-bit word, base b in bits [62 - 2 (b & 31), 63 - 2 (b & 31)] of word b >> 5 (first base highest, like a packed
+ * k-mer); the unused low bits of the last word are ignored. */
+enum { FMSI_GPU_TEXT_ASCII = 0, FMSI_GPU_TEXT_PACKED2 = 1 };
 /* Strand policy.
  *  LAZY: forward strand first, reverse complement only if undecided — the reference's evaluation
  *        order with a neutral strand predictor (src/fms_index.h:268-299 with should_swap == false).
@@ -60,7 +71,9 @@ typedef struct {
     int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto (2, else 1, else 0 as memory allows),
                             * 0 = off (backward search), 1 = SA-ordered dictionary (one probe per strand search),
                             * 2 = strand-folded dictionary (one probe per k-mer) */
-    int32_t reserved32;
+    int32_t multistep;     /* multi-step rank arrays of the backward-search kernels (m LF-steps per memory request):
+                            * -1 = auto (2 when no dictionary tier is resident and they fit), 0 = off, 2 or 3 = bases
+                            * per probe (2.3 / 9.1 bytes of device memory per BWT position) */
     int64_t reserved[5];
 } fmsi_gpu_options;
 
@@ -77,7 +90,8 @@ typedef struct {
     int32_t device;
     int32_t dict;        /* resident dictionary tier: 0 none, 1 SA-ordered, 2 strand-folded */
     int32_t dict_t;      /* bucket depth of that tier (bases) */
-    int32_t reserved[5];
+    int32_t multistep;   /* bases per probe of the resident multi-step rank arrays (0 = none) */
+    int32_t reserved[4];
 } fmsi_gpu_index_info;
 
 const char *fmsi_gpu_last_error(void);
@@ -148,7 +162,11 @@ int fmsi_gpu_query_kmers(fmsi_gpu_index *idx, int mode, int output, int strands,
  * ms_query, src/main.cpp:337-370); chunk c is bases[chunk_off[c] .. chunk_off[c]+chunk_len[c]),
  * chunk_len[c] >= k, and yields chunk_len[c]-k+1 results starting at result index res_off[c]
  * (res_off[] non-decreasing; result slots that no chunk covers are left unspecified).
- * With streaming != 0 a chunk holds at most FMSI_GPU_MAX_STREAM_KMERS k-mers.
+ * With streaming != 0 a chunk holds at most FMSI_GPU_MAX_STREAM_KMERS k-mers and k (<= 32) must equal the index's k
+ * (FMSI_GPU_ERR_K otherwise: the kLCP array describes the (k-1)-mers of that k, src/fms_index.h:357-385).
+ * Host-mode calls validate every chunk (FMSI_GPU_ERR_ARG when one runs past the text); device-mode calls cannot,
+ * and a chunk that runs past the text yields no results there. Device-mode calls on one index share its launch
+ * scratch: serialise them (one stream at a time per index; replicas of a pool are independent).
  * results layout as for fmsi_gpu_query_kmers with n = total number of k-mers.
  * k may exceed 32 here (the reference's get_range_with_pattern, src/fms_index.h:117-124, takes any k
  * and `fmsi index` builds such indexes, src/main.cpp:225-233), up to FMSI_GPU_MAX_K: the k-mers are
@@ -161,6 +179,14 @@ int fmsi_gpu_query_chunks(fmsi_gpu_index *idx, int mode, int output, int strands
                           const char *bases, size_t n_bases, const uint64_t *chunk_off,
                           const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                           size_t n_results, int k, void *results, int mem, void *stream);
+
+/* As fmsi_gpu_query_chunks with the text already 2-bit packed (FMSI_GPU_TEXT_PACKED2: text2 holds (n_bases + 31) / 32
+ * words): a 150-base read then crosses PCIe as 0.31 bytes per k-mer instead of 1.25, and with
+ * FMSI_GPU_OUT_PRESENCE_BITS its answers return as 0.125 bytes per k-mer. chunk_off / chunk_len are in bases. */
+int fmsi_gpu_query_chunks_packed(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
+                                 const uint64_t *text2, size_t n_bases, const uint64_t *chunk_off,
+                                 const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
+                                 size_t n_results, int k, void *results, int mem, void *stream);
 
 /* ---- f-MS framework: general demasking functions -------------------------------------------- */
 /* query_kmers<query_mode::general>() — reference src/fms_index.h:317-327 with single_query_general
@@ -209,6 +235,13 @@ int fmsi_gpu_pool_query_chunks(fmsi_gpu_pool *pool, int mode, int output, int st
 /* Number of kernel launches issued by this library on behalf of the calling process so far
  * (bench.py reports it as gpu_launches). */
 uint64_t fmsi_gpu_launch_count(void);
+
+/* Probe accounting for the roofline (bench.py): while `on`, the backward-search, streaming and strand-folded
+ * dictionary kernels launched for this index add the number of DEPENDENT memory requests they issue (suffix-table
+ * entries, rank / multi-step / aux / bucket / rows sectors; not the coalesced reads of the queries themselves) to a
+ * running total. The call synchronises the device, stores the total so far in *total (may be NULL) and switches the
+ * accounting on or off. Off by default: the timed kernels carry only a null-pointer test. */
+int fmsi_gpu_count_probes(fmsi_gpu_index *idx, int on, uint64_t *total);
 
 #ifdef __cplusplus
 }

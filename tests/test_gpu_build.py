@@ -92,6 +92,31 @@ def test_build_on_repetitive_inputs(name, tmp_path):
     idx.close()
 
 
+HASHES = os.path.join(GOLDEN, "ref_index_hashes.json")
+
+
+@pytest.mark.skipif(not os.path.exists(HASHES), reason="tests/golden/ref_index_hashes.json not generated")
+@pytest.mark.parametrize("name", sorted(json.load(open(HASHES))) if os.path.exists(HASHES) else [])
+def test_build_matches_reference_hashes_at_scale(name, tmp_path):
+    """Byte identity with the reference's `fmsi index` at 100 Mbp (and 20 Mbp without kLCP, half the mask OFF): the
+    reference was run once on the seeded input where it compiles (tests/golden/make_ref_index_hashes.py: 110 s,
+    1.6 GB) and the SHA-256 of each of its files committed; the GPU builder must reproduce every one of them."""
+    import hashlib
+    case = json.load(open(HASHES))[name]
+    ms = synth.random_masked_superstring(case["n"], case["seed"], case["k"], case["off"])
+    h = hashlib.sha256(b">ms\n" + ms + b"\n").hexdigest()
+    assert h == case["input_sha256"], "the seeded input is not the one the reference indexed"
+    idx = fg.Index.build(ms, case["k"], with_klcp=case["klcp"], dict=0, multistep=0, prefix_t=0)
+    out = str(tmp_path / "ms.fa")
+    idx.save(out)
+    for ext, want in case["files"].items():
+        got = hashlib.sha256(open(f"{out}.fmsi.{ext}", "rb").read()).hexdigest()
+        assert got == want, f"{name}: .fmsi.{ext} differs from the reference's file"
+        assert os.path.getsize(f"{out}.fmsi.{ext}") == case["sizes"][ext]
+    assert os.path.exists(f"{out}.fmsi.klcp") == case["klcp"]
+    idx.close()
+
+
 def test_build_rejects_bad_input():
     with pytest.raises(fg.FmsiGpuError):
         fg.Index.build(b"ACGTNACGT", 3)

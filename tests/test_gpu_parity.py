@@ -68,8 +68,18 @@ def test_unit_goldens_on_device(t):
     assert idx3.kmer_order_if_present([c[0] for c in ko], [c[1] for c in ko]).tolist() == [c[2] for c in ko]
 
 
-def test_streaming_and_query_goldens_on_device():
-    idx3 = gpu_fixture(3)
+TIER_KW = {"auto": {}, "backward": {"dict": 0}, "backward_t0": {"dict": 0, "prefix_t": 0}, "backward_ms0": {"dict": 0, "multistep": 0},
+           "backward_ms3": {"dict": 0, "multistep": 3}, "backward_t0_ms2": {"dict": 0, "prefix_t": 0, "multistep": 2}}
+
+
+@pytest.mark.parametrize("tier", list(TIER_KW))
+def test_streaming_and_query_goldens_on_device(tier):
+    """The reference's streaming / query unit goldens on every tier: with `auto` a dictionary tier answers the
+    chunks (fmsi_gpu.cu: via_kmers), with dict = 0 stream_kernel / query_kmers_kernel do — with and without the
+    suffix table, with single and multi-step probes."""
+    kw = TIER_KW[tier]
+    idx3 = gpu_fixture(3, **kw)
+    assert bool(idx3.dict) == (tier == "auto")
     # QUERY_KMERS_STREAMING :223-249 and _ORDERS :251-276 (results here do not depend on the predictor)
     for q, mo, want in [("CACATACA", False, "111001"), ("TGTATGTG", False, "100111"), ("CACATTGT", False, "111001"), ("CACATACA", True, "111001")]:
         got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, mode=fg.MODE_ALL if mo else fg.MODE_OR, streaming=True)
@@ -80,14 +90,14 @@ def test_streaming_and_query_goldens_on_device():
         for streaming in (True, False):
             got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, output=fg.OUT_ORDERS, streaming=streaming)
             assert got.tolist() == want
-    idx1 = gpu_fixture(1)
+    idx1 = gpu_fixture(1, **kw)
     # QUERY_ORDERS :278-306 / QUERY :308-332 (k varies per case)
     for q, k, want in [("A", 1, [3]), ("AG", 2, [-1]), ("CA", 2, [0]), ("AC", 2, [2]), ("TA", 2, [3]), ("GGTA", 4, [1]), ("ATGG", 4, [-1]),
                        ("GA", 2, [-1]), ("GGG", 3, [-1]), ("CC", 2, [1]), ("CCAG", 2, [1, 0, -1])]:
         assert idx1.query_chunks(q.encode(), [0], [len(q)], k=k, output=fg.OUT_ORDERS).tolist() == want
     for q, want in [("A", 1), ("AG", 0), ("CA", 1), ("GGTA", 1), ("ATGG", 0), ("GA", 0), ("GGG", 0), ("CC", 1)]:
         assert idx1.query_kmers([pack(q)], k=len(q)).tolist() == [want]
-    idx2 = gpu_fixture(2)
+    idx2 = gpu_fixture(2, **kw)
     for q, want in [("AAGA", 1), ("AAGAA", 0), ("GGTTAAGA", 1), ("GTTAAGA", 1)]:  # QUERY2 :334-354
         assert idx2.query_kmers([pack(q)], k=len(q)).tolist() == [want]
 
@@ -105,7 +115,8 @@ def _random_kmers(rng, ms_codes, k, n):
 
 
 @pytest.mark.parametrize("case", golden_cases())
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3", "dict_auto", "fold_t1", "fold_t3"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3", "dict_auto", "fold_t1", "fold_t3",
+                                     "ms0", "ms2_t0", "ms2_t2", "ms3", "ms3_t1"])
 def test_device_matches_oracle(case, variant):
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
@@ -116,7 +127,12 @@ def test_device_matches_oracle(case, variant):
     # auto = strand-folded dictionary at the automatic depth; dict_auto = SA-ordered dictionary there.
     kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "nodict": {"dict": 0},
           "dict_t1": {"dict": 1, "prefix_t": 1}, "dict_t3": {"dict": 1, "prefix_t": 3}, "dict_auto": {"dict": 1},
-          "fold_t1": {"dict": 2, "prefix_t": 1}, "fold_t3": {"dict": 2, "prefix_t": 3}}[variant]
+          "fold_t1": {"dict": 2, "prefix_t": 1}, "fold_t3": {"dict": 2, "prefix_t": 3},
+          # backward search with the multi-step rank arrays (multistep.cuh): off / 2 / 3 bases per probe, at table depths
+          # that leave k - t a multiple of m or not (the remainder takes single steps); nodict = auto = 2 per probe
+          "ms0": {"dict": 0, "multistep": 0}, "ms2_t0": {"dict": 0, "multistep": 2, "prefix_t": 0},
+          "ms2_t2": {"dict": 0, "multistep": 2, "prefix_t": 2}, "ms3": {"dict": 0, "multistep": 3},
+          "ms3_t1": {"dict": 0, "multistep": 3, "prefix_t": 1}}[variant]
     if variant != "auto" and case not in ("syn_k31_max", "syn_k9_min", "syn_k5_min", "quirks_k3", "data_k13", "syn_k32"):
         pytest.skip("variants run on a subset")
     prefix = os.path.join(d, "ms.fa")
@@ -124,7 +140,11 @@ def test_device_matches_oracle(case, variant):
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.n == oi.n and gi.k == k and gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
     assert gi.wide == (variant == "wide")
-    assert gi.dict == (variant not in ("t0", "wide", "nodict") and k <= 32)
+    assert gi.dict == (variant not in ("t0", "wide", "nodict") and not variant.startswith("ms") and k <= 32)
+    if variant.startswith("ms") or variant == "nodict":
+        assert gi.multistep == {"ms0": 0, "ms3": 3, "ms3_t1": 3}.get(variant, 2)
+    if variant == "wide":
+        assert gi.multistep == 0
     if gi.dict:  # the tier asked for, unless the payload would not fit a row (k - t > 30: k = 32 at depth 1)
         fold_ok = k - gi.dict_t <= 30
         assert gi.dict_kind == (2 if variant in ("auto", "fold_t1", "fold_t3") and fold_ok else 1)
@@ -252,12 +272,18 @@ def _chunks_of(seq_codes_list, k, max_kmers):
 
 
 @pytest.mark.parametrize("case", ["syn_k31_max", "syn_k31_min", "syn_k9_max", "syn_k9_min", "syn_k5_min", "data_k13", "data_k31", "syn_k32", "quirks_k3_nonmax"])
-def test_chunks_streaming_and_single_match_oracle(case):
+@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "backward_ms3"])
+def test_chunks_streaming_and_single_match_oracle(case, tier):
+    """Chunks of text, streamed (-S) and single, LAZY and BOTH strands, all three outputs, against the oracle. With
+    `auto` a dictionary tier answers streamed chunks too; the dict = 0 tiers put stream_kernel (query_kmers_streaming,
+    fms_index.h:181-254) itself in front of the oracle — with and without the suffix table, with multi-step probes
+    off / 2 / 3 bases per probe after a miss."""
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
     k = meta["k"]
     prefix = os.path.join(d, "ms.fa")
-    gi = fg.Index.load(prefix, use_klcp=True)
+    gi = fg.Index.load(prefix, use_klcp=True, **TIER_KW[tier])
+    assert bool(gi.dict) == (tier == "auto")
     oi = OracleIndex.load(prefix, use_klcp=True)
     ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
     rng = np.random.default_rng(7)
@@ -295,7 +321,7 @@ def test_chunks_streaming_and_single_match_oracle(case):
 
 
 @pytest.mark.parametrize("case", ["syn_k47_max", "syn_k64_min", "syn_k97_noklcp"])
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "ms0", "ms3"])
 def test_long_k_chunks_match_oracle(case, variant):
     """k > 32 (longk_kernels.cuh): k-mers are searched from the packed text, 32 pattern characters per
     register window. Every mode, LAZY and BOTH strands, with and without `streaming`, chunks of assorted
@@ -304,8 +330,9 @@ def test_long_k_chunks_match_oracle(case, variant):
     meta = json.load(open(os.path.join(d, "meta.json")))
     k = meta["k"]
     prefix = os.path.join(d, "ms.fa")
-    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}}[variant]
+    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "ms0": {"multistep": 0}, "ms3": {"multistep": 3}}[variant]
     gi = fg.Index.load(prefix, use_klcp=meta["klcp"], **kw)
+    assert gi.multistep == {"wide": 0, "ms0": 0, "ms3": 3}.get(variant, 2)
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.k == k and not gi.dict
     ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
@@ -423,7 +450,55 @@ def test_multi_gpu_pool_matches_single_index():
                 assert np.array_equal(a, b)
     with pytest.raises(fg.FmsiGpuError):
         fg.Pool(gi, [ndev + 7])
+    # a replica that fails AFTER the primary and another replica joined the pool, with the primary not first in the
+    # device list: the failure path must release the replica and leave the primary alive (it used to free members[1:])
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Pool(gi, [0, 0, ndev + 7])
+    with pytest.raises(fg.FmsiGpuError):
+        fg.Pool(gi, [(1 % ndev), 0, ndev + 7])
+    kmers = _random_kmers(rng, ms_codes, k, 500)
+    assert np.array_equal(pool.query_kmers(kmers, k, fg.MODE_ALL), gi.query_kmers(kmers, k, fg.MODE_ALL))  # primary still usable
     pool.close()
+    assert gi.query_kmers(kmers, k, fg.MODE_ALL).shape == (len(kmers),)
+    gi.close()
+
+
+@pytest.mark.parametrize("tier", ["auto", "backward"])
+def test_bit_packed_results_and_packed_text(tier):
+    """FMSI_GPU_OUT_PRESENCE_BITS (one bit per k-mer, packed on the device) must equal the byte results packed on the
+    host, for every batch shape of the host path; fmsi_gpu_query_chunks_packed (2-bit text in) must equal the ASCII
+    call, streamed and single, every output. The byte / ASCII results are the ones checked against the oracle."""
+    d = os.path.join(GOLDEN, "syn_k31_min")
+    k = 31
+    prefix = os.path.join(d, "ms.fa")
+    gi = fg.Index.load(prefix, use_klcp=True, **TIER_KW[tier])
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    rng = np.random.default_rng(23)
+    for n in (1, 7, 8, 9, 63, 64, 65, 5003, 5_000_011):  # the last one spans several host batches
+        kmers = _random_kmers(rng, ms_codes, k, max(n, 4))[:n]
+        for mode in (fg.MODE_ALL, fg.MODE_OR):
+            by = gi.query_kmers(kmers, k, mode, fg.OUT_PRESENCE)
+            bi = gi.query_kmers(kmers, k, mode, fg.OUT_PRESENCE_BITS)
+            assert bi.shape == ((n + 7) // 8,)
+            assert np.array_equal(bi, np.packbits(by, bitorder="little")), (n, mode)
+    reads = list(synth.read_queries(ms_codes, 150, 300, 4)) + [ms_codes[:k].copy(), ms_codes[5:5 + k + 1].copy()]
+    for max_kmers in (64, 9):
+        bases, offs, lens = _chunks_of(reads, k, max_kmers)
+        words = fg.pack_text(np.frombuffer(bases, dtype=np.uint8))
+        # the packed layout is the packed k-mer layout: word 0 of the text == the first 32 bases
+        assert int(words[0]) == int(synth.pack_kmers(synth.ascii_to_codes(bases[:32]), 32)[0])
+        for streaming in (False, True):
+            for mode, out, strands in ((fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY), (fg.MODE_OR, fg.OUT_PRESENCE, fg.STRANDS_BOTH),
+                                       (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_LAZY), (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_BOTH)):
+                a = gi.query_chunks(bases, offs, lens, k, mode, out, strands, streaming)
+                b = gi.query_chunks(bases, offs, lens, k, mode, out, strands, streaming, packed=True)
+                assert np.array_equal(a, b), (max_kmers, streaming, mode, out, strands)
+            by = gi.query_chunks(bases, offs, lens, k, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY, streaming)
+            for packed in (False, True):
+                bi = gi.query_chunks(bases, offs, lens, k, fg.MODE_ALL, fg.OUT_PRESENCE_BITS, fg.STRANDS_LAZY, streaming, packed=packed)
+                assert np.array_equal(bi, np.packbits(by, bitorder="little")), (max_kmers, streaming, packed)
+    with pytest.raises(fg.FmsiGpuError):  # one bit cannot hold two strands
+        gi.query_kmers(kmers[:10], k, fg.MODE_ALL, fg.OUT_PRESENCE_BITS, fg.STRANDS_BOTH)
     gi.close()
 
 
@@ -440,6 +515,17 @@ def test_error_behaviour():
     with pytest.raises(fg.FmsiGpuError):
         gi.query_kmers([0], k=33)
     assert gi.query_kmers(np.zeros(0, np.uint64)).size == 0  # empty batch
+    gi.close()
+    d = os.path.join(GOLDEN, "syn_k31_max")
+    gi = fg.Index.load(os.path.join(d, "ms.fa"), use_klcp=True, dict=0)
+    with pytest.raises(fg.FmsiGpuError) as e:  # the kLCP array is the index's k's: streaming with another k is refused
+        gi.query_chunks(b"A" * 40, [0], [40], k=21, streaming=True)
+    assert e.value.code == -5
+    assert gi.query_chunks(b"A" * 40, [0], [40], k=21, streaming=False).shape == (20,)
+    for streaming in (False, True):
+        with pytest.raises(fg.FmsiGpuError) as e:  # a chunk that runs past the text
+            gi.query_chunks(b"A" * 40, [0, 20], [40, 40], k=31, streaming=streaming)
+        assert e.value.code == -1
     gi.close()
 
 
@@ -522,8 +608,12 @@ def test_large_host_chunk_calls_are_pipelined_and_identical(midsize, tier):
             lo, hi = int(o[0]), int(o[-1] + l[-1])
             parts.append(gi.query_chunks(bases[lo:hi], o - np.uint64(lo), l, k, mode, out, strands, streaming))
         assert np.array_equal(big, np.concatenate(parts)), (tier, mode, out, strands, streaming)
+        assert np.array_equal(big, gi.query_chunks(bases, offs, lens, k, mode, out, strands, streaming, packed=True)), (tier, "packed text")
         if out == fg.OUT_PRESENCE and strands == fg.STRANDS_LAZY:
             assert np.array_equal(big[-len(sample):].astype(np.int64), oi.query_packed(sample, k, MODE_ALL, False))
+            for packed in (False, True):
+                bits = gi.query_chunks(bases, offs, lens, k, mode, fg.OUT_PRESENCE_BITS, strands, streaming, packed=packed)
+                assert np.array_equal(bits, np.packbits(big, bitorder="little")), (tier, "bits", packed)
     gi.close()
     oi.close()
 
