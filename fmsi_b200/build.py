@@ -53,6 +53,16 @@ def build_lib(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str], verbose: bool = True) -> str:
+    """A/B variants of the library (fmsi_b200/variants/, git-ignored; selected with $FMSI_GPU_LIB)."""
+    d = os.path.join(HERE, "variants")
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, f"libfmsi_gpu_{name}.so")
+    if _newer(out, _sources()):
+        _run([_nvcc(), *NVCC_FLAGS, *[f"-D{x}" for x in defines], "-shared", "-o", out, os.path.join(CSRC, "fmsi_gpu.cu")], verbose)
+    return out
+
+
 def build_cli(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BIN, exist_ok=True)
     exe = os.path.join(BIN, "fmsi")

@@ -131,6 +131,43 @@ u32 pick_chunk(size_t n, int grid, int block) {
     return (u32)c;
 }
 
+// north_star's "hot upper levels in L2-persisting windows", as an experiment switch (profiles/backward_ab.py):
+// $FMSI_GPU_L2_PERSIST = table|rank|aux|multi[:MiB] pins the head of that array in L2 for the query launches of a
+// stream (cudaAccessPolicyWindow, hit ratio 1, misses streaming). Off by default: with the suffix table in front
+// of the search no array has a hot head left (every probe is uniformly random), and the A/B shows no gain.
+void apply_l2_persist(const fmsi_gpu_index *idx, cudaStream_t st) {
+    static const char *env = std::getenv("FMSI_GPU_L2_PERSIST");
+    if (!env || !*env) return;
+    static thread_local cudaStream_t done_for = (cudaStream_t)-1;
+    if (done_for == st) return;
+    done_for = st;
+    std::string what(env);
+    size_t mib = 96;
+    const size_t colon = what.find(':');
+    if (colon != std::string::npos) {
+        mib = (size_t)std::atoll(what.c_str() + colon + 1);
+        what = what.substr(0, colon);
+    }
+    const void *base = what == "table" ? idx->d_table : what == "rank" ? idx->d_rank : what == "aux" ? idx->d_aux : what == "multi" ? idx->d_multi : nullptr;
+    size_t avail = what == "table" ? idx->b_table : what == "rank" ? idx->b_rank : what == "aux" ? idx->b_aux : what == "multi" ? idx->b_multi : 0;
+    if (!base || !avail) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, idx->device) != cudaSuccess) return;
+    size_t bytes = std::min(avail, mib << 20);
+    bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)prop.persistingL2CacheMaxSize));
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaError_t e = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    fprintf(stderr, "[fmsi] L2 persisting window on %s: %zu MiB (%s)\n", what.c_str(), bytes >> 20, cudaGetErrorString(e));
+    cudaGetLastError();
+}
+
 // Backward-search kernel over all n queries.
 template <int MODE, int OUT, int STRANDS, bool WIDE>
 int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
@@ -138,6 +175,7 @@ int launch_query(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers,
     auto kern = query_kmers_kernel<MODE, OUT, STRANDS, WIDE, false>;
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     const u32 chunk = pick_chunk(n, grid, kQueryBlock);
+    apply_l2_persist(idx, st);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
     kern<<<grid, kQueryBlock, 0, st>>>(d, kmers, (u64)n, out, ls.ctr, chunk, nullptr, nullptr, GenF{0, 0, 0}, probe_ctr(idx));
     CU(cudaGetLastError());
