@@ -939,9 +939,9 @@ def run_workload_modes(cx: Ctx, name: str, which: list[str], steps: int, warmup:
         gi = fg.Index.load(wl["prefix"], use_klcp=True, device=cx.local_rank)
     setup_s = time.time() - t_setup
     oi = None
+    if cx.rank == 0 and w.get("device_built") and (want_cpu or not cx.args.no_parity):
+        safe(f"{name}: index files", lambda: ensure_files(gi, wl))
     if cx.rank == 0 and not cx.args.no_parity:
-        if w.get("device_built"):
-            ensure_files(gi, wl)
         oi = safe(f"{name}: oracle load", lambda: load_oracle(wl, True))
         if isinstance(oi, dict):
             oi = None
@@ -1068,9 +1068,9 @@ def main():
     info = gi.info
 
     oi, alg = None, None
+    if rank == 0 and w.get("device_built") and not (args.no_parity and args.no_cpu_baseline and args.modes == "none"):
+        safe("index files", lambda: ensure_files(gi, wl))
     if rank == 0 and not args.no_parity:
-        if w.get("device_built"):
-            safe("index files", lambda: ensure_files(gi, wl))
         oi = safe("oracle load", lambda: load_oracle(wl, True))
         if isinstance(oi, dict):
             oi = None

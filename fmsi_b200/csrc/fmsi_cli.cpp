@@ -23,6 +23,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <future>
 #include <map>
 #include <memory>
@@ -140,6 +141,9 @@ struct Op {  // one stretch of a record's output
 struct Record {
     size_t name_begin, name_len;  // into Batch::names
     size_t op_begin, op_end;
+    // a record too long for one batch is laid out in pieces (layout_record with a limit): a piece that continues an
+    // earlier one prints no name, one that is continued prints no newline; comma0 = results were printed before it
+    bool cont_begin = false, cont_end = false, comma0 = false;
 };
 
 struct Batch {
@@ -167,7 +171,12 @@ struct Batch {
 
 // ms_query's record loop (main.cpp:328-373) turned into a layout: which k-mers exist, where the
 // reference cuts its chunks, and how many filler results each invalid character produces.
-void layout_record(Batch &b, const std::string &name, const std::string &s, int k, bool streaming) {
+// With `limit` > 0 a long record is cut into pieces: once the batch holds `limit` results, at the next boundary
+// between two of the reference's chunks (so that the predictor sees the same chunks) the batch is handed to
+// `emit` — which must leave it cleared — and the record continues in a fresh one. The reference holds a record in
+// memory and walks it chunk by chunk (main.cpp:337-354); the pieces keep the result buffers bounded the same way.
+void layout_record(Batch &b, const std::string &name, const std::string &s, int k, bool streaming, uint64_t limit = 0,
+                   const std::function<void(Batch &)> &emit = nullptr) {
     Record rec;
     rec.name_begin = b.names.size();
     rec.name_len = std::strlen(name.c_str());  // C-string semantics of `cout << seq->name.s`
@@ -178,29 +187,55 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
     max_chunk = k + std::max((int64_t)10, std::min(max_chunk, 2 * (int64_t)std::sqrt((double)sequence_length)));
     const char *sequence = s.data();
     const uint32_t gpu_max = streaming ? (uint32_t)(FMSI_GPU_MAX_STREAM_KMERS + k - 1) : 0xFFFFFF00u;
+    bool printed = false;  // the record has produced results (comma state of `lookup` output)
+    // k-mers [p0, p0 + m) of the valid run at `run`: text, GPU chunks (overlapping by k-1), one op
+    auto add_segment = [&](const char *run, uint64_t p0, uint64_t m) {
+        if (!m) return;
+        const uint64_t base0 = b.bases.size();
+        b.bases.append(run + p0, (size_t)(m + (uint64_t)k - 1));
+        for (uint64_t p = 0; p < m;) {
+            const uint64_t left = m + (uint64_t)k - 1 - p;
+            const uint32_t len = (uint32_t)std::min<uint64_t>(left, gpu_max);
+            b.chunk_off.push_back(base0 + p);
+            b.chunk_len.push_back(len);
+            b.res_off.push_back(b.n_results + p);
+            p += len - k + 1;
+        }
+        b.ops.push_back({m, true});
+        b.n_results += m;
+        printed = true;
+    };
+    auto cut_piece = [&]() {  // close this piece of the record, hand the batch over, open the next piece
+        rec.op_end = b.ops.size();
+        rec.cont_end = true;
+        b.records.push_back(rec);
+        emit(b);
+        rec = Record();
+        rec.name_begin = b.names.size();
+        rec.name_len = 0;
+        rec.op_begin = b.ops.size();
+        rec.cont_begin = true;
+        rec.comma0 = printed;
+    };
     while (sequence_length > 0) {
         int64_t current_length = 0;
         while (current_length < sequence_length && is_acgt((unsigned char)sequence[current_length])) ++current_length;
         if (current_length >= k) {
             const uint64_t run_kmers = (uint64_t)(current_length - k + 1);
-            const uint64_t base0 = b.bases.size();
-            b.bases.append(sequence, (size_t)current_length);
-            for (uint64_t p = 0; p < run_kmers;) {  // GPU chunks, overlapping by k-1
-                const uint64_t left = (uint64_t)current_length - p;
-                const uint32_t len = (uint32_t)std::min<uint64_t>(left, gpu_max);
-                b.chunk_off.push_back(base0 + p);
-                b.chunk_len.push_back(len);
-                b.res_off.push_back(b.n_results + p);
-                p += len - k + 1;
-            }
+            uint64_t seg0 = 0, done = 0;   // k-mers [seg0, done) of the run wait for their segment
             int64_t cur = current_length;  // reference chunks (main.cpp:340-354)
             while (cur >= k) {
                 const int64_t chunk_length = std::min(cur, max_chunk);
                 b.ref_chunks.push_back((uint32_t)(chunk_length - k + 1));
                 cur -= chunk_length - k + 1;
+                done += (uint64_t)(chunk_length - k + 1);
+                if (limit && emit && cur >= k && b.n_results + (done - seg0) >= limit) {
+                    add_segment(sequence, seg0, done - seg0);
+                    seg0 = done;
+                    cut_piece();
+                }
             }
-            b.ops.push_back({run_kmers, true});
-            b.n_results += run_kmers;
+            add_segment(sequence, seg0, run_kmers - seg0);
             sequence += run_kmers;
             sequence_length -= (int64_t)run_kmers;
             current_length -= (int64_t)run_kmers;
@@ -208,7 +243,11 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
         // current_length < k characters of the run remain, then the invalid character (main.cpp:355-370)
         sequence_length -= current_length + 1;
         sequence += current_length + 1;
-        if (sequence_length >= 0) b.ops.push_back({(uint64_t)std::min<int64_t>(k, current_length + 1), false});
+        if (sequence_length >= 0) {
+            b.ops.push_back({(uint64_t)std::min<int64_t>(k, current_length + 1), false});
+            printed = true;
+            if (limit && emit && sequence_length > 0 && b.ops.size() - rec.op_begin >= limit) cut_piece();  // a record of invalid characters
+        }
     }
     rec.op_end = b.ops.size();
     b.records.push_back(std::move(rec));
@@ -226,6 +265,7 @@ void layout_record(Batch &b, const std::string &name, const std::string &s, int 
 // With $FMSI_GPU_DEVICES the replicas live on several GPUs and blocks go to whichever is free.
 struct Job {
     uint64_t seq = 0;
+    size_t units = 0;         // what the job counts towards the pipeline's in-flight bound
     std::vector<char> block;  // raw input: whole records
     Batch b;
     std::vector<uint8_t> raw8, fin8;
@@ -251,15 +291,10 @@ class Pipeline {
         threads_.emplace_back([this] { sequencer(); });
         threads_.emplace_back([this] { writer(); });
     }
-    // reader side: blocks while too many batches are in flight
-    void submit(Job *job) {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return inflight_ < max_inflight_ || failed_; });
-        job->seq = submitted_++;
-        ++inflight_;
-        tasks_.push_back({job, kParse});
-        cv_.notify_all();
-    }
+    // reader side: blocks while too many batches, or too much work (input bytes ~ results), are in flight
+    void submit(Job *job) { enqueue(job, kParse, job->block.size()); }
+    // a batch laid out by the reader itself (a piece of a record too long for one batch)
+    void submit_parsed(Job *job) { enqueue(job, kQuery, (size_t)job->b.n_results + job->b.bases.size()); }
     bool finish() {
         {
             std::unique_lock<std::mutex> lk(mu_);
@@ -276,6 +311,21 @@ class Pipeline {
         Job *job;
         Stage stage;
     };
+    void enqueue(Job *job, Stage stage, size_t units) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return failed_ || inflight_ == 0 || (inflight_ < max_inflight_ && inflight_units_ + units <= kMaxInflightUnits); });
+        job->seq = submitted_++;
+        job->units = units;
+        ++inflight_;
+        inflight_units_ += units;
+        if (stage == kQuery) {  // queries leave in block order
+            auto at = std::find_if(tasks_.begin(), tasks_.end(), [&](const Task &x) { return x.stage == kQuery && x.job->seq > job->seq; });
+            tasks_.insert(at, {job, kQuery});
+        } else {
+            tasks_.push_back({job, stage});
+        }
+        cv_.notify_all();
+    }
     void fail(const std::string &msg) {
         std::unique_lock<std::mutex> lk(mu_);
         if (!failed_) std::cerr << "ERROR: GPU query failed: " << msg << std::endl;
@@ -370,10 +420,12 @@ class Pipeline {
                 formatted_.erase(next);
             }
             if (!job->out.empty()) std::fwrite(job->out.data(), 1, job->out.size(), stdout);
+            const size_t units = job->units;
             delete job;
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 --inflight_;
+                inflight_units_ -= units;
                 ++written_;
                 cv_.notify_all();
             }
@@ -410,6 +462,7 @@ class Pipeline {
                 fail(fmsi_gpu_last_error());
                 return false;
             }
+            if (!fix_mixed_case_palindromes(j, idx)) return false;
         } else if (n) {
             const int rc = fmsi_gpu_query_chunks(idx, gmode, gout, gstr, cfg_.streaming ? 1 : 0, b.bases.data(), b.bases.size(), b.chunk_off.data(),
                                                  b.chunk_len.data(), b.res_off.data(), b.chunk_off.size(), n, cfg_.k, raw, FMSI_GPU_MEM_HOST, nullptr);
@@ -419,6 +472,69 @@ class Pipeline {
             }
         }
         std::string().swap(b.bases);  // no longer needed: free early
+        return true;
+    }
+
+    // The reference decides "self-complementary: count once" by comparing the ASCII k-mer with its reverse complement
+    // (AreStringsEqual, fms_index.h:319; ReverseComplementString keeps the case, kmers.h:21-59), so a palindromic k-mer
+    // (even k) whose case pattern is not symmetric — `acGT` in a soft-masked query — is counted TWICE there. The
+    // kernels compare bases, not case; those k-mers are found here and given the reference's value f(2 ones, 2 total):
+    // xor -> 0, and / or unchanged, r-s -> a second query of just those k-mers with ceil(r/2) - floor(s/2).
+    bool fix_mixed_case_palindromes(Job &j, fmsi_gpu_index *idx) {
+        const int k = cfg_.k;
+        if ((k & 1) || (cfg_.f.kind != FMSI_GPU_F_XOR && cfg_.f.kind != FMSI_GPU_F_RANGE)) return true;
+        Batch &b = j.b;
+        auto comp = [](unsigned char c) -> unsigned char {  // complement of an ACGTacgt letter, upper case
+            switch (c & 0xDF) {
+            case 'A': return 'T';
+            case 'C': return 'G';
+            case 'G': return 'C';
+            default: return 'A';
+            }
+        };
+        std::vector<uint64_t> off, slot;
+        const char *t = b.bases.data();
+        for (size_t c = 0; c < b.chunk_off.size(); ++c) {
+            const uint64_t nk = b.chunk_len[c] - (uint32_t)k + 1;
+            for (uint64_t q = 0; q < nk; ++q) {
+                const unsigned char *s = (const unsigned char *)t + b.chunk_off[c] + q;
+                bool pal = true, mixed = false;
+                for (int i = 0; i < k / 2; ++i) {
+                    if ((s[i] & 0xDF) != comp(s[k - 1 - i])) {
+                        pal = false;
+                        break;
+                    }
+                    mixed |= ((s[i] ^ s[k - 1 - i]) & 0x20) != 0;
+                }
+                if (pal && mixed) {
+                    off.push_back(b.chunk_off[c] + q);
+                    slot.push_back(b.res_off[c] + q);
+                }
+            }
+        }
+        if (off.empty()) return true;
+        if (cfg_.f.kind == FMSI_GPU_F_XOR) {
+            for (uint64_t sl : slot) j.raw8[sl] = 0;
+            return true;
+        }
+        fmsi_gpu_function f2 = cfg_.f;
+        f2.r = (cfg_.f.r + 1) / 2;
+        f2.s = cfg_.f.s / 2;
+        if (f2.r > f2.s) {
+            for (uint64_t sl : slot) j.raw8[sl] = 0;
+            return true;
+        }
+        std::vector<uint32_t> len(off.size(), (uint32_t)k);
+        std::vector<uint64_t> ro(off.size());
+        for (size_t q = 0; q < ro.size(); ++q) ro[q] = q;
+        std::vector<uint8_t> res(off.size());
+        const int rc = fmsi_gpu_query_chunks_general(idx, &f2, b.bases.data(), b.bases.size(), off.data(), len.data(), ro.data(), off.size(), off.size(),
+                                                     k, res.data(), FMSI_GPU_MEM_HOST, nullptr);
+        if (rc != FMSI_GPU_OK) {
+            fail(fmsi_gpu_last_error());
+            return false;
+        }
+        for (size_t q = 0; q < slot.size(); ++q) j.raw8[slot[q]] = res[q];
         return true;
     }
 
@@ -511,9 +627,11 @@ class Pipeline {
         uint64_t q = 0;
         char num[24];
         for (const Record &rec : b.records) {
-            out.append(b.names.data() + rec.name_begin, rec.name_len);
-            out.push_back('\t');
-            bool comma = false;
+            if (!rec.cont_begin) {
+                out.append(b.names.data() + rec.name_begin, rec.name_len);
+                out.push_back('\t');
+            }
+            bool comma = rec.comma0;
             for (size_t o = rec.op_begin; o < rec.op_end; ++o) {
                 const Op &op = b.ops[o];
                 if (!orders) {
@@ -539,7 +657,7 @@ class Pipeline {
                     if (op.kmers) q += op.count;
                 }
             }
-            out.push_back('\n');
+            if (!rec.cont_end) out.push_back('\n');
         }
     }
     static int fast_itoa(int64_t v, char *buf) {
@@ -569,6 +687,10 @@ class Pipeline {
     std::map<uint64_t, Job *> queried_, formatted_;
     std::vector<std::thread> threads_;
     size_t max_inflight_ = 4, inflight_ = 0;
+    // bound on the work in flight (bytes of unparsed input, or results + text of laid-out batches): with `lookup -S`
+    // a result costs ~35 bytes of host buffers, so this keeps the pipeline below ~20 GB whatever the record sizes
+    static constexpr size_t kMaxInflightUnits = (size_t)512 << 20;
+    size_t inflight_units_ = 0;
     uint64_t submitted_ = 0, written_ = 0;
     bool closed_ = false, failed_ = false;
 };
@@ -822,10 +944,35 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     if (query_fn == "-") input->start();
     {
         Pipeline pipe(cfg, members, workers);
+        // A block beyond `giant` bytes holds a record longer than a batch should be (a chromosome, an assembly): the
+        // reader lays it out itself, in pieces of ~`piece` results that enter the pipeline as they are cut, so that
+        // result buffers stay bounded however long the record is (the text itself is held once, as in the reference).
+        size_t giant = (size_t)64 << 20;
+        uint64_t piece = (uint64_t)32 << 20;
+        if (const char *e = std::getenv("FMSI_GPU_GIANT_BLOCK")) giant = (size_t)atoll(e);
+        if (const char *e = std::getenv("FMSI_GPU_PIECE_RESULTS")) piece = (uint64_t)atoll(e);
         Job *job = new Job();
         while (input->pop(job->block)) {
-            pipe.submit(job);
-            job = new Job();
+            if (job->block.size() <= giant) {
+                pipe.submit(job);
+                job = new Job();
+                continue;
+            }
+            fmsi::MemRecordReader reader(job->block.data(), job->block.size());
+            std::string name, seq;
+            Batch cur;
+            auto emit = [&](Batch &b) {
+                Job *pj = new Job();
+                pj->b = std::move(b);
+                b = Batch();
+                pipe.submit_parsed(pj);
+            };
+            while (reader.next(name, seq) >= 0) {
+                layout_record(cur, name, seq, cfg.k, cfg.streaming, piece, emit);
+                if (cur.n_results >= piece) emit(cur);
+            }
+            if (!cur.records.empty()) emit(cur);
+            std::vector<char>().swap(job->block);
         }
         delete job;
         if (timing) std::cerr << "[fmsi timing] reader done: " << since(t_query) << " s" << std::endl;

@@ -90,6 +90,58 @@ def test_cli_small_batches_stdin_gzip_and_k_flag(tmp_path):
     assert r.stdout == want
 
 
+@pytest.mark.parametrize("case", ["syn_k31_max", "syn_k9_min", "quirks_k3", "quirks_k3_nonmax", "integration_a"])
+def test_cli_long_records_are_cut_into_pieces(case):
+    """Blocks beyond $FMSI_GPU_GIANT_BLOCK bytes (64 MB by default: a chromosome-sized record) are laid out by the reader
+    in pieces of $FMSI_GPU_PIECE_RESULTS results that run through the pipeline one after the other. With both limits
+    forced down to almost nothing every record of the goldens is cut, mid-run, and the output — predictor replay
+    across the pieces included — must still be the reference's, byte for byte."""
+    d = os.path.join(GOLDEN, case)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    for piece in ("1", "37"):
+        env = {"FMSI_GPU_GIANT_BLOCK": "1", "FMSI_GPU_PIECE_RESULTS": piece}
+        runs = run_many([ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")] for cmd in meta["cmds"]], env=env)
+        for cmd, r in zip(meta["cmds"], runs):
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}/piece={piece}"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fmsi")), reason="oracle/_ref/fmsi not shipped")
+@pytest.mark.parametrize("k", [4, 6])
+def test_cli_general_mode_mixed_case_palindromes(k, tmp_path):
+    """`query -f xor|INT-INT` on soft-masked queries: the reference compares the ASCII k-mer with its reverse complement
+    (AreStringsEqual, fms_index.h:319), so a palindromic k-mer with an asymmetric case pattern (`acGT`) counts twice
+    there. Live differential against the reference binary, even k, every demasking function."""
+    import numpy as np
+    ref = os.path.join(ROOT, "oracle", "_ref", "fmsi")
+    rng = np.random.default_rng(k)
+    half = ["ACGT"[i] for i in rng.integers(0, 4, size=k // 2)]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    pal = "".join(half) + "".join(comp[c] for c in reversed(half))
+    body = "".join("ACGT"[i] for i in rng.integers(0, 4, size=400))
+    ms_text = (pal + body[:50] + pal + body[50:200] + pal.lower() + body[200:]).upper()
+    mask = rng.random(len(ms_text)) < 0.6
+    ms = "".join(c if m else c.lower() for c, m in zip(ms_text, mask))
+    ms = ms[:len(ms) - (k - 1)] + ms[len(ms) - (k - 1):].lower()
+    fa = tmp_path / "ms.fa"
+    fa.write_text(">ms\n" + ms + "\n")
+    subprocess.run([ref, "index", "-k", str(k), str(fa)], check=True, capture_output=True)
+    variants = [pal, pal.lower(), pal[:k // 2].lower() + pal[k // 2:], pal[:1].lower() + pal[1:], pal[:1].lower() + pal[1:-1] + pal[-1:].lower(),
+                pal[:-1] + pal[-1:].lower()]
+    recs = []
+    for i, v in enumerate(variants):
+        recs.append(f">p{i}\n{v}\n")
+        recs.append(f">ctx{i}\n{body[:7].lower()}{v}{body[7:13]}{v.swapcase()}N{v}\n")
+    recs.append(">rand\n" + "".join(c.lower() if r < 0.5 else c for c, r in zip(body, rng.random(len(body)))) + "\n")
+    q = tmp_path / "q.fa"
+    q.write_text("".join(recs))
+    for f in ("xor", "and", "1-1", "2-2", "1-2", "2-3", "3-4", "0-0", "1-1000"):
+        want = subprocess.run([ref, "query", "-f", f, "-q", str(q), str(fa)], capture_output=True, check=True).stdout
+        r = run_cli(["query", "-f", f, "-q", str(q), str(fa)])
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == want, (k, f)
+
+
 def test_cli_multi_gpu_scheduler_is_byte_identical():
     """$FMSI_GPU_DEVICES shards every batch over index replicas (repeated ordinals share one GPU)."""
     for case, flags, exp in (("syn_k31_max", ["query", "-O", "-S"], "exp_query_OS.txt"), ("syn_k9_min", ["lookup"], "exp_lookup.txt"),

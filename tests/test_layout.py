@@ -18,9 +18,11 @@ TOOL = os.path.join(ROOT, "fmsi_b200", "bin", "layout_dump")
 FUZZ = os.path.join(GOLDEN, "layout_fuzz")
 
 
-def layout_counts(k, streaming, qfile):
-    r = subprocess.run([TOOL, str(k), "1" if streaming else "0", qfile], capture_output=True)
+def layout_counts(k, streaming, qfile, piece_limit=None):
+    r = subprocess.run([TOOL, str(k), "1" if streaming else "0", qfile] + ([str(piece_limit)] if piece_limit else []), capture_output=True)
     assert r.returncode == 0, (r.returncode, r.stderr.decode())
+    if piece_limit:
+        layout_counts.pieces = int(r.stderr.decode().split()[-1])
     rows = []
     for line in r.stdout.decode().split("\n")[:-1]:
         name, total, kmers = line.split("\t")
@@ -36,6 +38,19 @@ def test_result_counts_match_reference_output_lengths(k, streaming):
     assert len(got) == len(want) == 300
     assert [(n, t) for n, t, _ in got] == [(n, int(t)) for n, t in want]
     assert any(t > m for _, t, m in got) and any(m > 400 for _, _, m in got)  # fillers and multi-chunk records occur
+
+
+@pytest.mark.parametrize("k", [3, 31])
+@pytest.mark.parametrize("limit", [1, 50, 1000])
+def test_records_cut_into_pieces_print_the_same(k, limit):
+    """A record too long for one batch is laid out in pieces (fmsi_cli.cpp: layout_record with a limit; the CLI does
+    this for blocks beyond 64 MB). Cut at the reference's chunk boundaries into pieces of >= `limit` results, the
+    pieces of every record must add up to the reference's output lengths, chain up, and cover their k-mers exactly."""
+    want = [tuple(l.split("\t")) for l in open(os.path.join(FUZZ, f"exp_k{k}.tsv")).read().split("\n")[:-1]]
+    whole = layout_counts(k, True, os.path.join(FUZZ, "q.fa"))
+    got = layout_counts(k, True, os.path.join(FUZZ, "q.fa"), piece_limit=limit)
+    assert got == whole and [(n, t) for n, t, _ in got] == [(n, int(t)) for n, t in want]
+    assert layout_counts.pieces > (300 if limit <= 50 else 3)  # records were in fact cut
 
 
 def test_known_quirks(tmp_path):
