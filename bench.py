@@ -803,7 +803,7 @@ def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], 
                 with open(fn, "wb") as f:
                     f.write(blob)
                 shards.append(fn)
-        env = dict(os.environ, FMSI_GPU_DEVICE=str(device))
+        env = dict(os.environ, FMSI_GPU_DEVICE=str(device), FMSI_GPU_TIMING="1")
         ours_out = os.path.join(tmp, "ours.txt")
         t0 = time.perf_counter()
         with open(ours_out, "wb") as fo:
@@ -831,7 +831,16 @@ def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], 
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     n = per * P
-    return dict(command="fmsi " + " ".join(ref_args), records=n, fasta_bytes=n * (wl["k"] + 4), ours_wall_s=round(ours_s, 3), ours_kmers_s=n / ours_s,
+    stages = {}
+    for line in r.stderr.decode(errors="replace").splitlines():  # the CLI's own stage clock ($FMSI_GPU_TIMING)
+        if line.startswith("[fmsi timing] index load + replicas:"):
+            stages["index_load_s"] = float(line.split(":")[1].split()[0])
+        elif line.startswith("[fmsi timing] total:"):
+            stages["total_s"] = float(line.split(":")[1].split()[0])
+    if len(stages) == 2:
+        stages["kmers_s_after_load"] = n / max(stages["total_s"] - stages["index_load_s"], 1e-9)
+        stages["process_start_and_exit_s"] = round(ours_s - stages["total_s"], 3)
+    return dict(command="fmsi " + " ".join(ref_args), records=n, fasta_bytes=n * (wl["k"] + 4), ours_wall_s=round(ours_s, 3), ours_kmers_s=n / ours_s, ours_stages=stages,
                 reference_wall_s=round(ref_s, 3), reference_kmers_s=n / ref_s, reference_processes=P, speedup=round(ref_s / ours_s, 2),
                 outputs_byte_identical=bool(identical),
                 note="whole-process wall time, index load and CUDA context creation included on our side, one index load per process "
@@ -1024,7 +1033,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--modes", default=os.environ.get("FMSI_BENCH_MODES", "auto"),
                     help="auto = all BASELINE configs at N = 1, the streaming-read configs at N > 1; none; or a comma list of workloads")
-    ap.add_argument("--cli-records", type=int, default=int(os.environ.get("FMSI_BENCH_CLI_RECORDS", 10_000_000)))
+    ap.add_argument("--cli-records", type=int, default=int(os.environ.get("FMSI_BENCH_CLI_RECORDS", 30_000_000)),
+                    help="records of the like-for-like CLI runs (fixed costs - CUDA context 0.6-1.4 s, index load - weigh less the longer the run)")
     ap.add_argument("--prepare-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -79,6 +79,8 @@ struct fmsi_gpu_index {
     bool wide = false;
     DictView dict{};
     FoldView fold{};
+    int fold_ids_policy = 0;        // fmsi_gpu_options.fold_ids: 0 = on the first lookup, 1 = with the tier, -1 = never
+    bool fold_ids_failed = false;   // the lazy build ran out of memory once: lookups stay on the other tiers
     Slot slots[kSlots];
     cudaStream_t aux_stream = nullptr;       // second query stream of pipelined host-mode chunk calls
     std::vector<cudaEvent_t> piece_events;   // "text piece uploaded and packed" events of those calls
@@ -123,10 +125,13 @@ u32 pick_chunk(size_t n, int grid, int block) {
     if (forced >= 32) return (u32)(forced / 32 * 32);
     // ~32 grabs per warp: at the end of a launch warps run dry within one grab's duration of each other, and that
     // ramp-down is idle memory system (256 / 512 / 1408 k-mers per grab: 42.6 / 42.5 / 42.1 G k-mers/s at human scale)
+    // ... but never fewer than 256 per grab: a grab is two dependent round trips (cursor, then the k-mers) during which
+    // the warp has nothing in flight, and with 32-k-mer grabs a small launch (the 4-8 M k-mer batches of the host paths)
+    // ran at a third of the rate of a large one (ncu: 355 us per 2^22 k-mers vs 1680 us per 2^26).
     const size_t warps = (size_t)grid * (block / 32);
     size_t c = n / (warps * 32 + 1);
     c = (c / 32) * 32;
-    if (c < 32) c = 32;
+    if (c < 256) c = 256;
     if (c > 2048) c = 2048;
     return (u32)c;
 }
@@ -261,7 +266,7 @@ template <int MODE, int OUT, int STRANDS>
 int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
                    LaunchScratch &ls, cudaStream_t st) {
     if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, ls, st);
-    if (idx->fold.enabled && d.k == idx->fold.k) return launch_fold<MODE, OUT, STRANDS>(idx, kmers, n, out, ls, st);
+    if (idx->fold.enabled && d.k == idx->fold.k && (OUT != K_OUT_ORDERS || idx->fold.ids)) return launch_fold<MODE, OUT, STRANDS>(idx, kmers, n, out, ls, st);
     if (idx->dict.enabled && d.k == idx->dict.k && d.t && n < (1ull << 32)) return launch_dict<MODE, OUT, STRANDS>(idx, d, kmers, n, out, ls, st);
     return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, ls, st);
 }
@@ -405,22 +410,23 @@ int build_fold(fmsi_gpu_index *idx, u32 t, u32 tt) {
     const HostIndex &h = idx->meta;
     FoldArrays fa;
     uint64_t launches = 0;
+    const bool with_ids = idx->fold_ids_policy == 1;
     try {
-        build_fold_on_device(idx->dev, h.counts, (u32)h.k, t, fa, &launches);
+        build_fold_on_device(idx->dev, h.counts, (u32)h.k, t, true, with_ids, fa, &launches);
     } catch (const std::exception &e) {
         const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || std::string(e.what()).find("out of memory") != std::string::npos;
         return fail(oom ? FMSI_GPU_ERR_NOMEM : FMSI_GPU_ERR_CUDA, std::string("strand-folded dictionary: ") + e.what());
     }
     g_launches.fetch_add(launches);
     idx->d_fbuckets = fa.buckets;
-    idx->d_frows = fa.rows;
+    idx->d_frows = fa.orows;
     idx->d_fids = fa.ids;
     idx->b_fbuckets = (1ull << (2 * t)) * sizeof(FoldBucket);
-    idx->b_frows = (fa.n_rows + 8) * sizeof(u64);
-    idx->b_fids = (fa.n_rows + 1) * sizeof(uint2);
+    idx->b_frows = (fa.n_orows + 8) * sizeof(u64);
+    idx->b_fids = fa.ids ? (fa.n_rows + 1) * sizeof(uint2) : 0;
     idx->hbm_bytes += idx->b_fbuckets + idx->b_frows + idx->b_fids;
     idx->fold.buckets = fa.buckets;
-    idx->fold.rows = fa.rows;
+    idx->fold.orows = fa.orows;
     idx->fold.ids = fa.ids;
     idx->fold.n_rows = fa.n_rows;
     idx->fold.t = t;
@@ -428,6 +434,44 @@ int build_fold(fmsi_gpu_index *idx, u32 t, u32 tt) {
     idx->fold.k = (u32)h.k;
     idx->fold.enabled = 1;
     return build_table<false>(idx, tt);
+}
+
+// `lookup` through the strand-folded dictionary needs ids[] (8 bytes per row), which `query` never reads: unless
+// asked for with the tier (fold_ids = 1) it is built here, on the first lookup — the same passes over the BWT as
+// the tier's own build, keeping only the ids. Out of memory is not an error: lookups then stay on the other tiers.
+void ensure_fold_ids(fmsi_gpu_index *idx) {
+    if (!idx->fold.enabled || idx->fold.ids || idx->fold_ids_policy < 0 || idx->fold_ids_failed) return;
+    const HostIndex &h = idx->meta;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || fold_build_peak_bytes(h.n, idx->fold.t, true) - (32ull << (2 * idx->fold.t)) > free_b - free_b / 16) {
+        idx->fold_ids_failed = true;
+        fprintf(stderr, "[fmsi] note: not enough free device memory for the dictionary's lookup ids; lookups use the backward-search kernels\n");
+        return;
+    }
+    FoldArrays fa;
+    uint64_t launches = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    try {
+        build_fold_on_device(idx->dev, h.counts, (u32)h.k, idx->fold.t, false, true, fa, &launches);
+    } catch (const std::exception &e) {
+        cudaGetLastError();
+        idx->fold_ids_failed = true;
+        fprintf(stderr, "[fmsi] note: lookup ids of the dictionary not built (%s); lookups use the backward-search kernels\n", e.what());
+        return;
+    }
+    g_launches.fetch_add(launches);
+    if (fa.n_rows != idx->fold.n_rows) {  // cannot happen: the row numbering is a function of the index alone
+        cudaFree(fa.ids);
+        idx->fold_ids_failed = true;
+        return;
+    }
+    idx->d_fids = fa.ids;
+    idx->b_fids = (fa.n_rows + 1) * sizeof(uint2);
+    idx->hbm_bytes += idx->b_fids;
+    idx->fold.ids = fa.ids;
+    if (std::getenv("FMSI_GPU_TIMING"))
+        fprintf(stderr, "[fmsi timing] lookup ids of the strand-folded dictionary built in %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 }
 
 int select_device(fmsi_gpu_index *idx) {
@@ -523,6 +567,8 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     if (const char *e = std::getenv("FMSI_GPU_PREFIX_T")) t = std::atoi(e);
     int want_dict = opts ? opts->dict : -1;
     if (const char *e = std::getenv("FMSI_GPU_DICT")) want_dict = std::atoi(e);
+    idx->fold_ids_policy = opts ? opts->fold_ids : 0;
+    if (const char *e = std::getenv("FMSI_GPU_FOLD_IDS")) idx->fold_ids_policy = std::atoi(e);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
 
@@ -556,14 +602,15 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     bool done = false;
     if (narrow && (want_dict < 0 || want_dict == 2)) {
         int td = auto_depth();
+        const bool with_ids = idx->fold_ids_policy == 1;
         auto fits = [&](int x) {
-            return fold_build_peak_bytes(h.n, (u32)x) <= free_b - free_b / 10 && fold_resident_bytes(h.n, (u32)x) <= free_b / 10 * 6;
+            return fold_build_peak_bytes(h.n, (u32)x, with_ids) <= free_b - free_b / 10 && fold_resident_bytes(h.n, (u32)x, with_ids) <= free_b / 10 * 6;
         };
         while (td > 1 && t < 0 && !fits(td)) --td;
         if (td >= 1 && h.k - td <= 30 && fits(td)) {
             rc = build_fold(idx, (u32)td, (u32)table_depth(13));
             if (rc == FMSI_GPU_OK) done = true;
-            else if (rc != FMSI_GPU_ERR_NOMEM) return rc;
+            else if (rc != FMSI_GPU_ERR_NOMEM || want_dict == 2) return rc;
             else {  // release whatever the failed build left and try the next tier
                 for (void **p : {&idx->d_fbuckets, &idx->d_frows, &idx->d_fids}) {
                     if (*p) cudaFree(*p);
@@ -595,6 +642,11 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
         rc = idx->wide ? build_table<true>(idx, (u32)t) : build_table<false>(idx, (u32)t);
     }
     if (rc) return rc;
+    if (want_dict < 0 && narrow && !idx->fold.enabled)
+        // auto asked for the fastest tier that fits: say so when it is not the one-probe dictionary (info.dict tells which)
+        fprintf(stderr, "[fmsi] note: the strand-folded dictionary does not fit in the free device memory (%.1f GB free, %.1f GB needed while building); "
+                        "using %s — single k-mer queries run several times slower\n",
+                free_b / 1e9, fold_build_peak_bytes(h.n, (u32)auto_depth(), false) / 1e9, idx->dict.enabled ? "the SA-ordered dictionary" : "backward search");
     if ((rc = setup_multistep(idx, opts))) return rc;
     return alloc_slots(idx);
 }
@@ -1030,6 +1082,7 @@ int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info
     info->wide = idx->wide;
     info->device = idx->device;
     info->multistep = (int32_t)idx->dev.multi_m;
+    info->fold_ids = idx->fold.enabled && idx->fold.ids ? 1 : 0;
     return FMSI_GPU_OK;
 }
 
@@ -1153,6 +1206,7 @@ int query_kmers_impl(fmsi_gpu_index *idx, int mode, int output, int strands, con
     if (n == 0) return FMSI_GPU_OK;
     if (!kmers || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
+    if (output == FMSI_GPU_OUT_ORDERS && (u32)k == idx->fold.k) ensure_fold_ids(idx);
     const DevIndex d = dev_for_k(idx, k);
     const size_t rbytes = result_bytes(output, strands);
     int rc;
@@ -1218,6 +1272,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
     if (!text || !chunk_off || !chunk_len || !res_off || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
+    if (output == FMSI_GPU_OUT_ORDERS && (u32)k == idx->fold.k) ensure_fold_ids(idx);
     const DevIndex d = dev_for_k(idx, k);
     const size_t rbytes = result_bytes(output, strands);
     const bool on_host = mem == FMSI_GPU_MEM_HOST;
@@ -1240,7 +1295,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // k-mer instead of an aux probe + an LF-step per k-mer and strand (profiles/r01d_modes_*.json).
     // k > 32: queries are start positions into the packed text (longk_kernels.cuh), with or without -S.
     const bool longk = k > 32;
-    const bool via_kmers = longk || !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k) ||
+    const bool via_kmers = longk || !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k && (output != FMSI_GPU_OUT_ORDERS || idx->fold.ids)) ||
                                                          (idx->dict.enabled && (u32)k == idx->dict.k && d.t && n_results < (1ull << 32))));
     const size_t n_words = n_words_in + 4;
     size_t aux_need = n_words * 8;
@@ -1373,6 +1428,10 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // with pageable host buffers both copies block the calling thread, and this order keeps the GPU busy meanwhile.
     // Chunks are validated as they are scheduled; chunks out of text order end the pipeline and the call starts
     // over as a single batch (same results).
+    static const bool trace = std::getenv("FMSI_GPU_TRACE") != nullptr;  // host-side timeline of the pipelined call
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto tr_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count(); };
+    double tr_validate = 0;
     cudaStream_t qs[2] = {idx->slots[1].stream, idx->aux_stream};
     LaunchScratch *qls[2] = {&idx->slots[1].ls, &s.ls};
     size_t c_done = 0, r_done = 0, span = 0;
@@ -1385,6 +1444,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         const size_t w0 = p0 / 32, w1 = last ? n_words : p1 / 32;
         if ((rc = stage_words(w0, w1, st))) return rc;
         size_t c1 = c_done;
+        const double tv0 = trace ? tr_us() : 0;
         for (; c1 < n_chunks; ++c1) {
             const uint64_t end = chunk_off[c1] + chunk_len[c1];
             if (c1 > 0 && (chunk_off[c1] < chunk_off[c1 - 1] || end < chunk_off[c1 - 1] + chunk_len[c1 - 1] || res_off[c1] < res_off[c1 - 1])) {
@@ -1395,6 +1455,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
             if (!last && end > 32 * w1) break;
             if (streaming && !longk && bad_stream_chunk(c1)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
         }
+        if (trace) tr_validate += tr_us() - tv0;
         if (!ordered || c1 == c_done) continue;
         if ((rc = upload_chunks(c_done, c1, st))) return rc;
         const size_t r1 = std::max(r_done, c1 < n_chunks ? (size_t)std::min<uint64_t>(res_off[c1], n_results) : n_results);
@@ -1416,11 +1477,15 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         ++span;
     }
     if (ordered && back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
+    const double tr_enq = trace ? tr_us() : 0;
     CU(cudaEventRecord(s.done, st));
     CU(cudaEventRecord(idx->slots[1].done, qs[0]));
     CU(cudaStreamSynchronize(st));
     CU(cudaStreamSynchronize(qs[0]));
     CU(cudaStreamSynchronize(qs[1]));
+    if (trace)
+        fprintf(stderr, "[fmsi trace] chunks call: %zu chunks, %zu results, %zu spans: all enqueued at %.0f us (chunk validation %.0f us), drained at %.0f us\n",
+                n_chunks, n_results, span, tr_enq, tr_validate, tr_us());
     if (!ordered) return single_batch();
     if (bits) {  // every span's byte results are on the device: pack and fetch them
         if ((rc = finish_bits(st))) return rc;
@@ -1511,6 +1576,7 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->dev = src->dev;
     r->dict = src->dict;
     r->fold = src->fold;
+    r->fold_ids_policy = src->fold_ids_policy;
     r->b_fbuckets = src->b_fbuckets;
     r->b_frows = src->b_frows;
     r->b_fids = src->b_fids;
@@ -1543,7 +1609,7 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->dev.sb_base = reinterpret_cast<const u64 *>(r->d_sb);
     r->dict.rows = reinterpret_cast<const u64 *>(r->d_rows);
     r->fold.buckets = r->d_fbuckets;
-    r->fold.rows = reinterpret_cast<const u64 *>(r->d_frows);
+    r->fold.orows = reinterpret_cast<const u64 *>(r->d_frows);
     r->fold.ids = reinterpret_cast<const uint2 *>(r->d_fids);
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(FMSI_GPU_ERR_CUDA, "cudaSetDevice"));
     if ((rc = alloc_slots(r.get()))) return bail(rc);

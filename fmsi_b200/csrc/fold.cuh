@@ -14,24 +14,33 @@
 //                a hash order, unlike the lexicographic minimum, keeps the first t bases uniform)
 //   key(q)     = a bijective mix of orient(q) on 2k bits (fold_key) — a hash table, so the load of a bucket does
 //                not depend on how the index's k-mers share prefixes
+//   row        = one distinct key: payload (the low 2B key bits, B = k - t) and state sf | sr << 2; the rows of a
+//                bucket are sorted by payload and numbered globally in key order (row g <-> ids[g])
 //   bucket[x], x = top 2t bits of key(q)  (32 B = one sector, 4^t of them):
-//       u32 start, end      rows [start, end) of this bucket in rows[] / ids[] (sorted by payload, distinct)
-//       u32 flags           4 bits per inline row: sf | sr << 2
-//       PAY32: u32 pay[5]       the low 2B bits (B = k - t <= 16) of the keys of the first 5 rows
+//       u32 gstart          global number of the bucket's first row
+//       u32 ovf             where its overflow rows start in orows[] (a multiple of 4; only if it has more rows than fit)
+//       u32 meta            bits 0-19 (PAY64: 0-7): 4 state bits per inline row; bits 20-22: inline rows; bit 23: overflow
+//       PAY32: u32 pay[5]       payloads of its first 5 rows (B <= 16)
 //       PAY64: u32 pad; u64 pay[2]   (16 < B <= 30) first 2 rows
-//   rows[g]  (8 B)  pay << 4 | sf | sr << 2   — read only when the bucket holds more rows than fit inline
-//   ids[g]   (8 B)  {id_f, id_r} = rank1(sa_start) of either orientation (lookup only)
+//   orows[]  (8 B entries, one 32-byte sector = 4 entries; only for buckets with more rows than fit inline — 7 % of
+//            them at 2.9 rows per bucket): [count of overflow rows][row][row]... padded with ~0 to a multiple of 4, each
+//            row = pay << 4 | sf | sr << 2. The first sector settles buckets with up to 3 overflow rows; larger ones
+//            are binary-searched one sector per step.
+//   ids[g]   (8 B)  {id_f, id_r} = rank1(sa_start) of either orientation — lookup only, and only built when asked for
+//            (fmsi_gpu_options.fold_ids; on the first lookup otherwise)
 //   sf / sr: state of the interval of orient(q) / of its reverse complement:
 //       0 empty, 1 non-empty without ON occurrence, 2 ON occurrence(s) but mask[sa_start] == 0, 3 mask[sa_start] == 1
 //
 // A query computes orient(q), reads one bucket, compares <= 5 payloads; a row match is unique, so there is
-// no scan over runs and no overflow list: a bucket with more rows than fit is binary-searched in rows[]
-// (one sector = 4 rows per step). or / -O / lookup and LAZY / BOTH strands are all decided from (sf, sr).
+// no scan over runs and no overflow list. or / -O / lookup and LAZY / BOTH strands are all decided from (sf, sr).
+// Resident at human scale (N = 3.1e9, t = 15): buckets 34.4 GB + orows 2.6 GB (+ ids 24.8 GB for lookup) — the
+// round-1 layout kept every row twice (rows[] 24.8 GB + ids[] 24.8 GB whatever the workload).
 //
 // Built on the device from the BWT alone (file-loaded and device-built indexes alike): psi = inverse
 // LF-mapping, the k-mer of every SA row by walking psi (SA order = sorted k-mers, so equal k-mers are
 // runs = their SA intervals), one entry per run (state from the mask ranks at the run's ends), entries
-// radix-sorted by orient(k-mer), the two orientations of a k-mer merged into one row.
+// radix-sorted by key, the two orientations of a k-mer merged into one row. The sort runs in P passes over
+// ranges of buckets, so that its buffers (48 bytes per entry in flight) stay a fraction of the index.
 #pragma once
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -44,11 +53,12 @@ namespace fmsi {
 constexpr u32 kFoldCap32 = 5, kFoldCap64 = 2;
 constexpr u64 kFoldMul = 0x9E3779B97F4A7C15ull;
 constexpr u32 kFoldNoId = 0xFFFFFFFFu;
+constexpr u32 kFoldMetaOvf = 1u << 23;
 
 struct FoldView {
     const void *buckets;  // [4^t] 32-byte sectors
-    const u64 *rows;      // [n_rows + 8]
-    const uint2 *ids;     // [n_rows]
+    const u64 *orows;     // overflow regions
+    const uint2 *ids;     // [n_rows] or null (not built)
     u64 n_rows;
     u32 t, B, k, enabled;
 };
@@ -60,7 +70,7 @@ __device__ __forceinline__ bool fold_swapped(u64 q, u64 rc) { return rc * kFoldM
 // longer follows the k-mer's first t bases. Indexes whose k-mers share long prefixes (pangenomes: thousands of
 // near-copies of one genome) would otherwise pile their rows into the few buckets of the genome's own t-mers.
 constexpr u64 kFoldMul2 = 0xD6E8FEB86659FD93ull;
-__device__ __forceinline__ u64 fold_key(u64 c, u32 k) {
+__host__ __device__ __forceinline__ u64 fold_key(u64 c, u32 k) {
     const u64 m = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
     c = (c * kFoldMul) & m;
     c ^= c >> k;
@@ -107,45 +117,84 @@ struct FoldKeyHead {  // entry m starts a group of equal keys
     __host__ __device__ __forceinline__ bool operator()(const u32 m) const { return m == 0 || keys[m] != keys[m - 1]; }
 };
 
+__host__ __device__ __forceinline__ u64 fold_revcomp(u64 x, u32 k) {  // host-callable twin of revcomp_packed
+    x = ~x;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    x = (x >> 32) | (x << 32);
+    return x >> (64 - 2 * k);
+}
+
+struct FoldRunInPass {  // run h (a valid one) has its key in buckets [x_lo, x_hi)
+    const u64 *kmers;
+    const u32 *validbits;
+    const u32 *heads;
+    u32 k, B;
+    u64 x_lo, x_hi;
+    __host__ __device__ __forceinline__ bool operator()(const u32 h) const {
+        const u32 i = heads[h];
+        if (!((validbits[i >> 5] >> (i & 31u)) & 1u)) return false;
+        const u64 q = kmers[i], rc = fold_revcomp(q, k);
+        const u64 x = fold_key((rc * kFoldMul < q * kFoldMul) ? rc : q, k) >> (2 * B);
+        return x >= x_lo && x < x_hi;
+    }
+};
+
+// Sort passes over bucket ranges: bucket x belongs to pass x * P / 4^t.
+__host__ __device__ __forceinline__ u64 fold_pass_begin(u64 p, u64 P, u64 total) { return (p * total + P - 1) / P; }
+__global__ void fold_pass_hist_kernel(const FoldRunInPass pred, const u64 n_runs, const u64 total, const u32 P, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 h = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (h < n_runs) {
+        const u32 i = pred.heads[h];
+        if ((pred.validbits[i >> 5] >> (i & 31u)) & 1u) {
+            const u64 q = pred.kmers[i], rc = fold_revcomp(q, pred.k);
+            const u64 x = fold_key((rc * kFoldMul < q * kFoldMul) ? rc : q, pred.k) >> (2 * pred.B);
+            atomicAdd(&sh[(u32)(x * P / total)], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < P && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
 __device__ __forceinline__ u64 fold_rank1(const DevIndex &d, u64 p) {  // ones in mask[0, p), p in [0, N]
     const AuxBlock &a = d.aux[p >> 6];
     return a.mask_cum + (u64)__popcll(a.mask & low_mask((u32)p & 63u));
 }
 
-// One entry per run h = SA interval [heads[h], heads[h+1]) of a distinct k-mer: key = orient(k-mer),
-// val = id | state << 32 | (the run is the reverse complement of its key) << 34. Runs of invalid rows
-// get state 0 and drop out when the rows are assembled.
-__global__ void fold_entries_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u32 *__restrict__ validbits,
-                                    const u32 *__restrict__ heads, const u64 n_heads, const u32 k, u64 *__restrict__ keys,
-                                    u64 *__restrict__ vals) {
-    const u64 h = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (h >= n_heads) return;
+// One entry per selected run h = sel[e] = SA interval [heads[h], heads[h+1]) of a distinct k-mer: key = key(k-mer),
+// val = id | state << 32 | (the run is the reverse complement of its key's orientation) << 34 | self-complementary << 35.
+__global__ void fold_entries_kernel(const DevIndex d, const u64 *__restrict__ kmers, const u32 *__restrict__ heads, const u64 n_heads,
+                                    const u32 *__restrict__ sel, const u64 n_sel, const u32 k, u64 *__restrict__ keys, u64 *__restrict__ vals) {
+    const u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (e >= n_sel) return;
+    const u64 h = sel[e];
     const u64 i = heads[h], j = (h + 1 < n_heads) ? (u64)heads[h + 1] : d.n;
     const u64 q = kmers[i];
-    const bool valid = (validbits[i >> 5] >> (i & 31u)) & 1u;
     const u64 rc = revcomp_packed(q, k);
     const bool sw = fold_swapped(q, rc);
-    u64 state = 0, id = 0;
-    if (valid) {
-        const u64 ri = fold_rank1(d, i), rj = fold_rank1(d, j);
-        const bool first = (d.aux[i >> 6].mask >> (i & 63)) & 1ull;
-        state = rj > ri ? (first ? 3 : 2) : 1;
-        id = ri;
-    }
-    keys[h] = fold_key(sw ? rc : q, k);
-    vals[h] = id | (state << 32) | ((u64)sw << 34) | ((u64)(q == rc) << 35);
+    const u64 ri = fold_rank1(d, i), rj = fold_rank1(d, j);
+    const bool first = (d.aux[i >> 6].mask >> (i & 63)) & 1ull;
+    const u64 state = rj > ri ? (first ? 3 : 2) : 1;
+    keys[e] = fold_key(sw ? rc : q, k);
+    vals[e] = ri | (state << 32) | ((u64)sw << 34) | ((u64)(q == rc) << 35);
 }
 
 struct alignas(32) FoldBucket {
-    u32 start, end, flags, w[5];
+    u32 gstart, ovf, meta, w[5];
 };
 static_assert(sizeof(FoldBucket) == 32, "one sector");
 
-// One row per group g = entries [gs[g], gs[g+1]) of equal key (the run of the key itself and/or the run
-// of its reverse complement; a self-complementary k-mer has one run that stands for both).
+// One row per group g = entries [gs[g], gs[g+1]) of equal key (the run of the key itself and/or the run of its
+// reverse complement; a self-complementary k-mer has one run that stands for both). Row g of this pass is global
+// row g0 + g. bfirst / bcount: first local row and number of rows of every bucket of the pass (zeroed before).
 __global__ void fold_rows_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, const u32 *__restrict__ gs,
-                                 const u64 n_groups, const u64 n_entries, const u32 k, const u32 B, u64 *__restrict__ rows,
-                                 uint2 *__restrict__ ids, FoldBucket *__restrict__ buckets) {
+                                 const u64 n_groups, const u64 n_entries, const u32 B, const u64 g0, const u64 x_lo,
+                                 u64 *__restrict__ rows, uint2 *__restrict__ ids, u32 *__restrict__ bfirst, u32 *__restrict__ bcount) {
     const u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     const u64 e0 = gs[g], e1 = (g + 1 < n_groups) ? (u64)gs[g + 1] : n_entries;
@@ -156,7 +205,6 @@ __global__ void fold_rows_kernel(const u64 *__restrict__ keys, const u64 *__rest
         const u64 v = vals[e];
         const u32 st = (u32)(v >> 32) & 3u;
         self_rc |= (v >> 35) & 1ull;
-        if (!st) continue;
         if ((v >> 34) & 1ull) {
             sr = st;
             idr = (u32)v;
@@ -172,28 +220,44 @@ __global__ void fold_rows_kernel(const u64 *__restrict__ keys, const u64 *__rest
     if (sf < 2) idf = kFoldNoId;
     if (sr < 2) idr = kFoldNoId;
     const u64 pmask = B ? ((1ull << (2 * B)) - 1ull) : 0ull;
-    rows[g] = ((key & pmask) << 4) | sf | (sr << 2);
-    ids[g] = make_uint2(idf, idr);
-    const u64 x = key >> (2 * B);
-    const bool first = g == 0 || (keys[gs[g - 1]] >> (2 * B)) != x;
-    const bool last = g + 1 == n_groups || (keys[e1] >> (2 * B)) != x;
-    if (first) buckets[x].start = (u32)g;
-    if (last) buckets[x].end = (u32)(g + 1);
+    if (rows) rows[g] = ((key & pmask) << 4) | sf | (sr << 2);
+    if (ids) ids[g0 + g] = make_uint2(idf, idr);
+    if (bfirst) {
+        const u64 x = key >> (2 * B);
+        const bool first = g == 0 || (keys[gs[g - 1]] >> (2 * B)) != x;
+        const bool last = g + 1 == n_groups || (keys[e1] >> (2 * B)) != x;
+        if (first) bfirst[x - x_lo] = (u32)g;
+        if (last) bcount[x - x_lo] = (u32)(g + 1);  // = first + count once `first` is subtracted below
+    }
+}
+
+// entries a bucket needs in orows[]: count word + overflow rows, padded to whole sectors (0 when everything is inline)
+__global__ void fold_ovf_sizes_kernel(const u32 *__restrict__ bfirst, const u32 *__restrict__ bcount, const u64 n_buckets, const u32 cap,
+                                      u32 *__restrict__ sizes) {
+    const u64 x = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (x >= n_buckets) return;
+    const u32 cnt = bcount[x] ? bcount[x] - bfirst[x] : 0u;
+    sizes[x] = cnt > cap ? ((1u + cnt - cap + 3u) & ~3u) : 0u;
 }
 
 template <bool PAY64>
-__global__ void fold_bucket_fill_kernel(const u64 *__restrict__ rows, const u64 total, FoldBucket *__restrict__ buckets) {
+__global__ void fold_bucket_fill_kernel(const u64 *__restrict__ rows, const u32 *__restrict__ bfirst, const u32 *__restrict__ bcount,
+                                        const u64 *__restrict__ ovf_off, const u64 n_buckets, const u64 g0, const u64 o0,
+                                        FoldBucket *__restrict__ buckets, u64 *__restrict__ orows) {
     const u64 x = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (x >= total) return;
-    FoldBucket b = buckets[x];
-    b.flags = 0;
-    for (int s = 0; s < 5; ++s) b.w[s] = 0;
+    if (x >= n_buckets) return;
     const u32 cap = PAY64 ? kFoldCap64 : kFoldCap32;
-    const u32 cnt = b.end - b.start;
+    const u32 first = bfirst[x];
+    const u32 cnt = bcount[x] ? bcount[x] - first : 0u;
+    FoldBucket b;
+    b.gstart = (u32)(g0 + first);
+    b.ovf = (u32)(o0 + ovf_off[x]);
+    for (int s = 0; s < 5; ++s) b.w[s] = 0;
     const u32 m = cnt < cap ? cnt : cap;
+    u32 meta = m << 20;
     for (u32 s = 0; s < m; ++s) {
-        const u64 row = rows[(u64)b.start + s];
-        b.flags |= (u32)(row & 15ull) << (4 * s);
+        const u64 row = rows[(u64)first + s];
+        meta |= (u32)(row & 15ull) << (4 * s);
         const u64 pay = row >> 4;
         if (PAY64) {
             b.w[1 + 2 * s] = (u32)pay;
@@ -202,6 +266,15 @@ __global__ void fold_bucket_fill_kernel(const u64 *__restrict__ rows, const u64 
             b.w[s] = (u32)pay;
         }
     }
+    if (cnt > cap) {
+        meta |= kFoldMetaOvf;
+        const u32 n_ovf = cnt - cap;
+        u64 *o = orows + ovf_off[x];  // this pass's chunk
+        o[0] = n_ovf;
+        for (u32 s = 0; s < n_ovf; ++s) o[1 + s] = rows[(u64)first + cap + s];
+        for (u32 s = 1 + n_ovf; s < ((1u + n_ovf + 3u) & ~3u); ++s) o[s] = ~0ull;
+    }
+    b.meta = meta;
     buckets[x] = b;
 }
 
@@ -228,77 +301,190 @@ inline u64 fold_select_heads(u64 count, u32 *out, Pred pred) {
 
 struct FoldArrays {  // device arrays of a built tier (ownership passes to the caller)
     FoldBucket *buckets = nullptr;
-    u64 *rows = nullptr;
+    u64 *orows = nullptr;
     uint2 *ids = nullptr;
-    u64 n_rows = 0;
+    u64 n_rows = 0, n_orows = 0;
 };
 
+// Sort passes: the buffers of a pass (selection 4 B, keys / values and their sort doubles 32 B, group heads 4 B,
+// rows 8 B per entry) are kept near `kFoldPassBytes`.
+constexpr u64 kFoldPassBytes = 12ull << 30;
+inline u32 fold_passes(u64 N, u32 t) {
+    u64 p = (48ull * N + kFoldPassBytes - 1) / kFoldPassBytes;
+    const u64 buckets = 1ull << (2 * t);
+    if (p > buckets) p = buckets;
+    if (p > 256) p = 256;
+    return (u32)(p < 1 ? 1 : p);
+}
 // Peak device memory of build_fold_on_device beyond the index itself (bytes), and what stays resident.
-inline u64 fold_build_peak_bytes(u64 N, u32 t) { return 36ull * N + (32ull << (2 * t)) + (64ull << 20); }
-inline u64 fold_resident_bytes(u64 N, u32 t) { return 16ull * N + (32ull << (2 * t)); }
+inline u64 fold_build_peak_bytes(u64 N, u32 t, bool with_ids) {
+    const u64 passes = fold_passes(N, t);
+    return 12ull * N + N / 8 + (32ull << (2 * t)) + (with_ids ? 8ull * N : 0ull) + 48ull * N / passes + (12ull << (2 * t)) / passes + N / 2 + (64ull << 20);
+}
+inline u64 fold_resident_bytes(u64 N, u32 t, bool with_ids) { return (32ull << (2 * t)) + N + (with_ids ? 8ull * N : 0ull); }
 
+// want_table: buckets + overflow rows; want_ids: the lookup ids (row numbering is the same whichever is built).
 // Throws std::runtime_error (out of memory included); nothing is leaked then.
-inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, u32 t, FoldArrays &out, uint64_t *launches) {
+inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, u32 t, bool want_table, bool want_ids, FoldArrays &out,
+                                 uint64_t *launches) {
     const u64 N = d.n;
     const u32 B = k - t;
     const u64 total = 1ull << (2 * t);
+    const u32 cap = B > 16 ? kFoldCap64 : kFoldCap32;
     auto stage = [](const char *what) {  // surfaces asynchronous errors with the step that caused them
         cudaError_t e = cudaDeviceSynchronize();
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
     };
-    DevArr<FoldBucket> buckets(total);
-    BCU(cudaMemset(buckets.p, 0, total * sizeof(FoldBucket)));
-    DevArr<u64> keys, vals;
+    const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing) fprintf(stderr, "[fmsi timing] fold build: %s at %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    uint64_t nl = 0;
+    DevArr<u64> kmers(N);
+    DevArr<u32> validbits((N >> 5) + 2);
+    {
+        DevArr<u32> psi(N);
+        psi_scatter_kernel<<<nblocks_for(N), 256>>>(d, psi.p);
+        stage("psi");
+        fold_kmers_kernel<<<nblocks_for(N), 256>>>(N, psi.p, (u32)counts[1], (u32)counts[2], (u32)counts[3], k, kmers.p, validbits.p);
+        stage("k-mers of the SA rows");
+        nl += 2;
+    }
+    lap("k-mers of the SA rows");
+    DevArr<u32> heads;
     u64 M = 0;
     {
-        DevArr<u64> kmers(N);
-        DevArr<u32> validbits((N >> 5) + 2);
-        {
-            DevArr<u32> psi(N);
-            psi_scatter_kernel<<<nblocks_for(N), 256>>>(d, psi.p);
-            stage("psi");
-            fold_kmers_kernel<<<nblocks_for(N), 256>>>(N, psi.p, (u32)counts[1], (u32)counts[2], (u32)counts[3], k, kmers.p, validbits.p);
-            stage("k-mers of the SA rows");
-        }
-        DevArr<u32> heads(N);
-        M = fold_select_heads(N, heads.p, FoldRunHead{kmers.p, validbits.p});
+        DevArr<u32> all(N);
+        M = fold_select_heads(N, all.p, FoldRunHead{kmers.p, validbits.p});
         stage("run heads");
-        keys.alloc(M);
-        vals.alloc(M);
-        fold_entries_kernel<<<nblocks_for(M), 256>>>(d, kmers.p, validbits.p, heads.p, M, k, keys.p, vals.p);
-        stage("entries");
+        if (M * 10 < N * 9) {  // many rows per run (repetitive index): keep an exact-size copy
+            heads.alloc(M);
+            BCU(cudaMemcpy(heads.p, all.p, M * 4, cudaMemcpyDeviceToDevice));
+        } else {
+            heads.p = all.p;
+            heads.n = all.n;
+            all.p = nullptr;
+        }
     }
+    lap("run heads");
+    DevArr<FoldBucket> buckets;
+    if (want_table) buckets.alloc(total);
+    DevArr<uint2> ids;
+    if (want_ids) ids.alloc(M + 1);  // rows <= runs
+    std::vector<std::unique_ptr<DevArr<u64>>> ochunks;
+    std::vector<u64> ochunk_len;
+    const u32 P = fold_passes(M, t);
+    // how many runs each pass will select (one streamed pass over the runs), so that its buffers are exact
+    std::vector<unsigned long long> h_hist(P, 0);
     {
-        DevArr<u64> keys_alt(M), vals_alt(M);
-        radix_sort_pairs(keys, keys_alt, vals, vals_alt, M, (int)(2 * k));
-        stage("sort");
+        DevArr<unsigned long long> hist(P);
+        BCU(cudaMemset(hist.p, 0, P * sizeof(unsigned long long)));
+        fold_pass_hist_kernel<<<nblocks_for(M), 256>>>(FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, 0, total}, M, total, P, hist.p);
+        stage("pass histogram");
+        BCU(cudaMemcpy(h_hist.data(), hist.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        nl += 1;
     }
-    DevArr<u32> gs(M);
-    const u64 G = fold_select_heads(M, gs.p, FoldKeyHead{keys.p});
-    stage("group heads");
-    DevArr<u64> rows(G + 8);
-    DevArr<uint2> ids(G + 1);
-    BCU(cudaMemset(rows.p + G, 0xff, 8 * sizeof(u64)));
-    fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, M, k, B, rows.p, ids.p, buckets.p);
-    stage("rows");
-    if (B > 16) fold_bucket_fill_kernel<true><<<nblocks_for(total), 256>>>(rows.p, total, buckets.p);
-    else fold_bucket_fill_kernel<false><<<nblocks_for(total), 256>>>(rows.p, total, buckets.p);
-    stage("buckets");
-    if (launches) *launches += 12;
+    u64 G0 = 0, O0 = 0;
+    for (u32 p = 0; p < P; ++p) {
+        const u64 x_lo = fold_pass_begin(p, P, total), x_hi = fold_pass_begin(p + 1, P, total), nb = x_hi - x_lo;
+        DevArr<u32> bfirst, bcount;
+        if (want_table) {
+            bfirst.alloc(nb);
+            bcount.alloc(nb);
+            BCU(cudaMemset(bfirst.p, 0, nb * 4));
+            BCU(cudaMemset(bcount.p, 0, nb * 4));
+        }
+        DevArr<u64> rows;
+        u64 G = 0;
+        {
+            DevArr<u64> keys, vals;
+            u64 Mp = 0;
+            {
+                DevArr<u32> sel(h_hist[p] + 1);
+                Mp = fold_select_heads(M, sel.p, FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, x_lo, x_hi});
+                stage("runs of the pass");
+                if (Mp != h_hist[p]) throw std::runtime_error("pass histogram and selection disagree");
+                keys.alloc(Mp);
+                vals.alloc(Mp);
+                fold_entries_kernel<<<nblocks_for(Mp), 256>>>(d, kmers.p, heads.p, M, sel.p, Mp, k, keys.p, vals.p);
+                stage("entries");
+                nl += 2;
+            }
+            {
+                DevArr<u64> keys_alt(Mp), vals_alt(Mp);
+                radix_sort_pairs(keys, keys_alt, vals, vals_alt, Mp, (int)(2 * k));
+                stage("sort");
+            }
+            DevArr<u32> gs(Mp);
+            G = fold_select_heads(Mp, gs.p, FoldKeyHead{keys.p});
+            stage("group heads");
+            if (want_table) rows.alloc(G + 1);
+            fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, B, G0, x_lo, want_table ? rows.p : nullptr,
+                                                      want_ids ? ids.p : nullptr, want_table ? bfirst.p : nullptr, want_table ? bcount.p : nullptr);
+            stage("rows");
+            nl += 3;
+        }
+        if (want_table) {
+            DevArr<u32> sizes(nb);
+            fold_ovf_sizes_kernel<<<nblocks_for(nb), 256>>>(bfirst.p, bcount.p, nb, cap, sizes.p);
+            DevArr<u64> off(nb + 1);
+            exclusive_sum_u64(sizes.p, off.p, nb);
+            u64 last_off = 0;
+            u32 last_size = 0;
+            BCU(cudaMemcpy(&last_off, off.p + nb - 1, 8, cudaMemcpyDeviceToHost));
+            BCU(cudaMemcpy(&last_size, sizes.p + nb - 1, 4, cudaMemcpyDeviceToHost));
+            const u64 olen = last_off + last_size;
+            if (O0 + olen >= (1ull << 32)) throw std::runtime_error("overflow rows exceed 32-bit offsets");
+            ochunks.emplace_back(new DevArr<u64>(olen ? olen : 1));
+            ochunk_len.push_back(olen);
+            if (B > 16) fold_bucket_fill_kernel<true><<<nblocks_for(nb), 256>>>(rows.p, bfirst.p, bcount.p, off.p, nb, G0, O0, buckets.p + x_lo, ochunks.back()->p);
+            else fold_bucket_fill_kernel<false><<<nblocks_for(nb), 256>>>(rows.p, bfirst.p, bcount.p, off.p, nb, G0, O0, buckets.p + x_lo, ochunks.back()->p);
+            stage("buckets");
+            nl += 3;
+            O0 += olen;
+        }
+        G0 += G;
+    }
+    lap("sort passes");
+    if (G0 >= (1ull << 32)) throw std::runtime_error("more than 2^32 rows");
+    kmers.release();
+    heads.release();
+    validbits.release();
+    DevArr<u64> orows;
+    if (want_table) {
+        orows.alloc(O0 + 8);
+        BCU(cudaMemset(orows.p + O0, 0xff, 8 * sizeof(u64)));
+        u64 at = 0;
+        for (size_t c = 0; c < ochunks.size(); ++c) {
+            if (ochunk_len[c]) BCU(cudaMemcpy(orows.p + at, ochunks[c]->p, ochunk_len[c] * 8, cudaMemcpyDeviceToDevice));
+            at += ochunk_len[c];
+            ochunks[c].reset();
+        }
+    }
+    if (want_ids && G0 * 10 < M * 9) {  // far fewer rows than runs: exact-size ids
+        DevArr<uint2> exact(G0 + 1);
+        BCU(cudaMemcpy(exact.p, ids.p, G0 * sizeof(uint2), cudaMemcpyDeviceToDevice));
+        std::swap(exact.p, ids.p);
+        std::swap(exact.n, ids.n);
+    }
+    lap("done");
+    if (launches) *launches += nl;
     out.buckets = buckets.p;
-    out.rows = rows.p;
+    out.orows = orows.p;
     out.ids = ids.p;
-    out.n_rows = G;
+    out.n_rows = G0;
+    out.n_orows = O0;
     buckets.p = nullptr;
-    rows.p = nullptr;
+    orows.p = nullptr;
     ids.p = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------- query
-enum { FP_BUCKET = 0, FP_SEARCH = 1, FP_IDS = 2 };
+enum { FP_BUCKET = 0, FP_OVF = 1, FP_SEARCH = 2, FP_IDS = 3 };
 
-// A bucket / rows sector. LD64: ask L2 for a 64-byte fill instead of the whole 128-byte line.
+// A bucket / overflow sector. LD64: ask L2 for a 64-byte fill instead of the whole 128-byte line.
 template <bool LD64>
 __device__ __forceinline__ void ld_fold_sector(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
     if (LD64) {
@@ -330,7 +516,9 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
     bool active = false, swapped = false;
     u32 phase = FP_BUCKET;
     u64 idx = 0, q = 0, bx = 0;
-    u32 lo = 0, hi = 0, row = 0, st = 0;
+    // a bucket's overflow region: entries [ovf + 1, ovf + 1 + n_ovf) of orows[] hold its rows gbase + CAP, ...;
+    // a search narrows [lo, hi) (entry numbers)
+    u32 lo = 0, hi = 0, row = 0, st = 0, ovf = 0, gbase = 0;
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
     bool exhausted = false;
     u32 nprobe = 0;  // dependent memory requests issued by this lane (reported when probe_ctr is given)
@@ -390,22 +578,23 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
 
         // ---------------------------------------------------------------- issue this round's loads
         const bool isB = active && phase == FP_BUCKET;
+        const bool isO = active && phase == FP_OVF;
         const bool isS = active && phase == FP_SEARCH;
         const bool isI = active && phase == FP_IDS;
-        const u32 r0 = (lo + ((hi - lo) >> 1)) & ~3u;  // rows sector probed by a search step
+        const u32 r0 = isO ? ovf : ((lo + ((hi - lo) >> 1)) & ~3u);  // overflow sector probed (entry number)
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         if (isB) ld_fold_sector<LD64>(reinterpret_cast<const char *>(fv.buckets) + (bx << 5), a0, a1, a2, a3);
-        if (isS) ld_fold_sector<LD64>(fv.rows + r0, a0, a1, a2, a3);
+        if (isO || isS) ld_fold_sector<LD64>(fv.orows + r0, a0, a1, a2, a3);
         if (isI) a0 = __ldg(reinterpret_cast<const u64 *>(fv.ids) + row);
-        nprobe += (u32)(isB || isS || isI);
+        nprobe += (u32)(isB || isO || isS || isI);
 
         // ---------------------------------------------------------------- consume
         bool done = false;  // (st, row) final
         if (isB) {
-            const u32 start = (u32)a0, end = (u32)(a0 >> 32);
-            const u32 cnt = end - start;
-            const u32 flags = (u32)a1;
-            const u32 m = cnt < CAP ? cnt : CAP;
+            gbase = (u32)a0;
+            ovf = (u32)(a0 >> 32);
+            const u32 meta = (u32)a1;
+            const u32 m = (meta >> 20) & 7u;
             st = 0;
             bool found = false;
             u64 last = 0;
@@ -418,21 +607,27 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
                     last = pay;
                     if (pay == q) {
                         found = true;
-                        st = (flags >> (4 * s)) & 15u;
-                        row = start + s;
+                        st = (meta >> (4 * s)) & 15u;
+                        row = gbase + s;
                     }
                 }
             }
-            if (found || cnt <= CAP || last > q) {
-                done = true;
+            // rows are sorted by payload: the inline ones are the bucket's smallest
+            if (found || !(meta & kFoldMetaOvf) || last > q) done = true;
+            else phase = FP_OVF;
+        } else if (isO || isS) {
+            // entries [w0, w1) of this sector are rows; invariant of a search: rows before lo have payload < q,
+            // rows from hi on have payload > q
+            u32 w0, w1;
+            if (isO) {  // first sector of the region: a0 = number of overflow rows, then the first three
+                lo = ovf + 1;
+                hi = ovf + 1 + (u32)a0;
+                w0 = lo;
+                w1 = hi < ovf + 4 ? hi : ovf + 4;
             } else {
-                lo = start + CAP;
-                hi = end;
-                phase = FP_SEARCH;
+                w0 = r0 > lo ? r0 : lo;
+                w1 = (r0 + 4 < hi) ? r0 + 4 : hi;
             }
-        } else if (isS) {
-            // invariant: rows before lo have payload < q, rows from hi on have payload > q
-            const u32 w0 = r0 > lo ? r0 : lo, w1 = (r0 + 4 < hi) ? r0 + 4 : hi;  // rows [w0, w1) of this sector count
             bool found = false;
             u64 first = 0, last = 0;
 #pragma unroll
@@ -446,7 +641,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
                     if (pay == q) {
                         found = true;
                         st = (u32)rw & 15u;
-                        row = r;
+                        row = gbase + CAP + (r - ovf - 1);
                     }
                 }
             }
@@ -455,6 +650,7 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
             else if (first > q) hi = w0;
             else done = true;  // q falls between two rows of this sector: absent (st stays 0)
             if (!done && lo >= hi) done = true;
+            if (!done) phase = FP_SEARCH;
         }
 
         if (done || isI) {

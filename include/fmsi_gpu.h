@@ -68,13 +68,18 @@ typedef struct fmsi_gpu_index fmsi_gpu_index;
 typedef struct {
     int32_t prefix_t;      /* depth of the k-mer suffix lookup table; -1 = auto, 0 = none */
     int32_t sb_shift_log2; /* test hook: superblock size (log2 blocks); 0 = auto */
-    int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto (2, else 1, else 0 as memory allows),
+    int32_t dict;          /* k-mer dictionary tier for single-k-mer queries: -1 = auto (2, else 1, else 0 as memory allows; a note on
+                            * stderr says so when auto ends below 2, and fmsi_gpu_index_info.dict tells which tier is resident),
                             * 0 = off (backward search), 1 = SA-ordered dictionary (one probe per strand search),
                             * 2 = strand-folded dictionary (one probe per k-mer) */
     int32_t multistep;     /* multi-step rank arrays of the backward-search kernels (m LF-steps per memory request):
                             * -1 = auto (2 when no dictionary tier is resident and they fit), 0 = off, 2 or 3 = bases
                             * per probe (2.3 / 9.1 bytes of device memory per BWT position) */
-    int64_t reserved[5];
+    int32_t fold_ids;      /* lookup ids of the strand-folded dictionary (8 bytes per distinct k-mer, read only by OUT_ORDERS
+                            * queries): 0 = built on the first lookup, 1 = built with the tier, -1 = never (lookups then run
+                            * on the backward-search kernels) */
+    int32_t reserved32;
+    int64_t reserved[4];
 } fmsi_gpu_options;
 
 typedef struct {
@@ -91,7 +96,8 @@ typedef struct {
     int32_t dict;        /* resident dictionary tier: 0 none, 1 SA-ordered, 2 strand-folded */
     int32_t dict_t;      /* bucket depth of that tier (bases) */
     int32_t multistep;   /* bases per probe of the resident multi-step rank arrays (0 = none) */
-    int32_t reserved[4];
+    int32_t fold_ids;    /* 1 when the strand-folded dictionary's lookup ids are resident */
+    int32_t reserved[3];
 } fmsi_gpu_index_info;
 
 const char *fmsi_gpu_last_error(void);

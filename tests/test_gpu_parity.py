@@ -254,6 +254,35 @@ def test_dictionary_tier_on_repetitive_index(tmp_path):
         oi.close()
 
 
+def test_fold_lookup_ids_are_built_on_demand():
+    """The strand-folded dictionary keeps its lookup ids (8 bytes per distinct k-mer) out of device memory until a lookup
+    needs them (fmsi_gpu_options.fold_ids: 0 = on the first lookup, 1 = with the tier, -1 = never: lookups then run on
+    the backward-search kernels). The answers are the oracle's under every policy."""
+    d = os.path.join(GOLDEN, "syn_k31_min")
+    prefix = os.path.join(d, "ms.fa")
+    k = 31
+    oi = OracleIndex.load(prefix, use_klcp=False)
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    kmers = _random_kmers(np.random.default_rng(3), ms_codes, k, 3000)
+    want = oi.query_packed(kmers, k, MODE_OR, True)
+    sizes = {}
+    for policy in (0, 1, -1):
+        gi = fg.Index.load(prefix, use_klcp=True, dict=2, fold_ids=policy)
+        assert gi.dict_kind == 2 and gi.fold_ids == (policy == 1)
+        assert np.array_equal(gi.query_kmers(kmers, k, fg.MODE_ALL).astype(np.int64), oi.query_packed(kmers, k, MODE_ALL, False))
+        assert gi.refresh_info().fold_ids == (policy == 1)  # presence queries never build them
+        assert np.array_equal(gi.query_kmers(kmers, k, output=fg.OUT_ORDERS), want)
+        assert gi.refresh_info().fold_ids == (policy != -1)
+        sizes[policy] = gi.hbm_bytes
+        reads = list(synth.read_queries(ms_codes, 150, 40, 4))
+        bases, offs, lens = _chunks_of(reads, k, 64)
+        allk = np.concatenate([synth.pack_kmers(synth.ascii_to_codes(bases[o:o + l]), k) for o, l in zip(offs.tolist(), lens.tolist())])
+        assert np.array_equal(gi.query_chunks(bases, offs, lens, k, output=fg.OUT_ORDERS, streaming=True), oi.query_packed(allk, k, MODE_OR, True))
+        gi.close()
+    assert sizes[0] == sizes[1] > sizes[-1]
+    oi.close()
+
+
 def _chunks_of(seq_codes_list, k, max_kmers):
     """Concatenate sequences into one base buffer and cut each into chunks of <= max_kmers k-mers
     overlapping by k-1 (the shape ms_query produces)."""
