@@ -671,16 +671,13 @@ def bench_kmers(cx: Ctx, gi, wl: dict, mode: int, output: int, label: str, batch
 
 
 def bench_reads(cx: Ctx, gi, wl: dict, mode: int, output: int, streaming: bool, label: str, n_reads: int, steps: int, warmup: int, seed: int) -> tuple[dict, dict]:
-    """150-bp reads as chunks of text. Device-resident: 2-bit packed text + chunk arrays in HBM (two alternating read
-    sets). e2e: fmsi_gpu_query_chunks_packed from pinned host memory, presence bits back (ids for lookup)."""
+    """150-bp reads. Device-resident: 2-bit packed text + read offsets in HBM (two alternating read sets). e2e:
+    fmsi_gpu_query_reads_packed from pinned host memory, presence bits back (ids for lookup)."""
     import fmsi_b200 as fg
     torch = cx.torch
     k = wl["k"]
     L_ = fg.lib()
-    off, ln, roff, n_res = reads_layout(n_reads, k)
-    d_off = torch.from_numpy(off.view(np.int64)).to(cx.dev)
-    d_len = torch.from_numpy(ln.view(np.int32)).to(cx.dev)
-    d_roff = torch.from_numpy(roff.view(np.int64)).to(cx.dev)
+    n_res = n_reads * (READ_LEN - k + 1)
     nbuf = 2
     codes = wl["codes"] if wl.get("codes") is not None else torch.from_numpy(wl["genome"]).to(cx.dev)
     rds = [device_reads(codes, n_reads, seed + 31 * cx.rank + b, cx.dev) for b in range(nbuf)]
@@ -689,22 +686,25 @@ def bench_reads(cx: Ctx, gi, wl: dict, mode: int, output: int, streaming: bool, 
     rb = 1 if output == fg.OUT_PRESENCE else 8
     d_out = torch.empty(n_res * rb, dtype=torch.uint8, device=cx.dev)
     p_text = [t.cpu().pin_memory() for t in d_text]
-    p_off, p_len, p_roff = [torch.from_numpy(a).pin_memory() for a in (off.view(np.int64), ln.view(np.int32), roff.view(np.int64))]
     out_e2e = fg.OUT_PRESENCE_BITS if output == fg.OUT_PRESENCE else output
     e2e_out_bytes = (n_res + 7) // 8 if out_e2e == fg.OUT_PRESENCE_BITS else n_res * rb
     p_out = torch.empty(e2e_out_bytes, dtype=torch.uint8).pin_memory()
 
-    def call(text_ptr, off_ptr, len_ptr, roff_ptr, out_ptr, outk, mem, stream):
-        rc = L_.fmsi_gpu_query_chunks_packed(gi._h, mode, outk, fg.STRANDS_LAZY, int(streaming), text_ptr, n_bases, off_ptr, len_ptr, roff_ptr,
-                                             off.size, n_res, k, out_ptr, mem, stream)
+    # whole reads in (fmsi_gpu_query_reads_packed): 2-bit text + one offset per read; the device cuts them into chunks
+    read_off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    d_read_off = torch.from_numpy(read_off.view(np.int64)).to(cx.dev)
+    p_read_off = torch.from_numpy(read_off.view(np.int64)).pin_memory()
+
+    def call(text_ptr, roff_ptr, out_ptr, outk, mem, stream):
+        rc = L_.fmsi_gpu_query_reads_packed(gi._h, mode, outk, fg.STRANDS_LAZY, int(streaming), text_ptr, n_bases, roff_ptr, n_reads, n_res, k, out_ptr, mem, stream)
         if rc != 0:
             raise RuntimeError(L_.fmsi_gpu_last_error().decode())
 
     def step_device(s_):
-        call(d_text[s_ % nbuf].data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_roff.data_ptr(), d_out.data_ptr(), output, fg.MEM_DEVICE, cx.stream.cuda_stream)
+        call(d_text[s_ % nbuf].data_ptr(), d_read_off.data_ptr(), d_out.data_ptr(), output, fg.MEM_DEVICE, cx.stream.cuda_stream)
 
     def step_host(s_):
-        call(p_text[s_ % nbuf].data_ptr(), p_off.data_ptr(), p_len.data_ptr(), p_roff.data_ptr(), p_out.data_ptr(), out_e2e, fg.MEM_HOST, None)
+        call(p_text[s_ % nbuf].data_ptr(), p_read_off.data_ptr(), p_out.data_ptr(), out_e2e, fg.MEM_HOST, None)
 
     ms = cx.time_device(step_device, steps, warmup)
     e2e_s = cx.time_host(step_host, steps)
@@ -723,14 +723,14 @@ def bench_reads(cx: Ctx, gi, wl: dict, mode: int, output: int, streaming: bool, 
               (fg.MODE_OR, fg.OUT_ORDERS): "OR,ORDERS,LAZY"}[(mode, output)]
     kern = kernel_name(gi, True, streaming, suffix)
     in_bytes_per_kmer = n_bases / 4 / n_res  # 2 bits per base
-    h2d = int(p_text[0].numel() * 8 + off.nbytes + ln.nbytes + roff.nbytes)
+    h2d = int(p_text[0].numel() * 8 + read_off.nbytes)
     # the timed step = the query kernel plus, when a dictionary tier answers the chunks, the slot -> k-mer extraction
     res = dict(mode=label, value=cx.world * n_res / (ms / 1e3), unit=UNIT, ms_per_step=ms, kmers_per_step_per_gpu=n_res, reads_per_step_per_gpu=n_reads,
                tier={2: "strand-folded dictionary", 1: "SA-ordered dictionary", 0: "backward search"}[gi.dict_kind], multistep=gi.multistep,
                prefix_t=gi.prefix_t, index_hbm_bytes=gi.hbm_bytes, frac_present=round(frac_present, 4), e2e_equals_device=same,
                e2e=dict(value=cx.world * n_res / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=e2e_out_bytes,
                         h2d_gbs_per_gpu=round(h2d / e2e_s / 1e9, 2), bytes_per_kmer=round((h2d + e2e_out_bytes) / n_res, 3),
-                        note="2-bit packed text + chunk arrays in, " + ("presence bits" if out_e2e == fg.OUT_PRESENCE_BITS else "int64 ids") + " out"),
+                        note="fmsi_gpu_query_reads_packed: 2-bit packed text + one offset per read in, " + ("presence bits" if out_e2e == fg.OUT_PRESENCE_BITS else "int64 ids") + " out"),
                roofline=roofline_for(kern, n_res, ms, in_bytes_per_kmer, rb, ppk, cx.peak, cx.peak_src,
                                      traffic_key=f"{kern}@{wl['name']},reads" + (f",ms{gi.multistep}" if gi.dict_kind == 0 else "")),
                gpu_launches=int(launches))

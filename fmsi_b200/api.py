@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "fmsi_gpu_infer_presence", "fmsi_gpu_kmer_order_if_present", "fmsi_gpu_query_kmers",
     "fmsi_gpu_query_chunks", "fmsi_gpu_launch_count", "fmsi_gpu_pool_create", "fmsi_gpu_pool_size", "fmsi_gpu_pool_member", "fmsi_gpu_pool_free",
     "fmsi_gpu_pool_query_kmers", "fmsi_gpu_pool_query_chunks", "fmsi_gpu_query_kmers_general", "fmsi_gpu_query_chunks_general",
-    "fmsi_gpu_query_chunks_packed", "fmsi_gpu_count_probes",
+    "fmsi_gpu_query_chunks_packed", "fmsi_gpu_count_probes", "fmsi_gpu_query_reads_packed",
 ]
 F_OR, F_AND, F_XOR, F_RANGE = 0, 1, 2, 3
 
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
                                         C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks_packed.argtypes = L.fmsi_gpu_query_chunks.argtypes
     L.fmsi_gpu_count_probes.argtypes = [vp, C.c_int, u64p]
+    L.fmsi_gpu_query_reads_packed.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_kmers_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, C.c_int, vp, C.c_int, vp]
     L.fmsi_gpu_query_chunks_general.argtypes = [vp, C.POINTER(Function), vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int,
                                                 vp, C.c_int, vp]
@@ -338,6 +339,22 @@ class Index:
                                           out.ctypes.data, MEM_HOST, None))
         return out
 
+
+    def query_reads(self, reads, k: int | None = None, mode: int = MODE_OR, output: int = OUT_PRESENCE, strands: int = STRANDS_LAZY,
+                    streaming: bool = False) -> np.ndarray:
+        """fmsi_gpu_query_reads_packed: `reads` = list of ASCII byte strings (any lengths); results read by read."""
+        k = self.k if k is None else k
+        lens = np.array([len(r) for r in reads], dtype=np.int64)
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens).astype(np.uint64)
+        text = np.frombuffer(b"".join(reads), dtype=np.uint8)
+        words = pack_text(text)
+        n_res = int(np.maximum(lens - k + 1, 0).sum())
+        dt, shape = result_dtype_shape(output, strands, n_res)
+        out = np.empty(shape, dtype=dt)
+        _check(lib().fmsi_gpu_query_reads_packed(self._h, mode, output, strands, int(streaming), words.ctypes.data, text.size, off.ctypes.data,
+                                                len(reads), n_res, k, out.ctypes.data, MEM_HOST, None))
+        return out
 
     def _query_chunks_packed(self, words: np.ndarray, n_bases: int, chunk_off, chunk_len, k, mode, output, strands, streaming) -> np.ndarray:
         off = _u64(chunk_off)

@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include <thrust/iterator/transform_iterator.h>
+
 #include "device_index.cuh"
 #include "dict.cuh"
 #include "fold.cuh"
@@ -287,6 +289,19 @@ int dispatch_query(const fmsi_gpu_index *idx, const DevIndex &d, int mode, int o
     if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
     return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
 }
+
+// cub temp storage of one ExclusiveSum over n u32 counts, and the reads-mode device scratch behind the chunk arrays:
+// read offsets, result / chunk prefix sums (n + 1 u64 each), per-read counts (2 x u32), scan temp.
+struct U32ToU64 {  // 64-bit accumulation of 32-bit counts
+    __host__ __device__ __forceinline__ u64 operator()(const u32 x) const { return (u64)x; }
+};
+typedef thrust::transform_iterator<U32ToU64, const u32 *> CountIter;
+size_t reads_scan_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, CountIter((const u32 *)nullptr, U32ToU64()), (u64 *)nullptr, (int)n);
+    return bytes + 256;
+}
+size_t reads_scratch_bytes(size_t n) { return 3 * (n + 1) * 8 + 2 * ((n * 4 + 63) & ~size_t(63)) + reads_scan_temp_bytes(n) + 1024; }
 
 size_t result_bytes(int output, int strands) {
     if (output == FMSI_GPU_OUT_PRESENCE) return 1;
@@ -1270,7 +1285,10 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // the kLCP array describes (k-1)-mers of the index's own k (construct_klcp, fms_index.h:357-385)
     if (streaming && k <= 32 && k != idx->meta.k) return fail(FMSI_GPU_ERR_K, "streaming queries need k equal to the index's k");
     if (n_chunks == 0 || n_results == 0) return FMSI_GPU_OK;
-    if (!text || !chunk_off || !chunk_len || !res_off || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
+    // reads mode (fmsi_gpu_query_reads_packed): chunk_off = read_off[n_reads + 1], n_chunks = n_reads, no chunk arrays —
+    // the device cuts the reads into chunks itself
+    const bool reads_mode = chunk_len == nullptr && res_off == nullptr;
+    if (!text || !chunk_off || (!reads_mode && (!chunk_len || !res_off)) || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
     if (output == FMSI_GPU_OUT_ORDERS && (u32)k == idx->fold.k) ensure_fold_ids(idx);
     const DevIndex d = dev_for_k(idx, k);
@@ -1288,6 +1306,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     const u64 *d_off = chunk_off, *d_res = res_off;
     const u32 *d_len = chunk_len;
     void *d_results = results;
+    char *reads_scratch = nullptr;
     int rc;
     // scratch: [packed bases | (host mode) bases, offsets, lens, res_off | packed k-mers (non-streaming)]
     // Per-k-mer strand values do not depend on how they are computed (kLCP interval reuse is only a
@@ -1305,13 +1324,17 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // run (and their results come back) on two others, so H2D, kernels and D2H overlap within the call.
     const size_t kPiece = (size_t)8 << 20;  // bases per piece (a multiple of 32)
     const bool pipelined = on_host && n_bases > 2 * kPiece;
+    // reads mode: the streaming kernel takes chunks of <= 64 k-mers, every other path one chunk per read
+    const size_t n_reads = reads_mode ? n_chunks : 0;
+    const u32 read_max_kmers = (reads_mode && !via_kmers) ? FMSI_GPU_MAX_STREAM_KMERS : 0u;
+    if (reads_mode) n_chunks = read_max_kmers ? n_reads + n_results / read_max_kmers + 1 : n_reads;  // capacity of the device chunk arrays
     auto bad_stream_chunk = [&](size_t c) { return chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS; };
     const char *kBadStreamChunk = "streaming chunks must hold between 1 and FMSI_GPU_MAX_STREAM_KMERS k-mers";
     if (on_host) {
         for (auto &sl : idx->slots) CU(cudaEventSynchronize(sl.done));
         if (pipelined && !idx->aux_stream) CU(cudaStreamCreateWithFlags(&idx->aux_stream, cudaStreamNonBlocking));
         const size_t text_stage = packed_in ? 0 : ((n_bases + 15) & ~size_t(15));
-        const size_t in_need = text_stage + n_chunks * (8 + 8 + 4) + 64;
+        const size_t in_need = text_stage + n_chunks * (8 + 8 + 4) + 64 + (reads_mode ? reads_scratch_bytes(n_reads) : 0);
         // bit-packed output: the packed bits sit behind the byte results
         const size_t out_need = n_results * rbytes + (bits ? ((n_results + 7) / 8 + 64) : 0);
         if ((rc = ensure(&s.d_in, &s.in_cap, in_need)) || (rc = ensure(&s.d_out, &s.out_cap, out_need))) return rc;
@@ -1323,11 +1346,67 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         d_res = (const u64 *)p;
         p += n_chunks * 8;
         d_len = (const u32 *)p;
+        p += ((n_chunks * 4 + 63) & ~size_t(63));
+        reads_scratch = p;
         d_results = s.d_out;
-    } else if (bits) {
-        if ((rc = ensure(&idx->d_user_bytes, &idx->user_bytes_cap, n_results))) return rc;
-        d_results = idx->d_user_bytes;
+    } else {
+        if (bits) {
+            if ((rc = ensure(&idx->d_user_bytes, &idx->user_bytes_cap, n_results))) return rc;
+            d_results = idx->d_user_bytes;
+        }
+        if (reads_mode) {  // device-mode reads: the chunk arrays live in the slot's input scratch
+            const size_t need = n_chunks * (8 + 8 + 4) + 128 + reads_scratch_bytes(n_reads);
+            if ((rc = ensure(&s.d_in, &s.in_cap, need))) return rc;
+            char *p = (char *)s.d_in;
+            d_off = (const u64 *)p;
+            p += n_chunks * 8;
+            d_res = (const u64 *)p;
+            p += n_chunks * 8;
+            d_len = (const u32 *)p;
+            p += ((n_chunks * 4 + 63) & ~size_t(63));
+            reads_scratch = p;
+        }
     }
+    // reads -> device chunk arrays, on stream q (reads mode): read offsets up (host mode), counts, two prefix sums, expansion
+    auto expand_reads = [&](cudaStream_t q) -> int {
+        char *p = reads_scratch;
+        u64 *d_roff = (u64 *)p;
+        p += (n_reads + 1) * 8;
+        u64 *d_rbase = (u64 *)p;
+        p += (n_reads + 1) * 8;
+        u64 *d_cbase = (u64 *)p;
+        p += (n_reads + 1) * 8;
+        u32 *d_nk = (u32 *)p;
+        p += ((n_reads * 4 + 63) & ~size_t(63));
+        u32 *d_nch = (u32 *)p;
+        p += ((n_reads * 4 + 63) & ~size_t(63));
+        void *d_tmp = (void *)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+        size_t tmp_bytes = reads_scan_temp_bytes(n_reads);
+        const u64 *roff_dev = chunk_off;
+        if (on_host) {
+            CU(cudaMemcpyAsync(d_roff, chunk_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, q));
+            roff_dev = d_roff;
+        }
+        read_counts_kernel<<<blocks_for(n_reads), 256, 0, q>>>(roff_dev, (u64)n_reads, (u64)n_bases, (u32)k, read_max_kmers, d_nk, d_nch);
+        CU(cudaGetLastError());
+        CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, CountIter(d_nk, U32ToU64()), d_rbase, (int)n_reads, q));
+        tmp_bytes = reads_scan_temp_bytes(n_reads);
+        CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, CountIter(d_nch, U32ToU64()), d_cbase, (int)n_reads, q));
+        expand_reads_kernel<<<blocks_for(n_reads), 256, 0, q>>>(roff_dev, (u64)n_reads, (u64)n_bases, (u32)k, read_max_kmers, d_nk, d_rbase, d_cbase,
+                                                                 (u64 *)d_off, (u32 *)d_len, (u64 *)d_res);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(4);
+        return FMSI_GPU_OK;
+    };
+    // host view of a read (reads mode, host buffers): results and device chunks it yields; false if malformed
+    auto read_counts = [&](size_t r, u64 &nk, u64 &nch) -> bool {
+        const u64 a = chunk_off[r], b = chunk_off[r + 1];
+        if (b < a || b > n_bases) return false;
+        const u64 len = b - a;
+        nk = len >= (u64)k ? len - (u64)k + 1 : 0;
+        nch = read_max_kmers ? (nk + read_max_kmers - 1) / read_max_kmers : 1;
+        return true;
+    };
     // chunk metadata [c0, c1) to the device (host mode)
     auto upload_chunks = [&](size_t c0, size_t c1, cudaStream_t q) -> int {
         if (c1 <= c0) return FMSI_GPU_OK;
@@ -1400,7 +1479,25 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     };
 
     auto single_batch = [&]() -> int {
-        if (on_host) {
+        size_t chunks_used = n_chunks;
+        if (reads_mode) {
+            if (on_host) {
+                u64 R = 0, C = 0;
+                for (size_t r = 0; r < n_reads; ++r) {
+                    u64 nk, nch;
+                    if (!read_counts(r, nk, nch)) return fail(FMSI_GPU_ERR_ARG, "read offsets must be non-decreasing and end inside the text");
+                    R += nk;
+                    C += nch;
+                }
+                if (R != n_results) return fail(FMSI_GPU_ERR_ARG, "n_results does not match the reads");
+                chunks_used = (size_t)C;
+            }
+            // device-mode streamed reads: the chunk count is only known on the device; the unused tail of the chunk
+            // arrays (sized for the worst case) holds empty chunks, which the kernel skips — no synchronisation
+            if (!on_host && read_max_kmers) CU(cudaMemsetAsync((void *)d_len, 0, n_chunks * 4, st));
+            int e = expand_reads(st);
+            if (e) return e;
+        } else if (on_host) {
             for (size_t c = 0; c < n_chunks; ++c) {
                 if (chunk_off[c] + chunk_len[c] > n_bases) return fail(FMSI_GPU_ERR_ARG, "chunk exceeds the text");
                 if (streaming && !longk && bad_stream_chunk(c)) return fail(FMSI_GPU_ERR_ARG, kBadStreamChunk);
@@ -1410,7 +1507,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         }
         int e = stage_words(0, n_words, st);
         if (e) return e;
-        e = run_span(0, n_chunks, 0, n_results, st, on_host ? s.ls : idx->user);
+        e = run_span(0, chunks_used, 0, n_results, st, on_host ? s.ls : idx->user);
         if (e) return e;
         if ((e = finish_bits(st))) return e;
         if (on_host) {
@@ -1438,6 +1535,9 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     size_t back_r0 = 0, back_r1 = 0;  // span whose results are still on the device
     cudaStream_t back_q = nullptr;
     bool ordered = true;
+    size_t rd_done = 0;  // reads mode: reads whose chunks have been scheduled
+    u64 rd_R = 0, rd_C = 0;  //             results / device chunks of those reads
+    if (reads_mode && (rc = expand_reads(st))) return rc;
     for (size_t p0 = 0; p0 < n_bases && ordered; p0 += kPiece) {
         const size_t p1 = std::min(n_bases, p0 + kPiece);
         const bool last = p1 == n_bases;
@@ -1445,6 +1545,36 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         if ((rc = stage_words(w0, w1, st))) return rc;
         size_t c1 = c_done;
         const double tv0 = trace ? tr_us() : 0;
+        if (reads_mode) {  // the reads that lie wholly inside the uploaded prefix
+            for (; rd_done < n_reads; ++rd_done) {
+                u64 nk, nch;
+                if (!read_counts(rd_done, nk, nch)) return fail(FMSI_GPU_ERR_ARG, "read offsets must be non-decreasing and end inside the text");
+                if (!last && chunk_off[rd_done + 1] > 32 * w1) break;
+                rd_R += nk;
+                rd_C += nch;
+            }
+            if (trace) tr_validate += tr_us() - tv0;
+            if (rd_C == c_done && rd_R == r_done) continue;
+            if (last && rd_R != n_results) return fail(FMSI_GPU_ERR_ARG, "n_results does not match the reads");
+            if (rd_R > n_results) return fail(FMSI_GPU_ERR_ARG, "n_results does not match the reads");
+            if (idx->piece_events.size() <= span) {
+                cudaEvent_t ev;
+                CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                idx->piece_events.push_back(ev);
+            }
+            CU(cudaEventRecord(idx->piece_events[span], st));
+            cudaStream_t q = qs[span & 1];
+            CU(cudaStreamWaitEvent(q, idx->piece_events[span], 0));
+            if ((rc = run_span(c_done, (size_t)rd_C, r_done, (size_t)rd_R, q, *qls[span & 1]))) return rc;
+            if (back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
+            back_r0 = r_done;
+            back_r1 = (size_t)rd_R;
+            back_q = q;
+            c_done = (size_t)rd_C;
+            r_done = (size_t)rd_R;
+            ++span;
+            continue;
+        }
         for (; c1 < n_chunks; ++c1) {
             const uint64_t end = chunk_off[c1] + chunk_len[c1];
             if (c1 > 0 && (chunk_off[c1] < chunk_off[c1 - 1] || end < chunk_off[c1 - 1] + chunk_len[c1 - 1] || res_off[c1] < res_off[c1 - 1])) {
@@ -1518,6 +1648,14 @@ int fmsi_gpu_query_chunks_packed(fmsi_gpu_index *idx, int mode, int output, int 
     if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
     return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, text2, FMSI_GPU_TEXT_PACKED2, n_bases, chunk_off, chunk_len, res_off,
                              n_chunks, n_results, k, results, mem, stream);
+}
+
+int fmsi_gpu_query_reads_packed(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming, const uint64_t *text2, size_t n_bases,
+                                const uint64_t *read_off, size_t n_reads, size_t n_results, int k, void *results, int mem, void *stream) {
+    if (mode != FMSI_GPU_MODE_OR && mode != FMSI_GPU_MODE_ALL) return fail(FMSI_GPU_ERR_ARG, "bad mode/output/strands");
+    if (n_reads >= (1ull << 31)) return fail(FMSI_GPU_ERR_ARG, "too many reads in one call");
+    return query_chunks_impl(idx, mode, output, strands, streaming, nullptr, text2, FMSI_GPU_TEXT_PACKED2, n_bases, read_off, nullptr, nullptr, n_reads,
+                             n_results, k, results, mem, stream);
 }
 
 int fmsi_gpu_query_kmers_general(fmsi_gpu_index *idx, const fmsi_gpu_function *f, const uint64_t *kmers, size_t n, int k,

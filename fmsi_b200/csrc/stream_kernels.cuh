@@ -153,6 +153,40 @@ __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *
                      [&](u64 slot) { kmers[slot] = 0; });
 }
 
+// Reads -> chunks, on the device (fmsi_gpu_query_reads_packed): read r = bases [roff[r], roff[r+1]) yields
+// nk = max(0, len - k + 1) results, cut into chunks of at most `max_kmers` k-mers overlapping by k-1 (the streaming
+// kernel's limit), or one chunk per read when max_kmers == 0 (the single-query kernels take chunks of any length; a read
+// shorter than k becomes a chunk without results). rbase / cbase = exclusive prefix sums of nk / chunk counts.
+__global__ void read_counts_kernel(const u64 *__restrict__ roff, const u64 n_reads, const u64 n_bases, const u32 k, const u32 max_kmers,
+                                   u32 *__restrict__ nk, u32 *__restrict__ nch) {
+    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const u64 a = roff[r], b = roff[r + 1];
+    const u64 len = (b >= a && b <= n_bases) ? b - a : 0;  // a malformed read (device-mode callers) yields nothing
+    const u64 m = len >= k ? len - k + 1 : 0;
+    nk[r] = (u32)(m > 0xFFFFFF00ull ? 0xFFFFFF00ull : m);
+    nch[r] = max_kmers ? (u32)((m + max_kmers - 1) / max_kmers) : 1u;
+}
+__global__ void expand_reads_kernel(const u64 *__restrict__ roff, const u64 n_reads, const u64 n_bases, const u32 k, const u32 max_kmers,
+                                    const u32 *__restrict__ nk, const u64 *__restrict__ rbase, const u64 *__restrict__ cbase,
+                                    u64 *__restrict__ coff, u32 *__restrict__ clen, u64 *__restrict__ cres) {
+    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const u64 a = roff[r], m = nk[r], c0 = cbase[r], r0 = rbase[r];
+    if (!max_kmers) {
+        coff[c0] = a < n_bases ? a : 0;
+        clen[c0] = m ? (u32)(m + k - 1) : 0u;
+        cres[c0] = r0;
+        return;
+    }
+    for (u64 p = 0, c = c0; p < m; p += max_kmers, ++c) {
+        const u64 take = m - p < max_kmers ? m - p : max_kmers;
+        coff[c] = a + p;
+        clen[c] = (u32)(take + k - 1);
+        cres[c] = r0 + p;
+    }
+}
+
 enum { SP_TABLE = 0, SP_STEP = 1, SP_MX = 2 };
 
 __device__ __forceinline__ u64 sel3(u32 w, u64 w0, u64 w1, u64 w2) { return w == 0 ? w0 : (w == 1 ? w1 : w2); }

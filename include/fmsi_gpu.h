@@ -194,6 +194,17 @@ int fmsi_gpu_query_chunks_packed(fmsi_gpu_index *idx, int mode, int output, int 
                                  const uint32_t *chunk_len, const uint64_t *res_off, size_t n_chunks,
                                  size_t n_results, int k, void *results, int mem, void *stream);
 
+/* The same over whole READS: read r is bases [read_off[r], read_off[r+1]) of the 2-bit packed text (read_off[] has
+ * n_reads + 1 non-decreasing entries, the last <= n_bases), a read shorter than k yields nothing, and results come back to
+ * back in read order — n_results = sum over reads of max(0, length - k + 1), which the caller computes to size `results`
+ * (checked: FMSI_GPU_ERR_ARG). The device cuts the reads into the chunks its kernels take (<= FMSI_GPU_MAX_STREAM_KMERS
+ * k-mers each for the streaming kernel), so a read costs 8 bytes of offsets on PCIe instead of 20 bytes per chunk and the
+ * host validates one entry per read: what ms_query's record loop (src/main.cpp:337-354) hands to query_kmers(), batched.
+ * With mem = DEVICE read_off is a device pointer as well (malformed entries then yield no results). */
+int fmsi_gpu_query_reads_packed(fmsi_gpu_index *idx, int mode, int output, int strands, int streaming,
+                                const uint64_t *text2, size_t n_bases, const uint64_t *read_off, size_t n_reads,
+                                size_t n_results, int k, void *results, int mem, void *stream);
+
 /* ---- f-MS framework: general demasking functions -------------------------------------------- */
 /* query_kmers<query_mode::general>() — reference src/fms_index.h:317-327 with single_query_general
  * (:171-179) and the demasking functions of src/functions.h:7-57: the number of ON occurrences and of

@@ -117,6 +117,53 @@ def test_build_matches_reference_hashes_at_scale(name, tmp_path):
     idx.close()
 
 
+@pytest.mark.usefixtures("oracle_built")
+@pytest.mark.skipif(not os.path.exists(HASHES), reason="tests/golden/ref_index_hashes.json not generated")
+def test_wide_layout_at_100mbp(tmp_path):
+    """The wide (N >= 2^32) device layout — 64-bit positions, per-superblock counter bases, 16-byte table entries — on a
+    100 Mbp index (the reference-hash input above), forced through the `sb_shift_log2` hook with superblocks of 2^10 and
+    2^16 blocks: every mode and strand policy, single k-mers and streamed reads, must equal the narrow layout on 1 M
+    queries and the oracle on a sample. (A BWT beyond 2^32 rows itself is out of the GPU builder's reach.)"""
+    from oracle_ffi import MODE_ALL, MODE_OR, OracleIndex
+    case = json.load(open(HASHES))["iid_100m_k31"]
+    k = case["k"]
+    ms = synth.random_masked_superstring(case["n"], case["seed"], k, case["off"])
+    built = fg.Index.build(ms, k, with_klcp=True, dict=0, multistep=0, prefix_t=0)
+    prefix = str(tmp_path / "ms.fa")
+    built.save(prefix)
+    built.close()
+    codes = synth.ascii_to_codes(ms[:3_000_000])
+    kmers = synth.pack_rows(synth.kmer_queries(codes, k, 1_000_000, 11))
+    reads = list(synth.read_queries(codes, 150, 3000, 12))
+    bases = b"".join(synth.codes_to_ascii(r) for r in reads)
+    offs = np.repeat(np.arange(len(reads), dtype=np.uint64) * 150, 2) + np.tile(np.array([0, 64], dtype=np.uint64), len(reads))
+    lens = np.tile(np.array([64 + k - 1, 150 - 64], dtype=np.uint32), len(reads))
+    narrow = fg.Index.load(prefix, use_klcp=True, dict=0)
+    assert not narrow.wide and narrow.multistep == 2
+    oi = OracleIndex.load(prefix, use_klcp=True)
+    sample = kmers[:20_000]
+    combos = ((fg.MODE_ALL, fg.OUT_PRESENCE, MODE_ALL, False), (fg.MODE_OR, fg.OUT_PRESENCE, MODE_OR, False), (fg.MODE_OR, fg.OUT_ORDERS, MODE_OR, True))
+    ref = {}
+    for mode, out, omode, oord in combos:
+        for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+            ref[(mode, out, strands)] = narrow.query_kmers(kmers, k, mode, out, strands)
+            ref[(mode, out, strands, "S")] = narrow.query_chunks(bases, offs, lens, k, mode, out, strands, True)
+        assert np.array_equal(ref[(mode, out, fg.STRANDS_LAZY)][:len(sample)].astype(np.int64), oi.query_packed(sample, k, omode, oord))
+    narrow.close()
+    for shift in (10, 16):
+        wide = fg.Index.load(prefix, use_klcp=True, sb_shift_log2=shift)
+        assert wide.wide and not wide.dict and wide.multistep == 0
+        for mode, out, omode, oord in combos:
+            for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+                assert np.array_equal(wide.query_kmers(kmers, k, mode, out, strands), ref[(mode, out, strands)]), (shift, mode, out, strands)
+                assert np.array_equal(wide.query_chunks(bases, offs, lens, k, mode, out, strands, True), ref[(mode, out, strands, "S")]), (shift, "S")
+        ii = np.random.default_rng(shift).integers(0, wide.n + 1, size=2000).astype(np.uint64)
+        cc = np.random.default_rng(shift + 1).integers(0, 4, size=2000).astype(np.uint8)
+        assert wide.rank(ii, cc).tolist() == [oi.rank(i, c) for i, c in zip(ii, cc)]
+        wide.close()
+    oi.close()
+
+
 def test_build_rejects_bad_input():
     with pytest.raises(fg.FmsiGpuError):
         fg.Index.build(b"ACGTNACGT", 3)

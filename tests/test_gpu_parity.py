@@ -531,6 +531,56 @@ def test_bit_packed_results_and_packed_text(tier):
     gi.close()
 
 
+@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0"])
+def test_reads_api_matches_chunk_calls(tier):
+    """fmsi_gpu_query_reads_packed: the caller hands over whole reads (offsets into one 2-bit text), the device cuts them
+    into the chunks its kernels take. Reads of every awkward length (empty, shorter than k, exactly k, 64 / 65 / 129
+    k-mers, thousands of bases) must give what the chunk calls give — those are the ones checked against the oracle —
+    streamed and single, every output, and through the pipelined host path (> 16 MiB of text)."""
+    d = os.path.join(GOLDEN, "syn_k31_min")
+    k = 31
+    prefix = os.path.join(d, "ms.fa")
+    gi = fg.Index.load(prefix, use_klcp=True, **TIER_KW[tier])
+    ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    rng = np.random.default_rng(31)
+    lens = [0, 5, k - 1, k, k + 1, k + 63, k + 64, k + 128, 150, 150, 151, 3000, 1, 200, k + 62]
+    seqs = []
+    for ln in lens * 3:
+        if ln <= len(ms_codes) and rng.random() < 0.7:
+            p0 = int(rng.integers(0, len(ms_codes) - ln + 1))
+            c = ms_codes[p0:p0 + ln].copy()
+            if ln and rng.random() < 0.5:
+                c = synth.revcomp_codes(c)
+        else:
+            c = rng.integers(0, 4, size=ln).astype(np.uint8)
+        seqs.append(c.astype(np.uint8))
+    reads = [synth.codes_to_ascii(c) for c in seqs]
+    bases, offs, clens = _chunks_of([c for c in seqs if len(c) >= k], k, 64)
+    for streaming in (False, True):
+        for mode, out, strands in ((fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY), (fg.MODE_OR, fg.OUT_PRESENCE, fg.STRANDS_BOTH),
+                                   (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_LAZY), (fg.MODE_OR, fg.OUT_ORDERS, fg.STRANDS_BOTH), (fg.MODE_ALL, fg.OUT_PRESENCE_BITS, fg.STRANDS_LAZY)):
+            a = gi.query_reads(reads, k, mode, out, strands, streaming)
+            b = gi.query_chunks(bases, offs, clens, k, mode, out, strands, streaming)
+            assert np.array_equal(a, b), (tier, streaming, mode, out, strands)
+    # pipelined host path: 130 000 reads of 150 bp (19.5 M bases)
+    big = synth.read_queries(ms_codes, 150, 130_000, 21)
+    big_reads = [synth.codes_to_ascii(r) for r in big]
+    bases, offs, clens = _chunks_of(list(big), k, 64)
+    for streaming, out in ((True, fg.OUT_PRESENCE), (False, fg.OUT_PRESENCE_BITS), (True, fg.OUT_ORDERS)):
+        assert np.array_equal(gi.query_reads(big_reads, k, fg.MODE_ALL if out != fg.OUT_ORDERS else fg.MODE_OR, out, fg.STRANDS_LAZY, streaming),
+                              gi.query_chunks(bases, offs, clens, k, fg.MODE_ALL if out != fg.OUT_ORDERS else fg.MODE_OR, out, fg.STRANDS_LAZY, streaming)), (tier, "big", streaming, out)
+    # malformed calls
+    L_ = fg.lib()
+    words = fg.pack_text(np.frombuffer(b"ACGT" * 50, dtype=np.uint8))
+    res = np.zeros(1000, np.uint8)
+    for off, n_res in (([0, 100, 50, 200], 140 - 0), ([0, 100, 300], 240), ([0, 100, 200], 7)):
+        o = np.array(off, dtype=np.uint64)
+        rc = L_.fmsi_gpu_query_reads_packed(gi._h, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY, 0, words.ctypes.data, 200, o.ctypes.data, len(off) - 1, n_res, k,
+                                            res.ctypes.data, fg.MEM_HOST, None)
+        assert rc == -1, (off, n_res)
+    gi.close()
+
+
 def test_error_behaviour():
     with pytest.raises(fg.FmsiGpuError) as e:
         fg.Index.load("/nonexistent/prefix")
