@@ -506,9 +506,12 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-        self.dev = torch.device("cuda", self.local_rank)
-        torch.cuda.set_device(self.dev)
-        self.stream = torch.cuda.current_stream(self.dev)
+        if torch.cuda.is_available():
+            self.dev = torch.device("cuda", self.local_rank)
+            torch.cuda.set_device(self.dev)
+            self.stream = torch.cuda.current_stream(self.dev)
+        else:  # the bookkeeping (process group, gathers) is testable without a device: tests/test_shard.py
+            self.dev, self.stream = torch.device("cpu"), None
         self.dist = None
         self.peak, self.peak_src = measured_peak_gbs()
 
@@ -541,6 +544,8 @@ class Ctx:
             self.dist.barrier()
 
     def sync_all(self):
+        if self.stream is None:
+            return self.barrier()
         self.torch.cuda.synchronize(self.dev)
         if self.dist:
             self.dist.barrier()
@@ -1155,6 +1160,22 @@ def main():
         oi.close()
         oi = None
 
+    # ---- one COMMON batch sharded over the ranks (fmsi_b200/shard.py: contiguous ranges, gather to rank 0 in query order) --
+    sharded = None
+    if world > 1:
+        def sharded_run():
+            from fmsi_b200 import shard
+            q = host_kmer_sample(wl, 1 << 22, 4242)  # same seed on every rank: the same batch
+            t0 = time.perf_counter()
+            full = shard.sharded_query_kmers(q, lambda part: gi.query_kmers(part, k, fg.MODE_ALL), rank, world)
+            dt = cx.max_over_ranks(time.perf_counter() - t0)
+            if rank != 0:
+                return None
+            whole = gi.query_kmers(q, k, fg.MODE_ALL)
+            return dict(kmers=int(q.size), ranks=world, equals_single_gpu=bool(np.array_equal(full, whole)), seconds=round(dt, 4),
+                        note="plan_kmers ranges answered by each rank's replica, shards gathered to rank 0 in query order over the bookkeeping group")
+        sharded = safe("sharded common batch", sharded_run)
+
     # ---- in-process multi-GPU scheduler (fmsi_gpu_pool_*): replicas by device-to-device copy --------------------------
     if world > 1 and args.modes != "none":
         def pool_run():
@@ -1225,7 +1246,7 @@ def main():
     line = dict(metric=METRIC, value=head["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=head["ms_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64", data="synthetic", config=cfg, details=details,
                 roofline=head["roofline"], cpu_baseline=cpu, e2e=head["e2e"], gpu_launches=head["gpu_launches"], clocks=clocks,
-                tiers=tiers, modes=modes, cli=cli, pool=pool)
+                tiers=tiers, modes=modes, cli=cli, pool=pool, sharded=sharded)
     print(json.dumps(line))
     if cx.dist:
         cx.dist.barrier()

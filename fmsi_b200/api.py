@@ -177,9 +177,9 @@ class Index:
         self.dict_t = int(info.dict_t)
         self.multistep = int(info.multistep)
         self.fold_ids = bool(info.fold_ids)
-        return self
         self.hbm_bytes = int(info.hbm_bytes)
         self.mask_ones = int(info.mask_ones)
+        return self
 
     # ---- construction -------------------------------------------------------------------------
     @staticmethod

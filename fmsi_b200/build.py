@@ -98,6 +98,15 @@ def build_tools(force: bool = False, verbose: bool = True) -> None:
         _run(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", exe, src], verbose)
 
 
+def build_wide_synth(force: bool = False, verbose: bool = True) -> str:
+    """Synthetic-index generator for the N >= 2^32 tests (tests/test_gpu_wide.py)."""
+    src = os.path.join(CSRC, "tools", "wide_synth.cpp")
+    exe = os.path.join(BIN, "wide_synth")
+    if force or _newer(exe, [src, os.path.join(CSRC, "sdsl_io.hpp")]):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", exe, src], verbose)
+    return exe
+
+
 def build_oracle(verbose: bool = True) -> None:
     """Test infrastructure: the C restatement, and the reference binaries when their sources exist."""
     _run(["make", "-C", os.path.join(ROOT, "oracle"), "-j4", "all"] + ([] if verbose else ["-s"]), verbose)
@@ -107,6 +116,7 @@ def build_all(force: bool = False, verbose: bool = True) -> None:
     build_lib(force, verbose)
     build_cli(force, verbose)
     build_tools(force, verbose)
+    build_wide_synth(force, verbose)
     build_oracle(verbose)
 
 

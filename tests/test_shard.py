@@ -108,3 +108,58 @@ def test_world_size_2_gloo_shard_and_gather(tmp_path, oracle_built):
     res = json.load(open(out))
     assert res["ok"] and res["n"] == 3001
     assert res["n_chunk_results"] == 40 * (150 - 31 + 1)
+
+
+def _bench_worker(rank, world, port, case, out_path):
+    """bench.py's multi-rank bookkeeping without a device: process group over gloo, max over ranks, the parity sample
+    of EVERY rank gathered to and checked on rank 0 (the oracle stands in for the rank's GPU replica)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import argparse
+    import bench
+    from oracle_ffi import OracleIndex
+    cx = bench.Ctx(argparse.Namespace(batch=0, no_parity=False))
+    cx.init_dist()
+    assert cx.world == world and cx.rank == rank
+    assert cx.max_over_ranks(float(rank + 1)) == float(world)
+    k = json.load(open(os.path.join(case, "meta.json")))["k"]
+    prefix = os.path.join(case, "ms.fa")
+    ms = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
+    wl = dict(name="t", prefix=prefix, k=k, genome=ms, codes=None)
+    replica = OracleIndex.load(prefix, use_klcp=False)
+
+    class Replica:  # what bench.py calls on the rank's index
+        def __init__(self, wrong):
+            self.wrong = wrong
+
+        def query_kmers(self, q, kk, mode, output):
+            r = replica.query_packed(q, kk, 1 if mode == 1 else 0, output == 1)
+            if self.wrong and len(r):
+                r = r.copy()
+                r[0] ^= 1
+            return r
+
+    oi = replica if rank == 0 else None
+    ok = bench.parity_kmers(cx, Replica(False), oi, wl, 500, 7, 1, 0, 1, False)
+    bad = bench.parity_kmers(cx, Replica(rank == world - 1), oi, wl, 500, 8, 1, 0, 1, False)  # only the LAST rank answers wrongly
+    reads = synth.read_queries(ms, 150, 20, 5 + rank)
+    allk = np.concatenate([synth.pack_kmers(r, k) for r in reads])
+    res = (replica.query_packed(allk, k, 1, False) == 1).astype(np.uint8)
+    rok = bench.parity_reads(cx, oi, wl, dict(reads=reads, results=res), 1, False)
+    if rank == 0:
+        with open(out_path, "w") as f:
+            json.dump({"ok": ok, "bad": bad, "reads": rok}, f)
+    else:
+        assert ok is None and bad is None and rok is None
+    cx.barrier()
+    cx.dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_2_bench_parity_bookkeeping(tmp_path, oracle_built):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.json")
+    mp.spawn(_bench_worker, args=(2, _free_port(), os.path.join(GOLDEN, "syn_k31_max"), out), nprocs=2, join=True)
+    res = json.load(open(out))
+    assert res == {"ok": True, "bad": False, "reads": True}  # a wrong answer on rank 1 is caught on rank 0
