@@ -103,6 +103,52 @@ __global__ void fold_kmers_kernel(const u64 n, const u32 *__restrict__ psi, cons
     if ((threadIdx.x & 31u) == 0 && r < n) validbits[r >> 5] = b;
 }
 
+// The same k-mers by pointer doubling instead of a k-1 step walk per row (30 dependent random reads at k = 31):
+//   K_l[r] = the first l characters of the suffix of row r, P_l[r] = the row l characters further on;
+//   K_2l[r] = K_l[r] . K_l[P_l[r]],  P_2l[r] = P_l[P_l[r]]            (l = 1, 2, 4, 8, 16: 8 random gathers in all)
+// with psi made sticky at row 0 (the sentinel's suffix: psi'[0] = 0, and row 0 reads as A), which pads past the
+// sentinel with A exactly like the walk. The rows whose suffix is shorter than k are the k rows LF reaches from row 0.
+__device__ __forceinline__ u32 fold_fcol(u32 row, u32 c1, u32 c2, u32 c3) { return (row >= c3) ? 3u : (row >= c2) ? 2u : (row >= c1) ? 1u : 0u; }
+__global__ void fold_sticky_kernel(u32 *__restrict__ psi) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) psi[0] = 0;
+}
+// one doubling step: kin == nullptr means l = 1 (characters come from the F column)
+__global__ void fold_double_kernel(const u64 n, const u32 *__restrict__ pin, const u32 *__restrict__ kin, const u32 l, const u32 c1, const u32 c2,
+                                   const u32 c3, u32 *__restrict__ pout, u32 *__restrict__ kout) {
+    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u32 p = __ldg(pin + r);
+    const u32 a = kin ? __ldg(kin + r) : fold_fcol((u32)r, c1, c2, c3);
+    const u32 b = kin ? __ldg(kin + p) : fold_fcol(p, c1, c2, c3);
+    kout[r] = (a << (2 * l)) | b;
+    pout[r] = __ldg(pin + p);
+}
+__global__ void fold_double_last_kernel(const u64 n, const u32 *__restrict__ p16, const u32 *__restrict__ k16, const u32 k, u64 *__restrict__ kmers) {
+    const u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u64 k32 = ((u64)__ldg(k16 + r) << 32) | (u64)__ldg(k16 + __ldg(p16 + r));
+    kmers[r] = k32 >> (2 * (32 - k));
+}
+// validbits: all rows valid, except the k rows whose suffix holds fewer than k characters (LF-walk from row 0)
+__global__ void fold_valid_fill_kernel(const u64 n, u32 *__restrict__ validbits) {
+    const u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (w * 32 >= n) return;
+    const u64 left = n - w * 32;
+    validbits[w] = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+}
+__global__ void fold_valid_clear_kernel(const DevIndex d, const u32 k, u32 *__restrict__ validbits) {
+    if (blockIdx.x || threadIdx.x) return;
+    u64 cur = 0;
+    for (u32 s = 0; s < k; ++s) {
+        validbits[cur >> 5] &= ~(1u << (cur & 31u));
+        if (cur == d.dollar) break;  // that was the whole text
+        u64 a0, a1, a2, a3;
+        ld_sector_l1(d.rank + (cur >> 6), a0, a1, a2, a3);
+        const u32 c = block_symbol(a2, a3, (u32)cur & 63u);
+        cur = lf_map<false>(d, a0, a1, a2, a3, (u32)cur, c);
+    }
+}
+
 struct FoldRunHead {  // row r starts a run of equal k-mers of equal validity
     const u64 *kmers;
     const u32 *validbits;
@@ -319,7 +365,9 @@ inline u32 fold_passes(u64 N, u32 t) {
 // Peak device memory of build_fold_on_device beyond the index itself (bytes), and what stays resident.
 inline u64 fold_build_peak_bytes(u64 N, u32 t, bool with_ids) {
     const u64 passes = fold_passes(N, t);
-    return 12ull * N + N / 8 + (32ull << (2 * t)) + (with_ids ? 8ull * N : 0ull) + 48ull * N / passes + (12ull << (2 * t)) / passes + N / 2 + (64ull << 20);
+    const u64 sort_stage = 12ull * N + N / 8 + (32ull << (2 * t)) + (with_ids ? 8ull * N : 0ull) + 48ull * N / passes + (12ull << (2 * t)) / passes + N / 2;
+    const u64 kmer_stage = 20ull * N + N / 8;  // pointer doubling: k-mers 8N (holds K_l meanwhile), P_l twice, K_16
+    return (sort_stage > kmer_stage ? sort_stage : kmer_stage) + (64ull << 20);
 }
 inline u64 fold_resident_bytes(u64 N, u32 t, bool with_ids) { return (32ull << (2 * t)) + N + (with_ids ? 8ull * N : 0ull); }
 
@@ -345,12 +393,40 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
     DevArr<u64> kmers(N);
     DevArr<u32> validbits((N >> 5) + 2);
     {
-        DevArr<u32> psi(N);
-        psi_scatter_kernel<<<nblocks_for(N), 256>>>(d, psi.p);
+        const u32 c1 = (u32)counts[1], c2 = (u32)counts[2], c3 = (u32)counts[3];
+        DevArr<u32> pa(N);
+        psi_scatter_kernel<<<nblocks_for(N), 256>>>(d, pa.p);
         stage("psi");
-        fold_kmers_kernel<<<nblocks_for(N), 256>>>(N, psi.p, (u32)counts[1], (u32)counts[2], (u32)counts[3], k, kmers.p, validbits.p);
-        stage("k-mers of the SA rows");
-        nl += 2;
+        static const bool walk = std::getenv("FMSI_GPU_FOLD_WALK") != nullptr;  // the k-1 step walk per row (A/B switch)
+        if (walk) {
+            fold_kmers_kernel<<<nblocks_for(N), 256>>>(N, pa.p, c1, c2, c3, k, kmers.p, validbits.p);
+            stage("k-mers of the SA rows");
+            nl += 2;
+        } else {
+            fold_sticky_kernel<<<1, 32>>>(pa.p);
+            // K_l lives in the upper / lower half of the (not yet used) kmers array, P_l in pa / pb
+            DevArr<u32> pb(N);
+            u32 *ka = reinterpret_cast<u32 *>(kmers.p), *kb = ka + N;
+            const u32 *pin = pa.p, *kin = nullptr;
+            u32 *pout = pb.p, *kout = ka;
+            for (u32 l = 1; l < 16; l *= 2) {
+                fold_double_kernel<<<nblocks_for(N), 256>>>(N, pin, kin, l, c1, c2, c3, pout, kout);
+                stage("k-mer doubling");
+                pin = pout;
+                kin = kout;
+                pout = pout == pb.p ? pa.p : pb.p;
+                kout = kout == ka ? kb : ka;
+            }
+            // K_16 sits in one half of kmers[]: move it out before the 64-bit k-mers overwrite that array
+            DevArr<u32> k16(N);
+            BCU(cudaMemcpy(k16.p, kin, N * 4, cudaMemcpyDeviceToDevice));
+            fold_double_last_kernel<<<nblocks_for(N), 256>>>(N, pin, k16.p, k, kmers.p);
+            stage("k-mers of the SA rows");
+            fold_valid_fill_kernel<<<nblocks_for((N + 31) / 32), 256>>>(N, validbits.p);
+            fold_valid_clear_kernel<<<1, 32>>>(d, k, validbits.p);
+            stage("valid rows");
+            nl += 9;
+        }
     }
     lap("k-mers of the SA rows");
     DevArr<u32> heads;

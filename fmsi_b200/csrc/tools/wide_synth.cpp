@@ -41,7 +41,8 @@ int main(int argc, char **argv) {
                 const uint64_t valid = N - w * 64 >= 64 ? ~0ull : ((1ull << (N - w * 64)) - 1);
                 ac_gt.w[w] = mix(seed + 4 * w) & valid;
                 lo.w[w] = mix(seed + 4 * w + 1) & valid;
-                mask.w[w] = (mix(seed + 4 * w + 2) | mix(seed * 7 + w)) & valid;                // ~3/4 ones
+                // 63/64 ones: the lookup ids (mask ranks) of the last rows then exceed 2^32 as well
+                mask.w[w] = ~(mix(seed + 4 * w + 2) & mix(seed * 7 + w) & mix(seed * 13 + w) & mix(seed * 17 + w) & mix(seed * 19 + w) & mix(seed * 23 + w)) & valid;
                 klcp.w[w] = (mix(seed + 4 * w + 3) & mix(seed * 11 + w)) & valid;               // ~1/4 ones
             }
         });
