@@ -15,6 +15,7 @@
 // ties remain. For the benchmark's i.i.d. sequences round 1 already resolves everything.
 #pragma once
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <cstdint>
 #include <stdexcept>
@@ -292,12 +293,19 @@ inline void max_scan_inplace(u64 *data, u64 count) {
     BCU(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, data, data, MaxOp(), count));
 }
 
+// Exclusive prefix sums of 32-bit (or narrower) counts, accumulated in 64 bits: cub sums in the input's own type
+// otherwise, and the mask of an index with more than 2^32 rows holds more than 2^32 ones (tests/test_gpu_wide.py).
+template <typename InT>
+struct CastToU64 {
+    __host__ __device__ __forceinline__ u64 operator()(const InT &x) const { return (u64)x; }
+};
 template <typename InT>
 inline void exclusive_sum_u64(const InT *in, u64 *out, u64 count) {
+    thrust::transform_iterator<CastToU64<InT>, const InT *> it(in, CastToU64<InT>());
     size_t tmp_bytes = 0;
-    BCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, count));
+    BCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, out, count));
     DevArr<unsigned char> tmp(tmp_bytes);
-    BCU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, count));
+    BCU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, it, out, count));
 }
 
 // Compact `vals[q]` where flags[q] != 0; returns the number selected.
