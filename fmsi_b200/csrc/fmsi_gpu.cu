@@ -245,30 +245,35 @@ bool fold_ld64() {  // $FMSI_GPU_LD64=0: whole-line L2 fills for bucket probes (
 }
 
 template <int MODE, int OUT, int STRANDS, bool PAY64, bool LD64>
-int launch_fold_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
+int launch_fold_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const ReadSrc &rs) {
     auto kern = fold_query_kernel<MODE, OUT, STRANDS, PAY64, LD64>;
     const int grid = persistent_grid(idx, kern, kQueryBlock);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(idx->fold, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), probe_ctr(idx));
+    kern<<<grid, kQueryBlock, 0, st>>>(idx->fold, kmers, (u64)n, out, ls.ctr, pick_chunk(n, grid, kQueryBlock), probe_ctr(idx), rs);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
 }
 
 template <int MODE, int OUT, int STRANDS>
-int launch_fold(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st) {
+int launch_fold(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const ReadSrc &rs) {
     const bool pay64 = idx->fold.B > 16, ld64 = fold_ld64();
-    if (pay64) return ld64 ? launch_fold_v<MODE, OUT, STRANDS, true, true>(idx, kmers, n, out, ls, st)
-                           : launch_fold_v<MODE, OUT, STRANDS, true, false>(idx, kmers, n, out, ls, st);
-    return ld64 ? launch_fold_v<MODE, OUT, STRANDS, false, true>(idx, kmers, n, out, ls, st)
-                : launch_fold_v<MODE, OUT, STRANDS, false, false>(idx, kmers, n, out, ls, st);
+    if (pay64) return ld64 ? launch_fold_v<MODE, OUT, STRANDS, true, true>(idx, kmers, n, out, ls, st, rs)
+                           : launch_fold_v<MODE, OUT, STRANDS, true, false>(idx, kmers, n, out, ls, st, rs);
+    return ld64 ? launch_fold_v<MODE, OUT, STRANDS, false, true>(idx, kmers, n, out, ls, st, rs)
+                : launch_fold_v<MODE, OUT, STRANDS, false, false>(idx, kmers, n, out, ls, st, rs);
+}
+
+// does the strand-folded dictionary answer this query shape? (then reads can feed it directly: ReadSrc)
+bool fold_answers(const fmsi_gpu_index *idx, int k, int mode, int output) {
+    return !idx->wide && mode != 2 && idx->fold.enabled && (u32)k == idx->fold.k && (output != FMSI_GPU_OUT_ORDERS || idx->fold.ids);
 }
 
 template <int MODE, int OUT, int STRANDS>
 int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmers, size_t n, void *out,
-                   LaunchScratch &ls, cudaStream_t st) {
+                   LaunchScratch &ls, cudaStream_t st, const ReadSrc &rs) {
     if (idx->wide) return launch_query<MODE, OUT, STRANDS, true>(idx, d, kmers, n, out, ls, st);
-    if (idx->fold.enabled && d.k == idx->fold.k && (OUT != K_OUT_ORDERS || idx->fold.ids)) return launch_fold<MODE, OUT, STRANDS>(idx, kmers, n, out, ls, st);
+    if (idx->fold.enabled && d.k == idx->fold.k && (OUT != K_OUT_ORDERS || idx->fold.ids)) return launch_fold<MODE, OUT, STRANDS>(idx, kmers, n, out, ls, st, rs);
     if (idx->dict.enabled && d.k == idx->dict.k && d.t && n < (1ull << 32)) return launch_dict<MODE, OUT, STRANDS>(idx, d, kmers, n, out, ls, st);
     return launch_query<MODE, OUT, STRANDS, false>(idx, d, kmers, n, out, ls, st);
 }
@@ -276,18 +281,19 @@ int launch_query_w(const fmsi_gpu_index *idx, const DevIndex &d, const u64 *kmer
 // mode FMSI_GPU_MODE_GENERAL_ (internal) carries its function in *gf
 constexpr int FMSI_GPU_MODE_GENERAL_ = 2;
 int dispatch_query(const fmsi_gpu_index *idx, const DevIndex &d, int mode, int output, int strands,
-                   const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const GenF *gf = nullptr) {
+                   const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const GenF *gf = nullptr,
+                   const ReadSrc &rs = ReadSrc{nullptr, nullptr, nullptr, 0, 0}) {
     if (mode == FMSI_GPU_MODE_GENERAL_) return launch_general(idx, d, *gf, kmers, n, out, ls, st);
     if (output == FMSI_GPU_OUT_ORDERS) {
-        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
-        return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st, rs);
+        return launch_query_w<K_MODE_OR, K_OUT_ORDERS, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st, rs);
     }
     if (mode == FMSI_GPU_MODE_ALL) {
-        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
-        return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
+        if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st, rs);
+        return launch_query_w<K_MODE_ALL, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st, rs);
     }
-    if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st);
-    return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st);
+    if (strands == FMSI_GPU_STRANDS_BOTH) return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_BOTH>(idx, d, kmers, n, out, ls, st, rs);
+    return launch_query_w<K_MODE_OR, K_OUT_PRESENCE, K_STRANDS_LAZY>(idx, d, kmers, n, out, ls, st, rs);
 }
 
 // cub temp storage of one ExclusiveSum over n u32 counts, and the reads-mode device scratch behind the chunk arrays:
@@ -1463,6 +1469,12 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
             int e = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_slots + r0, r1 - r0, out_span, ls.ctr, q);
             if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)e));
             g_launches.fetch_add(2);
+        } else if (via_kmers && reads_mode && fold_answers(idx, k, mode, output)) {
+            // the dictionary kernel cuts its k-mers out of the reads itself (one chunk per read: d_off = first base,
+            // d_res = first result slot of every read)
+            const ReadSrc rs{d_packed, d_off, d_res, (u64)n_reads, (u64)r0};
+            int e = dispatch_query(idx, d, mode, output, strands, nullptr, r1 - r0, out_span, ls, q, gf, rs);
+            if (e) return e;
         } else if (via_kmers) {
             extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, (u64)n_bases, d_slots);
             CU(cudaGetLastError());

@@ -570,6 +570,44 @@ __device__ __forceinline__ void ld_fold_sector(const void *p, u64 &a, u64 &b, u6
     }
 }
 
+// Queries taken straight from reads (fmsi_gpu_query_reads_packed): query q of the launch is result slot slot0 + q, the
+// k-mer at position slot - rbase[r] of read r = the last read with rbase[r] <= slot. text == nullptr: queries are
+// packed k-mers in an array (the default). Saves the slot -> k-mer array that extract_kmers_kernel writes and this
+// kernel would read back (16 bytes per k-mer of traffic, against 42 algorithmic ones).
+struct ReadSrc {
+    const u64 *text;   // 2-bit packed text
+    const u64 *roff;   // [n_reads + 1] first base of every read
+    const u64 *rbase;  // [n_reads] first result slot of every read (non-decreasing; equal for reads shorter than k)
+    u64 n_reads;
+    u64 slot0;
+};
+// read of `slot`, searching forward from read `from` (rbase[from] <= slot): gallop, then bisect
+__device__ __forceinline__ u64 read_of_slot(const ReadSrc &rs, u64 slot, u64 from) {
+    u64 lo = from, step = 1, hi;
+    for (;;) {  // invariant: rbase[lo] <= slot
+        hi = lo + step;
+        if (hi >= rs.n_reads) {
+            hi = rs.n_reads;
+            break;
+        }
+        if (__ldg(rs.rbase + hi) > slot) break;
+        lo = hi;
+        step <<= 1;
+    }
+    while (hi - lo > 1) {  // rbase[lo] <= slot < rbase[hi] (hi == n_reads counts as +inf)
+        const u64 mid = (lo + hi) >> 1;
+        if (__ldg(rs.rbase + mid) <= slot) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ u64 window64(const u64 *__restrict__ text, u64 s, u32 len) {  // len (<= 32) bases from base s
+    const u64 w0 = __ldg(text + (s >> 5)), w1 = __ldg(text + (s >> 5) + 1);
+    const u32 sh = 2u * ((u32)s & 31u);
+    const u64 v = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+    return v >> (64 - 2 * len);
+}
+
 // value of one orientation's interval: infer_presence<maximized_ones> (fms_index.h:126-144)
 template <int MODE>
 __device__ __forceinline__ int fold_presence(u32 st) {
@@ -581,7 +619,7 @@ __device__ __forceinline__ int fold_presence(u32 st) {
 template <int MODE, int OUT, int STRANDS, bool PAY64, bool LD64>
 __global__ void __launch_bounds__(kQueryBlock)
 fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n, void *__restrict__ out,
-                  unsigned long long *__restrict__ cursor, const u32 chunk, unsigned long long *__restrict__ probe_ctr) {
+                  unsigned long long *__restrict__ cursor, const u32 chunk, unsigned long long *__restrict__ probe_ctr, const ReadSrc rs) {
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -598,6 +636,24 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
     u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
     bool exhausted = false;
     u32 nprobe = 0;  // dependent memory requests issued by this lane (reported when probe_ctr is given)
+    const bool from_reads = rs.text != nullptr;
+    u64 rd_hint = 0;  // from_reads: a read at or before the one of the next tile's first query (warp-uniform)
+    // query q of the launch, q < cend (0 beyond): from the k-mer array, or cut out of its read
+    auto fetch = [&](u64 q) -> u64 {
+        if (q >= cend) return 0ull;
+        if (!from_reads) return kmers[q];
+        const u64 slot = rs.slot0 + q;
+        const u64 r = read_of_slot(rs, slot, rd_hint);
+        return window64(rs.text, __ldg(rs.roff + r) + (slot - __ldg(rs.rbase + r)), k);
+    };
+    // after a tile load: the next tile starts at or after this tile's first query, whose read lane 0 just found
+    auto advance_hint = [&](u64 first_q) {
+        if (!from_reads) return;
+        u64 r = 0;
+        if (lane == 0 && first_q < cend) r = read_of_slot(rs, rs.slot0 + first_q, rd_hint);
+        r = __shfl_sync(FULL, r, 0);
+        if (first_q < cend) rd_hint = r;
+    };
 
     for (;;) {
         // ---------------------------------------------------------------- refill idle lanes
@@ -612,8 +668,12 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
                 } else {
                     wnext = tile_base = c0;
                     cend = (c0 + chunk < n) ? c0 + chunk : n;
-                    bufA = (tile_base + lane < cend) ? kmers[tile_base + lane] : 0ull;
-                    bufB = (tile_base + 32 + lane < cend) ? kmers[tile_base + 32 + lane] : 0ull;
+                    if (from_reads) {  // a new grab may lie anywhere: search from the first read
+                        rd_hint = 0;
+                        advance_hint(tile_base);
+                    }
+                    bufA = fetch(tile_base + lane);
+                    bufB = fetch(tile_base + 32 + lane);
                 }
             }
             if (!exhausted) {
@@ -632,7 +692,8 @@ fold_query_kernel(const FoldView fv, const u64 *__restrict__ kmers, const u64 n,
                 if (wnext - tile_base >= 32) {
                     tile_base += 32;
                     bufA = bufB;
-                    bufB = (tile_base + 32 + lane < cend) ? kmers[tile_base + 32 + lane] : 0ull;
+                    advance_hint(tile_base);
+                    bufB = fetch(tile_base + 32 + lane);
                 }
                 if (take) {
                     active = true;
