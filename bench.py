@@ -1166,14 +1166,24 @@ def main():
         def sharded_run():
             from fmsi_b200 import shard
             q = host_kmer_sample(wl, 1 << 22, 4242)  # same seed on every rank: the same batch
+            times = {}
+
+            def mine(part):
+                t0 = time.perf_counter()
+                r = gi.query_kmers(part, k, fg.MODE_ALL)
+                times["query"] = time.perf_counter() - t0
+                return r
             t0 = time.perf_counter()
-            full = shard.sharded_query_kmers(q, lambda part: gi.query_kmers(part, k, fg.MODE_ALL), rank, world)
-            dt = cx.max_over_ranks(time.perf_counter() - t0)
+            full = shard.sharded_query_kmers(q, mine, rank, world)
+            total = cx.max_over_ranks(time.perf_counter() - t0)
+            query = cx.max_over_ranks(times["query"])
             if rank != 0:
                 return None
             whole = gi.query_kmers(q, k, fg.MODE_ALL)
-            return dict(kmers=int(q.size), ranks=world, equals_single_gpu=bool(np.array_equal(full, whole)), seconds=round(dt, 4),
-                        note="plan_kmers ranges answered by each rank's replica, shards gathered to rank 0 in query order over the bookkeeping group")
+            return dict(kmers=int(q.size), ranks=world, equals_single_gpu=bool(np.array_equal(full, whole)), shard_query_seconds=round(query, 4),
+                        gather_seconds=round(total - query, 4),
+                        note="plan_kmers ranges answered by each rank's replica (pageable host buffers), shards gathered to rank 0 in query order "
+                             "over the gloo bookkeeping group (its first use pays the pairwise connection set-up)")
         sharded = safe("sharded common batch", sharded_run)
 
     # ---- in-process multi-GPU scheduler (fmsi_gpu_pool_*): replicas by device-to-device copy --------------------------
@@ -1184,20 +1194,22 @@ def main():
             pl = fg.Pool(gb, list(range(world)))
             rep_s = time.time() - t0
             n = world * (1 << 24)
-            q = host_kmer_sample(wl, n, 555)
-            out = pl.query_kmers(q, k, fg.MODE_ALL)  # warm-up (buffers)
+            q = torch.from_numpy(host_kmer_sample(wl, n, 555).view(np.int64)).pin_memory().numpy().view(np.uint64)  # pinned, like the e2e arm
+            out = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+            pl.query_kmers(q, k, fg.MODE_ALL, out=out)  # warm-up (buffers)
             t0 = time.perf_counter()
             reps = 3
             for _ in range(reps):
-                out = pl.query_kmers(q, k, fg.MODE_ALL)
+                pl.query_kmers(q, k, fg.MODE_ALL, out=out)
             dt = (time.perf_counter() - t0) / reps
             single = gb.query_kmers(q[:1 << 20], k, fg.MODE_ALL)
             ok = bool(np.array_equal(single, out[:1 << 20]))
             pl.close()
             gb.close()
             return dict(members=world, replicate_s=round(rep_s, 2), index_bytes=int(gb.hbm_bytes), value=n / dt, unit=UNIT, kmers_per_call=n,
-                        equals_single_index=ok, note="one process, replicas of the backward-search index copied device to device "
-                        "(cudaMemcpyPeer), host buffers split into contiguous ranges, one host thread per member")
+                        h2d_gbs_aggregate=round(n * 8 / dt / 1e9, 1), equals_single_index=ok,
+                        note="one process, replicas of the backward-search index copied device to device (cudaMemcpyPeer) instead of N index "
+                             "builds, pinned host buffers split into contiguous ranges, one host thread per member; 8 B per k-mer over the host links")
         cx.barrier()
         if rank == 0 and os.path.exists(wl["prefix"] + ".fmsi.misc"):
             pool = safe("pool", pool_run)

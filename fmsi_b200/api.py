@@ -410,11 +410,14 @@ class Pool:
             pass
 
     def query_kmers(self, kmers, k: int | None = None, mode: int = MODE_OR, output: int = OUT_PRESENCE,
-                    strands: int = STRANDS_LAZY) -> np.ndarray:
+                    strands: int = STRANDS_LAZY, out: np.ndarray | None = None) -> np.ndarray:
         kmers = _u64(kmers)
         k = self.primary.k if k is None else k
         dt, shape = result_dtype_shape(output, strands, kmers.size)
-        out = np.empty(shape, dtype=dt)
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        elif out.dtype != dt or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous %s array of shape %s" % (np.dtype(dt).name, shape))
         _check(lib().fmsi_gpu_pool_query_kmers(self._h, mode, output, strands, kmers.ctypes.data, kmers.size, k, out.ctypes.data))
         return out
 

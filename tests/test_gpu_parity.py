@@ -450,14 +450,18 @@ def test_general_demasking_functions_properties(case):
             gi.close()
 
 
-def test_multi_gpu_pool_matches_single_index():
+@pytest.mark.parametrize("tier", ["auto", "backward"])
+def test_multi_gpu_pool_matches_single_index(tier):
     """The scheduler (fmsi_gpu_pool_*): replicas made by device-to-device copy answer contiguous
     shards from their own host threads; results must equal the single-index call, in query order.
-    With one GPU the replicas share it (repeated ordinals), with more they spread over the GPUs."""
+    With one GPU the replicas share it (repeated ordinals), with more they spread over the GPUs.
+    auto: replicas of the strand-folded dictionary (each builds its lookup ids on its first lookup);
+    backward: replicas carry the multi-step rank arrays."""
     d = os.path.join(GOLDEN, "syn_k31_max")
     prefix = os.path.join(d, "ms.fa")
     k = 31
-    gi = fg.Index.load(prefix, use_klcp=True)
+    gi = fg.Index.load(prefix, use_klcp=True, **TIER_KW[tier])
+    assert (gi.multistep == 2) == (tier == "backward")
     ndev = fg.device_count()
     devices = [0, 1 % ndev, 2 % ndev, 0]
     pool = fg.Pool(gi, devices)
