@@ -386,8 +386,14 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
     };
     const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
+    size_t low_free = ~(size_t)0;  // lowest free device memory seen at the stage ends ($FMSI_GPU_TIMING): the build's peak
     auto lap = [&](const char *what) {
-        if (timing) fprintf(stderr, "[fmsi timing] fold build: %s at %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        if (!timing) return;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (free_b < low_free) low_free = free_b;
+        fprintf(stderr, "[fmsi timing] fold build: %s at %.3f s (device memory in use %.1f GB, peak so far %.1f GB)\n", what,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), (total_b - free_b) / 1e9, (total_b - low_free) / 1e9);
     };
     uint64_t nl = 0;
     DevArr<u64> kmers(N);
@@ -422,6 +428,7 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
             BCU(cudaMemcpy(k16.p, kin, N * 4, cudaMemcpyDeviceToDevice));
             fold_double_last_kernel<<<nblocks_for(N), 256>>>(N, pin, k16.p, k, kmers.p);
             stage("k-mers of the SA rows");
+            lap("pointer doubling");
             fold_valid_fill_kernel<<<nblocks_for((N + 31) / 32), 256>>>(N, validbits.p);
             fold_valid_clear_kernel<<<1, 32>>>(d, k, validbits.p);
             stage("valid rows");
@@ -492,6 +499,7 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
                 DevArr<u64> keys_alt(Mp), vals_alt(Mp);
                 radix_sort_pairs(keys, keys_alt, vals, vals_alt, Mp, (int)(2 * k));
                 stage("sort");
+                if (p == 0 || p + 1 == P) lap(p == 0 ? "first pass sorted" : "last pass sorted");
             }
             DevArr<u32> gs(Mp);
             G = fold_select_heads(Mp, gs.p, FoldKeyHead{keys.p});
