@@ -469,51 +469,48 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
         BCU(cudaMemcpy(h_hist.data(), hist.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         nl += 1;
     }
+    // The buffers of a pass are allocated once, for the largest pass, and reused: allocating and freeing ~10 GB per
+    // pass cost more than the sorting itself on boxes where cudaMalloc is slow (first touch of fresh device memory).
+    u64 max_mp = 1, max_nb = 1;
+    for (u32 p = 0; p < P; ++p) {
+        max_mp = std::max<u64>(max_mp, h_hist[p]);
+        max_nb = std::max<u64>(max_nb, fold_pass_begin(p + 1, P, total) - fold_pass_begin(p, P, total));
+    }
+    DevArr<u32> sel(max_mp + 1), gs(max_mp + 1);
+    DevArr<u64> keys(max_mp), vals(max_mp), keys_alt(max_mp), vals_alt(max_mp);
+    DevArr<u64> rows;
+    DevArr<u32> bfirst, bcount, sizes;
+    DevArr<u64> off;
+    if (want_table) {
+        rows.alloc(max_mp + 1);
+        bfirst.alloc(max_nb);
+        bcount.alloc(max_nb);
+        sizes.alloc(max_nb);
+        off.alloc(max_nb + 1);
+    }
     u64 G0 = 0, O0 = 0;
     for (u32 p = 0; p < P; ++p) {
         const u64 x_lo = fold_pass_begin(p, P, total), x_hi = fold_pass_begin(p + 1, P, total), nb = x_hi - x_lo;
-        DevArr<u32> bfirst, bcount;
         if (want_table) {
-            bfirst.alloc(nb);
-            bcount.alloc(nb);
             BCU(cudaMemset(bfirst.p, 0, nb * 4));
             BCU(cudaMemset(bcount.p, 0, nb * 4));
         }
-        DevArr<u64> rows;
-        u64 G = 0;
-        {
-            DevArr<u64> keys, vals;
-            u64 Mp = 0;
-            {
-                DevArr<u32> sel(h_hist[p] + 1);
-                Mp = fold_select_heads(M, sel.p, FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, x_lo, x_hi});
-                stage("runs of the pass");
-                if (Mp != h_hist[p]) throw std::runtime_error("pass histogram and selection disagree");
-                keys.alloc(Mp);
-                vals.alloc(Mp);
-                fold_entries_kernel<<<nblocks_for(Mp), 256>>>(d, kmers.p, heads.p, M, sel.p, Mp, k, keys.p, vals.p);
-                stage("entries");
-                nl += 2;
-            }
-            {
-                DevArr<u64> keys_alt(Mp), vals_alt(Mp);
-                radix_sort_pairs(keys, keys_alt, vals, vals_alt, Mp, (int)(2 * k));
-                stage("sort");
-                if (p == 0 || p + 1 == P) lap(p == 0 ? "first pass sorted" : "last pass sorted");
-            }
-            DevArr<u32> gs(Mp);
-            G = fold_select_heads(Mp, gs.p, FoldKeyHead{keys.p});
-            stage("group heads");
-            if (want_table) rows.alloc(G + 1);
-            fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, B, G0, x_lo, want_table ? rows.p : nullptr,
-                                                      want_ids ? ids.p : nullptr, want_table ? bfirst.p : nullptr, want_table ? bcount.p : nullptr);
-            stage("rows");
-            nl += 3;
-        }
+        const u64 Mp = fold_select_heads(M, sel.p, FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, x_lo, x_hi});
+        stage("runs of the pass");
+        if (Mp != h_hist[p]) throw std::runtime_error("pass histogram and selection disagree");
+        fold_entries_kernel<<<nblocks_for(Mp), 256>>>(d, kmers.p, heads.p, M, sel.p, Mp, k, keys.p, vals.p);
+        stage("entries");
+        radix_sort_pairs(keys, keys_alt, vals, vals_alt, Mp, (int)(2 * k));
+        stage("sort");
+        if (p == 0 || p + 1 == P) lap(p == 0 ? "first pass sorted" : "last pass sorted");
+        const u64 G = fold_select_heads(Mp, gs.p, FoldKeyHead{keys.p});
+        stage("group heads");
+        fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, B, G0, x_lo, want_table ? rows.p : nullptr,
+                                                  want_ids ? ids.p : nullptr, want_table ? bfirst.p : nullptr, want_table ? bcount.p : nullptr);
+        stage("rows");
+        nl += 5;
         if (want_table) {
-            DevArr<u32> sizes(nb);
             fold_ovf_sizes_kernel<<<nblocks_for(nb), 256>>>(bfirst.p, bcount.p, nb, cap, sizes.p);
-            DevArr<u64> off(nb + 1);
             exclusive_sum_u64(sizes.p, off.p, nb);
             u64 last_off = 0;
             u32 last_size = 0;
@@ -531,6 +528,13 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
         }
         G0 += G;
     }
+    sel.release();
+    gs.release();
+    keys.release();
+    vals.release();
+    keys_alt.release();
+    vals_alt.release();
+    rows.release();
     lap("sort passes");
     if (G0 >= (1ull << 32)) throw std::runtime_error("more than 2^32 rows");
     kmers.release();
