@@ -787,22 +787,23 @@ def sha_file(path: str) -> str:
     return h.hexdigest()
 
 
-def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], device: int) -> dict:
+def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], device: int, reads: bool = False) -> dict:
     """The drop-in claim: this repo's `fmsi` binary against the reference binary, whole process (index load included),
-    same FASTA of single-k-mer records, stdout compared byte for byte. The reference is single-threaded, so its run is
-    P concurrent processes over record shards (each loads the index) and the concatenated outputs are compared."""
+    same FASTA (single-k-mer records, or 150-bp reads with 1 % substitutions), stdout compared byte for byte. The
+    reference is single-threaded, so its run is P concurrent processes over record shards (each loads the index) and
+    the concatenated outputs are compared."""
     if not (os.path.exists(OUR_FMSI) and os.path.exists(REF_FMSI)):
         return dict(error="fmsi binaries missing")
     P = os.cpu_count() or 1
     per = (n_records + P - 1) // P
-    q = host_kmer_sample(wl, per * P, seed)
+    q = host_read_sample(wl, per * P, seed) if reads else host_kmer_sample(wl, per * P, seed)
     tmp = tempfile.mkdtemp(prefix="fmsi_cli_")
     try:
         whole = os.path.join(tmp, "all.fa")
         shards = []
         with open(whole, "wb") as fw:
             for p in range(P):
-                blob = synth.packed_to_fasta(q[p * per:(p + 1) * per], wl["k"])
+                blob = reads_to_fasta(q[p * per:(p + 1) * per]) if reads else synth.packed_to_fasta(q[p * per:(p + 1) * per], wl["k"])
                 fw.write(blob)
                 fn = os.path.join(tmp, f"s{p}.fa")
                 with open(fn, "wb") as f:
@@ -836,6 +837,7 @@ def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], 
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     n = per * P
+    kmers_total = n * (READ_LEN - wl["k"] + 1) if reads else n
     stages = {}
     for line in r.stderr.decode(errors="replace").splitlines():  # the CLI's own stage clock ($FMSI_GPU_TIMING)
         if line.startswith("[fmsi timing] index load + replicas:"):
@@ -843,10 +845,11 @@ def cli_like_for_like(wl: dict, n_records: int, seed: int, ref_args: list[str], 
         elif line.startswith("[fmsi timing] total:"):
             stages["total_s"] = float(line.split(":")[1].split()[0])
     if len(stages) == 2:
-        stages["kmers_s_after_load"] = n / max(stages["total_s"] - stages["index_load_s"], 1e-9)
+        stages["kmers_s_after_load"] = kmers_total / max(stages["total_s"] - stages["index_load_s"], 1e-9)
         stages["process_start_and_exit_s"] = round(ours_s - stages["total_s"], 3)
-    return dict(command="fmsi " + " ".join(ref_args), records=n, fasta_bytes=n * (wl["k"] + 4), ours_wall_s=round(ours_s, 3), ours_kmers_s=n / ours_s, ours_stages=stages,
-                reference_wall_s=round(ref_s, 3), reference_kmers_s=n / ref_s, reference_processes=P, speedup=round(ref_s / ours_s, 2),
+    return dict(command="fmsi " + " ".join(ref_args), records=n, kmers=kmers_total, input="150-bp reads, 1% substitutions" if reads else "single k-mer records",
+                ours_wall_s=round(ours_s, 3), ours_kmers_s=kmers_total / ours_s, ours_stages=stages,
+                reference_wall_s=round(ref_s, 3), reference_kmers_s=kmers_total / ref_s, reference_processes=P, speedup=round(ref_s / ours_s, 2),
                 outputs_byte_identical=bool(identical),
                 note="whole-process wall time, index load and CUDA context creation included on our side, one index load per process "
                      "on the reference's; one GPU against P host cores")
@@ -1155,6 +1158,9 @@ def main():
         # ---- like-for-like CLI ---------------------------------------------------------------------------------------
         if want_cpu and args.cli_records > 0:
             cli[name] = safe("cli like-for-like", lambda: cli_like_for_like(wl, args.cli_records, 31337, ["query", "-O"], cx.local_rank))
+            cli[name + "_reads_S"] = safe("cli like-for-like, reads -S", lambda: cli_like_for_like(wl, max(1, args.cli_records // 60), 31339, ["query", "-O", "-S"],
+                                                                                                     cx.local_rank, reads=True))
+            cli[name + "_lookup"] = safe("cli like-for-like, lookup", lambda: cli_like_for_like(wl, max(1, args.cli_records // 3), 31340, ["lookup"], cx.local_rank))
 
     if oi is not None:
         oi.close()
