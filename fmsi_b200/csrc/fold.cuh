@@ -464,7 +464,7 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
     {
         DevArr<unsigned long long> hist(P);
         BCU(cudaMemset(hist.p, 0, P * sizeof(unsigned long long)));
-        fold_pass_hist_kernel<<<nblocks_for(M), 256>>>(FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, 0, total}, M, total, P, hist.p);
+        if (M) fold_pass_hist_kernel<<<nblocks_for(M), 256>>>(FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, 0, total}, M, total, P, hist.p);
         stage("pass histogram");
         BCU(cudaMemcpy(h_hist.data(), hist.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         nl += 1;
@@ -498,15 +498,16 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
         const u64 Mp = fold_select_heads(M, sel.p, FoldRunInPass{kmers.p, validbits.p, heads.p, k, B, x_lo, x_hi});
         stage("runs of the pass");
         if (Mp != h_hist[p]) throw std::runtime_error("pass histogram and selection disagree");
-        fold_entries_kernel<<<nblocks_for(Mp), 256>>>(d, kmers.p, heads.p, M, sel.p, Mp, k, keys.p, vals.p);
+        if (Mp) fold_entries_kernel<<<nblocks_for(Mp), 256>>>(d, kmers.p, heads.p, M, sel.p, Mp, k, keys.p, vals.p);
         stage("entries");
         radix_sort_pairs(keys, keys_alt, vals, vals_alt, Mp, (int)(2 * k));
         stage("sort");
         if (p == 0 || p + 1 == P) lap(p == 0 ? "first pass sorted" : "last pass sorted");
         const u64 G = fold_select_heads(Mp, gs.p, FoldKeyHead{keys.p});
         stage("group heads");
-        fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, B, G0, x_lo, want_table ? rows.p : nullptr,
-                                                  want_ids ? ids.p : nullptr, want_table ? bfirst.p : nullptr, want_table ? bcount.p : nullptr);
+        if (G)
+            fold_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, B, G0, x_lo, want_table ? rows.p : nullptr,
+                                                      want_ids ? ids.p : nullptr, want_table ? bfirst.p : nullptr, want_table ? bcount.p : nullptr);
         stage("rows");
         nl += 5;
         if (want_table) {
