@@ -1191,6 +1191,7 @@ def main():
                 r = gi.query_kmers(part, k, fg.MODE_ALL)
                 times["query"] = time.perf_counter() - t0
                 return r
+            cx.barrier()  # rank 0 comes from checking every rank's parity sample against the oracle
             t0 = time.perf_counter()
             full = shard.sharded_query_kmers(q, mine, rank, world)
             total = cx.max_over_ranks(time.perf_counter() - t0)
@@ -1201,7 +1202,7 @@ def main():
             return dict(kmers=int(q.size), ranks=world, equals_single_gpu=bool(np.array_equal(full, whole)), shard_query_seconds=round(query, 4),
                         gather_seconds=round(total - query, 4),
                         note="plan_kmers ranges answered by each rank's replica (pageable host buffers), shards gathered to rank 0 in query order "
-                             "over the gloo bookkeeping group (its first use pays the pairwise connection set-up)")
+                             "over the gloo bookkeeping group")
         sharded = safe("sharded common batch", sharded_run)
 
     # ---- in-process multi-GPU scheduler (fmsi_gpu_pool_*): replicas by device-to-device copy --------------------------
