@@ -86,6 +86,7 @@ struct fmsi_gpu_index {
     Slot slots[kSlots];
     cudaStream_t aux_stream = nullptr;       // second query stream of pipelined host-mode chunk calls
     std::vector<cudaEvent_t> piece_events;   // "text piece uploaded and packed" events of those calls
+    cudaEvent_t span_done[2] = {nullptr, nullptr};  // "results of the latest span on query stream 0 / 1 are written" (bit-packed output)
     LaunchScratch user;  // scratch for MEM_DEVICE launches
     unsigned long long *d_probes = nullptr;  // fmsi_gpu_count_probes: running total of the kernels' dependent requests
     bool count_probes = false;
@@ -1077,6 +1078,8 @@ int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
         if (p) cudaFree(p);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
     for (cudaEvent_t ev : idx->piece_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : idx->span_done)
+        if (ev) cudaEventDestroy(ev);
     for (auto &s : idx->slots) {
         for (void *p : {s.d_in, s.d_out, s.d_aux, (void *)s.ls.ctr, s.ls.ovf})
             if (p) cudaFree(p);
@@ -1328,7 +1331,11 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     if (via_kmers) aux_need += n_results * 8;
     // Host mode, large ordered inputs: the text goes up in pieces on one stream while the chunks that are complete
     // run (and their results come back) on two others, so H2D, kernels and D2H overlap within the call.
-    const size_t kPiece = (size_t)8 << 20;  // bases per piece (a multiple of 32)
+    static const size_t kPiece = [] {  // bases per piece (a multiple of 32); $FMSI_GPU_PIECE_MIB: design experiment switch
+        const char *e = std::getenv("FMSI_GPU_PIECE_MIB");
+        const size_t mib = e ? (size_t)std::atoll(e) : 0;
+        return (mib >= 1 && mib <= 1024 ? mib : 8) << 20;
+    }();
     const bool pipelined = on_host && n_bases > 2 * kPiece;
     // reads mode: the streaming kernel takes chunks of <= 64 k-mers, every other path one chunk per read
     const size_t n_reads = reads_mode ? n_chunks : 0;
@@ -1460,6 +1467,29 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         if (on_host) CU(cudaMemcpyAsync(results, d_bits, (n_results + 7) / 8, cudaMemcpyDeviceToHost, q));
         return FMSI_GPU_OK;
     };
+    // Bit-packed output of a pipelined call: once span `span` (results [.., r1)) has been launched on q, every result byte
+    // that is complete — [bits_done, r1 / 8), all of them after the last span — is packed and sent back on q, behind
+    // that span's kernel, so only the last span's bits return after the queries. The first byte may hold results of
+    // the previous span, which ran on the other query stream: q waits for that span's event.
+    size_t bits_done = 0;
+    auto span_bits = [&](size_t span, size_t r1, bool last_span, cudaStream_t q) -> int {
+        if (!bits) return FMSI_GPU_OK;
+        for (int e = 0; e < 2; ++e)
+            if (!idx->span_done[e]) CU(cudaEventCreateWithFlags(&idx->span_done[e], cudaEventDisableTiming));
+        const size_t byte_hi = last_span ? (n_results + 7) / 8 : r1 / 8;
+        if (byte_hi > bits_done) {
+            if (span > 0) CU(cudaStreamWaitEvent(q, idx->span_done[(span - 1) & 1], 0));
+            unsigned char *d_bits = (unsigned char *)d_results + ((n_results + 63) & ~size_t(63));
+            const size_t q0 = bits_done * 8, q1 = std::min(byte_hi * 8, n_results);
+            pack_presence_bits_kernel<<<blocks_for(byte_hi - bits_done), 256, 0, q>>>((const unsigned char *)d_results + q0, (u64)(q1 - q0), d_bits + bits_done);
+            CU(cudaGetLastError());
+            g_launches.fetch_add(1);
+            CU(cudaMemcpyAsync((char *)results + bits_done, d_bits + bits_done, byte_hi - bits_done, cudaMemcpyDeviceToHost, q));
+            bits_done = byte_hi;
+        }
+        CU(cudaEventRecord(idx->span_done[span & 1], q));
+        return FMSI_GPU_OK;
+    };
     auto run_span = [&](size_t c0, size_t c1, size_t r0, size_t r1, cudaStream_t q, LaunchScratch &ls) -> int {
         if (c1 <= c0 || r1 <= r0) return FMSI_GPU_OK;
         void *out_span = (char *)d_results + r0 * rbytes;
@@ -1578,6 +1608,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
             cudaStream_t q = qs[span & 1];
             CU(cudaStreamWaitEvent(q, idx->piece_events[span], 0));
             if ((rc = run_span(c_done, (size_t)rd_C, r_done, (size_t)rd_R, q, *qls[span & 1]))) return rc;
+            if ((rc = span_bits(span, (size_t)rd_R, last && rd_done == n_reads, q))) return rc;
             if (back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
             back_r0 = r_done;
             back_r1 = (size_t)rd_R;
@@ -1610,6 +1641,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         cudaStream_t q = qs[span & 1];
         CU(cudaStreamWaitEvent(q, idx->piece_events[span], 0));
         if ((rc = run_span(c_done, c1, r_done, r1, q, *qls[span & 1]))) return rc;
+        if ((rc = span_bits(span, r1, last && c1 == n_chunks, q))) return rc;
         if (back_q && (rc = copy_back(back_r0, back_r1, back_q))) return rc;
         back_r0 = r_done;
         back_r1 = r1;
@@ -1629,7 +1661,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
         fprintf(stderr, "[fmsi trace] chunks call: %zu chunks, %zu results, %zu spans: all enqueued at %.0f us (chunk validation %.0f us), drained at %.0f us\n",
                 n_chunks, n_results, span, tr_enq, tr_validate, tr_us());
     if (!ordered) return single_batch();
-    if (bits) {  // every span's byte results are on the device: pack and fetch them
+    if (bits && bits_done < (n_results + 7) / 8) {  // (result slots no chunk covers at the end) pack and fetch everything
         if ((rc = finish_bits(st))) return rc;
         CU(cudaStreamSynchronize(st));
     }

@@ -573,6 +573,16 @@ def test_reads_api_matches_chunk_calls(tier):
     for streaming, out in ((True, fg.OUT_PRESENCE), (False, fg.OUT_PRESENCE_BITS), (True, fg.OUT_ORDERS)):
         assert np.array_equal(gi.query_reads(big_reads, k, fg.MODE_ALL if out != fg.OUT_ORDERS else fg.MODE_OR, out, fg.STRANDS_LAZY, streaming),
                               gi.query_chunks(bases, offs, clens, k, fg.MODE_ALL if out != fg.OUT_ORDERS else fg.MODE_OR, out, fg.STRANDS_LAZY, streaming)), (tier, "big", streaming, out)
+    # pipelined again with 121 k-mers per read: the result spans of the text pieces then end in the middle of a byte of
+    # the bit-packed output, which is packed and returned span by span
+    odd = synth.read_queries(ms_codes, 151, 120_000, 22)
+    odd_reads = [synth.codes_to_ascii(r) for r in odd]
+    bases, offs, clens = _chunks_of(list(odd), k, 64)
+    assert len(bases) > (16 << 20)
+    by = gi.query_chunks(bases, offs, clens, k, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY, True)
+    assert np.array_equal(gi.query_reads(odd_reads, k, fg.MODE_ALL, fg.OUT_PRESENCE_BITS, fg.STRANDS_LAZY, True), np.packbits(by, bitorder="little")), (tier, "odd reads")
+    assert np.array_equal(gi.query_chunks(bases, offs, clens, k, fg.MODE_ALL, fg.OUT_PRESENCE_BITS, fg.STRANDS_LAZY, False, packed=True),
+                          np.packbits(by, bitorder="little")), (tier, "odd chunks")
     # malformed calls
     L_ = fg.lib()
     words = fg.pack_text(np.frombuffer(b"ACGT" * 50, dtype=np.uint8))
