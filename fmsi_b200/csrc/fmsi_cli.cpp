@@ -919,6 +919,11 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     cfg.streaming = has_klcp;
     cfg.orders = output_orders;
     cfg.mode = f_name == "all" ? fmsi::QueryMode::All : fmsi::QueryMode::Or;
+    // Plain `fmsi query` (`or` mode, presence output) prints 1 iff either strand has an ON occurrence, whichever strand the
+    // predictor tries first (fms_index.h:289-293, :212-233): no replay is needed, one value per k-mer comes back.
+    // `-O`, `lookup` and their `-S` forms stop at the first decided strand and do depend on the predictor's history
+    // (SURVEY 8a row P): they get both strands and the exact replay unless $FMSI_GPU_STRANDS=lazy says the index makes it moot.
+    cfg.lazy = !output_orders && f_name == "or";
     if (const char *e = std::getenv("FMSI_GPU_STRANDS")) cfg.lazy = std::string(e) == "lazy";
     if (general) {  // mask_function(), src/functions.h:23-57
         cfg.general = true;

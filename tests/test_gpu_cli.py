@@ -74,6 +74,19 @@ def test_cli_lazy_mode_where_order_independent(case):
         assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}"
 
 
+@pytest.mark.parametrize("case", ["quirks_k3", "quirks_k3_nonmax", "syn_k9_min", "syn_k31_min"])
+def test_cli_or_mode_needs_no_replay_but_can_do_it(case):
+    """Plain `fmsi query` [-S] prints the OR over both strands whatever the predictor says, so the CLI asks for one value
+    per k-mer by default (test_cli_matches_reference_outputs covers that on every case); with FMSI_GPU_STRANDS=both it takes
+    both strands and replays the predictor as for `-O` / `lookup` — the output must be the same reference bytes."""
+    d = os.path.join(GOLDEN, case)
+    cmds = [c for c in json.load(open(os.path.join(d, "meta.json")))["cmds"] if c in ("query", "query_S")]
+    runs = run_many([ARGS[cmd] + ["-q", os.path.join(d, "q.fa"), os.path.join(d, "ms.fa")] for cmd in cmds], env={"FMSI_GPU_STRANDS": "both"})
+    for cmd, r in zip(cmds, runs):
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == open(os.path.join(d, f"exp_{cmd}.txt"), "rb").read(), f"{case}/{cmd}"
+
+
 def test_cli_small_batches_stdin_gzip_and_k_flag(tmp_path):
     d = os.path.join(GOLDEN, "syn_k9_max")
     want = open(os.path.join(d, "exp_lookup_S.txt"), "rb").read()
