@@ -593,6 +593,7 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     if (const char *e = std::getenv("FMSI_GPU_FOLD_IDS")) idx->fold_ids_policy = std::atoi(e);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
+    if (const char *e = std::getenv("FMSI_GPU_FREE_CAP")) free_b = std::min<size_t>(free_b, (size_t)std::atoll(e));  // test hook: a busier GPU
 
     // Dictionary tiers: narrow indexes with k <= 32. Bucket depth = the largest t <= min(k, 15) with
     // 4^t <= 4N (on average at most ~4 and at least ~0.25 rows per bucket).

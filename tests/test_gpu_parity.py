@@ -18,6 +18,7 @@ from fmsi_b200 import synth
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("oracle_built")]
 
 L = "ACGT"
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def pack(s: str) -> int:
@@ -281,6 +282,21 @@ def test_fold_lookup_ids_are_built_on_demand():
         gi.close()
     assert sizes[0] == sizes[1] > sizes[-1]
     oi.close()
+
+
+def test_auto_tier_falls_back_loudly_when_memory_is_short():
+    """`dict = auto` takes the fastest tier that fits in the free device memory. When that is not the one-probe dictionary the
+    caller must be able to see it: a note on stderr, and fmsi_gpu_index_info.dict (round 1 fell back silently — an 11 x cliff
+    on a shared GPU). $FMSI_GPU_FREE_CAP stands in for a GPU that is mostly taken."""
+    import sys
+    prefix = os.path.join(GOLDEN, "syn_k31_max", "ms.fa")
+    code = ("import sys; sys.path.insert(0, %r); import fmsi_b200 as fg; gi = fg.Index.load(%r, use_klcp=False); "
+            "print(gi.dict_kind, gi.multistep); import numpy as np; print(int(gi.query_kmers(np.zeros(3, np.uint64), 31).sum()))" % (ROOT_DIR, prefix))
+    plenty = subprocess.run([sys.executable, "-c", code], capture_output=True)
+    assert plenty.returncode == 0 and plenty.stdout.split()[0] == b"2" and b"does not fit" not in plenty.stderr
+    short = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, FMSI_GPU_FREE_CAP=str(70 << 20)))
+    assert short.returncode == 0, short.stderr.decode()
+    assert short.stdout.split()[0] in (b"0", b"1") and b"strand-folded dictionary does not fit" in short.stderr
 
 
 def _chunks_of(seq_codes_list, k, max_kmers):
