@@ -25,7 +25,6 @@ constexpr uint32_t kMultiRows = 224;
 struct DevIndex {
     const RankBlock *rank;
     const AuxBlock *aux;
-    const char *rx;           // streaming copy: block b = 64 bytes {RankBlock, AuxBlock} side by side (null: not built)
     const MultiBlock *multi;  // [4^m][multi_nblk], x-major; null when the tier is not built
     u32 multi_m;              // bases per multi-step probe (0 = off, else 2 or 3)
     u32 multi_nblk;           // N / 224 + 1

@@ -75,8 +75,6 @@ struct fmsi_gpu_index {
     void *d_fbuckets = nullptr, *d_frows = nullptr, *d_fids = nullptr;  // strand-folded dictionary (fold.cuh)
     void *d_multi = nullptr;                                            // multi-step rank arrays (multistep.cuh)
     size_t b_multi = 0;
-    void *d_rx = nullptr;                                               // interleaved {rank, aux} blocks for the streaming kernel
-    size_t b_rx = 0;
     size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
     size_t b_fbuckets = 0, b_frows = 0, b_fids = 0;
     uint64_t hbm_bytes = 0;
@@ -567,33 +565,6 @@ int setup_multistep(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     return FMSI_GPU_OK;
 }
 
-// The streaming kernel's interleaved copy of the rank / aux blocks (stream_kernels.cuh): built when the kLCP array is
-// loaded, no dictionary tier answers streamed chunks, and 64 bytes per block are to spare. $FMSI_GPU_STREAM_BLOCKS=0: off.
-int setup_stream_blocks(fmsi_gpu_index *idx) {
-    const HostIndex &h = idx->meta;
-    if (!h.has_klcp || idx->fold.enabled || idx->dict.enabled) return FMSI_GPU_OK;
-    if (const char *e = std::getenv("FMSI_GPU_STREAM_BLOCKS"))
-        if (std::atoi(e) == 0) return FMSI_GPU_OK;
-    const u64 nblk = (h.n >> 6) + 1;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    if (nblk * 64 > free_b / 4) return FMSI_GPU_OK;
-    void *rx = nullptr;
-    if (cudaMalloc(&rx, nblk * 64) != cudaSuccess) {
-        cudaGetLastError();
-        return FMSI_GPU_OK;
-    }
-    interleave_blocks_kernel<<<blocks_for(nblk * 4), 256>>>((const uint4 *)idx->d_rank, (const uint4 *)idx->d_aux, nblk, (uint4 *)rx);
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    g_launches.fetch_add(1);
-    idx->d_rx = rx;
-    idx->b_rx = nblk * 64;
-    idx->hbm_bytes += idx->b_rx;
-    idx->dev.rx = (const char *)rx;
-    return FMSI_GPU_OK;
-}
-
 // Common tail once d_rank / d_aux / d_sb / d_counts hold the layout: suffix table or dictionary,
 // streams, launch scratch.
 int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
@@ -602,7 +573,6 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     d.rank = reinterpret_cast<const RankBlock *>(idx->d_rank);
     d.aux = reinterpret_cast<const AuxBlock *>(idx->d_aux);
     d.table = nullptr;
-    d.rx = nullptr;
     d.multi = nullptr;
     d.multi_m = 0;
     d.multi_nblk = 0;
@@ -701,7 +671,6 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
                         "using %s — single k-mer queries run several times slower\n",
                 free_b / 1e9, fold_build_peak_bytes(h.n, (u32)auto_depth(), false) / 1e9, idx->dict.enabled ? "the SA-ordered dictionary" : "backward search");
     if ((rc = setup_multistep(idx, opts))) return rc;
-    if ((rc = setup_stream_blocks(idx))) return rc;
     return alloc_slots(idx);
 }
 
@@ -1106,7 +1075,7 @@ int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     if (!idx) return FMSI_GPU_OK;
     cudaSetDevice(idx->device);
     for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, idx->d_fbuckets, idx->d_frows, idx->d_fids,
-                    idx->d_multi, idx->d_rx, idx->d_user_bytes, (void *)idx->d_probes, (void *)idx->user.ctr, idx->user.ovf})
+                    idx->d_multi, idx->d_user_bytes, (void *)idx->d_probes, (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
     for (cudaEvent_t ev : idx->piece_events) cudaEventDestroy(ev);
@@ -1801,7 +1770,6 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->b_sb = src->b_sb;
     r->b_rows = src->b_rows;
     r->b_multi = src->b_multi;
-    r->b_rx = src->b_rx;
     auto bail = [&](int code) {
         fmsi_gpu_index_free(r.release());
         return code;
@@ -1815,14 +1783,12 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
         (rc = replicate_array(&r->d_fbuckets, dev, src->d_fbuckets, src->device, src->b_fbuckets)) ||
         (rc = replicate_array(&r->d_frows, dev, src->d_frows, src->device, src->b_frows)) ||
         (rc = replicate_array(&r->d_fids, dev, src->d_fids, src->device, src->b_fids)) ||
-        (rc = replicate_array(&r->d_multi, dev, src->d_multi, src->device, src->b_multi)) ||
-        (rc = replicate_array(&r->d_rx, dev, src->d_rx, src->device, src->b_rx)))
+        (rc = replicate_array(&r->d_multi, dev, src->d_multi, src->device, src->b_multi)))
         return bail(rc);
     r->dev.rank = reinterpret_cast<const RankBlock *>(r->d_rank);
     r->dev.aux = reinterpret_cast<const AuxBlock *>(r->d_aux);
     r->dev.table = r->d_table;
     r->dev.multi = reinterpret_cast<const MultiBlock *>(r->d_multi);
-    r->dev.rx = reinterpret_cast<const char *>(r->d_rx);
     r->dev.sb_base = reinterpret_cast<const u64 *>(r->d_sb);
     r->dict.rows = reinterpret_cast<const u64 *>(r->d_rows);
     r->fold.buckets = r->d_fbuckets;

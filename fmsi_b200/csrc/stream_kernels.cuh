@@ -153,16 +153,6 @@ __global__ void extract_kmers_kernel(const u64 *__restrict__ packed, const u64 *
                      [&](u64 slot) { kmers[slot] = 0; });
 }
 
-// {RankBlock, AuxBlock} of every block side by side, 64 bytes per block: the streaming kernel's copy of the index (3 % of
-// what the dictionary tier takes). One thread per 16 bytes.
-__global__ void interleave_blocks_kernel(const uint4 *__restrict__ rank, const uint4 *__restrict__ aux, const u64 nblk, uint4 *__restrict__ rx) {
-    const u64 q = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // 4 x 16 B per block
-    if (q >= nblk * 4) return;
-    const u64 b = q >> 2;
-    const u32 part = (u32)q & 3u;
-    rx[b * 4 + part] = part < 2 ? rank[b * 2 + part] : aux[b * 2 + (part - 2)];
-}
-
 // Reads -> chunks, on the device (fmsi_gpu_query_reads_packed): read r = bases [roff[r], roff[r+1]) yields
 // nk = max(0, len - k + 1) results, cut into chunks of at most `max_kmers` k-mers overlapping by k-1 (the streaming
 // kernel's limit), or one chunk per read when max_kmers == 0 (the single-query kernels take chunks of any length; a read
@@ -325,16 +315,8 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 n_base
         } else {
             bi = (u64)i >> 6;
             bj = isM ? (((u64)j - 1) >> 6) : ((u64)j >> 6);
-            if (d.rx) {
-                // interleaved copy: the LF-step that follows a mask / kLCP probe usually lands in the same 64-row block,
-                // whose rank sector came in with the aux sector's 64-byte fill — an L2 hit instead of a DRAM activate
-                const u32 sub = isS ? 0u : 32u;
-                pa = d.rx + (bi << 6) + sub;
-                pb = d.rx + (bj << 6) + sub;
-            } else {
-                pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
-                pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
-            }
+            pa = isS ? (const void *)(d.rank + bi) : (const void *)(d.aux + bi);
+            pb = isS ? (const void *)(d.rank + bj) : (const void *)(d.aux + bj);
         }
         const bool two = (isS || (isM && (need_j || will_cont))) && (bj != bi);
         u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
