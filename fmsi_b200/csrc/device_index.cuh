@@ -21,13 +21,22 @@ struct alignas(32) MultiBlock {
 };
 static_assert(sizeof(MultiBlock) == 32, "one sector");
 constexpr uint32_t kMultiRows = 224;
+// The same sector for indexes of 2^32 rows and more: a 64-bit absolute counter leaves 192 rows per sector.
+struct alignas(32) MultiBlockWide {
+    uint64_t cnt;
+    uint32_t bits[6];
+};
+static_assert(sizeof(MultiBlockWide) == 32, "one sector");
+constexpr uint32_t kMultiRowsWide = 192;
+template <bool WIDE> struct MultiGeom { static constexpr uint32_t rows = kMultiRows, hdr = 1; };
+template <> struct MultiGeom<true> { static constexpr uint32_t rows = kMultiRowsWide, hdr = 2; };
 
 struct DevIndex {
     const RankBlock *rank;
     const AuxBlock *aux;
-    const MultiBlock *multi;  // [4^m][multi_nblk], x-major; null when the tier is not built
+    const MultiBlock *multi;  // [4^m][multi_nblk], x-major; null when the tier is not built (MultiBlockWide sectors when wide)
     u32 multi_m;              // bases per multi-step probe (0 = off, else 2 or 3)
-    u32 multi_nblk;           // N / 224 + 1
+    u32 multi_nblk;           // N / 224 + 1 (wide: N / 192 + 1)
     const void *table;    // 4^t entries, 1 << tshift bytes apart, each starting with {i, j}: u32 pairs
                           // (narrow; 32-byte dictionary buckets when tshift == 5) or u64 pairs (wide)
     const u64 *sb_base;   // [n_superblocks][4]
@@ -114,6 +123,23 @@ __device__ __forceinline__ u32 popc_upto32(u32 w, int n) {
 __device__ __forceinline__ u32 lf_multi(u64 a, u64 b, u64 c, u64 d, u32 off) {
     const int o = (int)off;
     return (u32)a + popc_upto32((u32)(a >> 32), o) + popc_upto64(b, o - 32) + popc_upto64(c, o - 96) + popc_upto64(d, o - 160);
+}
+
+// the wide sector: a = cnt (64 bits), b..d = 192 bits
+__device__ __forceinline__ u64 lf_multi_wide(u64 a, u64 b, u64 c, u64 d, u32 off) {
+    const int o = (int)off;
+    return a + (u64)(popc_upto64(b, o) + popc_upto64(c, o - 64) + popc_upto64(d, o - 128));
+}
+template <bool WIDE>
+__device__ __forceinline__ typename PosT<WIDE>::type lf_multi_t(u64 a, u64 b, u64 c, u64 d, u32 off) {
+    if (WIDE) return (typename PosT<WIDE>::type)lf_multi_wide(a, b, c, d, off);
+    return (typename PosT<WIDE>::type)lf_multi(a, b, c, d, off);
+}
+// block / offset of SA row i in a multi-step array
+template <bool WIDE>
+__device__ __forceinline__ u64 multi_block_of(typename PosT<WIDE>::type i) {
+    if (WIDE) return (u64)i / MultiGeom<true>::rows;
+    return (u64)((u32)i / MultiGeom<false>::rows);
 }
 
 // 2-bit reverse complement of a packed k-mer (first base in the highest used bits).

@@ -524,32 +524,34 @@ int alloc_slots(fmsi_gpu_index *idx) {
 }
 
 // Multi-step rank arrays for the backward-search kernels (multistep.cuh). opts->multistep / $FMSI_GPU_MULTISTEP:
-// 0 = off, 2 / 3 = bases per probe, -1 = auto: 2 for narrow indexes when no dictionary tier is resident (the
-// dictionary tiers answer single k-mers themselves) and the arrays fit in a quarter of the free memory.
+// 0 = off, 2 / 3 = bases per probe, -1 = auto: 2 when no dictionary tier is resident (the dictionary tiers answer
+// single k-mers themselves) and the arrays fit in a quarter of the free memory. Wide indexes take the 64-bit-counter
+// sectors (192 rows each).
 int setup_multistep(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     int want = opts ? opts->multistep : -1;
     if (const char *e = std::getenv("FMSI_GPU_MULTISTEP")) want = std::atoi(e);
     if (want == 0) return FMSI_GPU_OK;
     if (want != -1 && want != 2 && want != 3) return fail(FMSI_GPU_ERR_ARG, "multistep must be -1, 0, 2 or 3");
     const HostIndex &h = idx->meta;
-    const bool narrow = !idx->wide && h.n < (1ull << 32) - 256;
-    if (!narrow) return FMSI_GPU_OK;  // wide indexes keep single steps
+    // a narrow layout holds u32 positions and counters: keep clear of 2^32 (the loader switches to wide well before)
+    if (!idx->wide && h.n >= (1ull << 32) - 256) return FMSI_GPU_OK;
+    const bool wide = idx->wide;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     u32 m = 2;
     if (want == -1) {
         if (idx->fold.enabled || idx->dict.enabled) return FMSI_GPU_OK;
-        if (multi_bytes(h.n, 2) + multi_build_scratch_bytes(h.n, 2) > free_b / 4) return FMSI_GPU_OK;
+        if (multi_bytes(h.n, 2, wide) + multi_build_scratch_bytes(h.n, 2, wide) > free_b / 4) return FMSI_GPU_OK;
     } else {
         m = (u32)want;
-        if (multi_bytes(h.n, m) + multi_build_scratch_bytes(h.n, m) > free_b - free_b / 16)
+        if (multi_bytes(h.n, m, wide) + multi_build_scratch_bytes(h.n, m, wide) > free_b - free_b / 16)
             return fail(FMSI_GPU_ERR_NOMEM, "multi-step rank arrays do not fit in device memory");
     }
     MultiBlock *multi = nullptr;
     u32 nblk = 0;
     uint64_t launches = 0;
     try {
-        build_multi_on_device(idx->dev, m, &multi, &nblk, &launches);
+        build_multi_on_device(idx->dev, wide, m, &multi, &nblk, &launches);
     } catch (const std::exception &e) {
         const bool oom = cudaGetLastError() == cudaErrorMemoryAllocation || std::string(e.what()).find("out of memory") != std::string::npos;
         if (oom && want == -1) return FMSI_GPU_OK;
@@ -557,7 +559,7 @@ int setup_multistep(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     }
     g_launches.fetch_add(launches);
     idx->d_multi = multi;
-    idx->b_multi = multi_bytes(h.n, m);
+    idx->b_multi = multi_bytes(h.n, m, wide);
     idx->hbm_bytes += idx->b_multi;
     idx->dev.multi = multi;
     idx->dev.multi_m = m;

@@ -65,7 +65,7 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
     const u32 t = d.t, k = d.k;  // t <= 16 < 32 < k
     const u64 tmask = t ? ((1ull << (2 * t)) - 1ull) : 0ull;
     const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
-    const u32 mm = WIDE ? 0u : d.multi_m;
+    const u32 mm = d.multi_m;
     const u64 xmask = (1ull << (2 * mm)) - 1ull;
 
     // lane state
@@ -162,12 +162,12 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
         const bool isS = active && phase == PH_STEP;
         const bool isM = active && phase == PH_MASK;
         // multi-step probe (multistep.cuh) while the register window still holds mm bases
-        const bool isX = !WIDE && isS && mm && steps >= mm && navail >= mm;
+        const bool isX = isS && mm && steps >= mm && navail >= mm;
         u64 bi, bj;
         const void *pa, *pb;
         if (isX) {
-            bi = (u32)i / kMultiRows;
-            bj = (u32)j / kMultiRows;
+            bi = multi_block_of<WIDE>(i);
+            bj = multi_block_of<WIDE>(j);
             const MultiBlock *base = d.multi + (pat & xmask) * (u64)d.multi_nblk;
             pa = base + bi;
             pb = base + bj;
@@ -202,9 +202,9 @@ long_query_kernel(const DevIndex d, const u64 *__restrict__ text, const u64 *__r
                 b0 = a0; b1 = a1; b2 = a2; b3 = a3;
             }
             if (isX) {
-                const u32 oi = (u32)i - (u32)bi * kMultiRows, oj = (u32)j - (u32)bj * kMultiRows;
-                i = (pos_t)lf_multi(a0, a1, a2, a3, oi);
-                j = (pos_t)lf_multi(b0, b1, b2, b3, oj);
+                const u32 oi = (u32)((u64)i - bi * MultiGeom<WIDE>::rows), oj = (u32)((u64)j - bj * MultiGeom<WIDE>::rows);
+                i = lf_multi_t<WIDE>(a0, a1, a2, a3, oi);
+                j = lf_multi_t<WIDE>(b0, b1, b2, b3, oj);
                 pat >>= 2 * mm;
                 navail -= mm;
                 steps -= mm;

@@ -203,7 +203,7 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 n_base
     const u32 t = d.t, k = d.k;
     const u64 tmask = t ? ((t >= 32) ? ~0ull : ((1ull << (2 * t)) - 1ull)) : 0ull;
     const bool need_j = !(OUT == K_OUT_PRESENCE && MODE == K_MODE_ALL);
-    const u32 mm = WIDE ? 0u : d.multi_m;
+    const u32 mm = d.multi_m;
     const u64 xmask = (1ull << (2 * mm)) - 1ull;
 
     bool active = false;
@@ -303,12 +303,12 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 n_base
         }
         // a fresh search (after a miss) takes multi-step probes like a single query (multistep.cuh); the one
         // step that continues a neighbour's interval is a plain LF-step
-        const bool isX = !WIDE && isS && mm && steps >= mm;
+        const bool isX = isS && mm && steps >= mm;
         u64 bi, bj;
         const void *pa, *pb;
         if (isX) {
-            bi = (u32)i / kMultiRows;
-            bj = (u32)j / kMultiRows;
+            bi = multi_block_of<WIDE>(i);
+            bj = multi_block_of<WIDE>(j);
             const MultiBlock *base = d.multi + (pat & xmask) * (u64)d.multi_nblk;
             pa = base + bi;
             pb = base + bj;
@@ -344,9 +344,9 @@ stream_kernel(const DevIndex d, const u64 *__restrict__ packed, const u64 n_base
                 b0 = a0; b1 = a1; b2 = a2; b3 = a3;
             }
             if (isX) {
-                const u32 oi = (u32)i - (u32)bi * kMultiRows, oj = (u32)j - (u32)bj * kMultiRows;
-                i = (pos_t)lf_multi(a0, a1, a2, a3, oi);
-                j = (pos_t)lf_multi(b0, b1, b2, b3, oj);
+                const u32 oi = (u32)((u64)i - bi * MultiGeom<WIDE>::rows), oj = (u32)((u64)j - bj * MultiGeom<WIDE>::rows);
+                i = lf_multi_t<WIDE>(a0, a1, a2, a3, oi);
+                j = lf_multi_t<WIDE>(b0, b1, b2, b3, oj);
                 pat >>= 2 * mm;
                 steps -= mm;
             } else {

@@ -74,7 +74,8 @@ typedef struct {
                             * 2 = strand-folded dictionary (one probe per k-mer) */
     int32_t multistep;     /* multi-step rank arrays of the backward-search kernels (m LF-steps per memory request):
                             * -1 = auto (2 when no dictionary tier is resident and they fit), 0 = off, 2 or 3 = bases
-                            * per probe (2.3 / 9.1 bytes of device memory per BWT position) */
+                            * per probe (2.3 / 9.1 bytes of device memory per BWT position; 2.7 / 10.7 for indexes of
+                            * 2^32 positions and more, whose sectors carry a 64-bit counter) */
     int32_t fold_ids;      /* lookup ids of the strand-folded dictionary (8 bytes per distinct k-mer, read only by OUT_ORDERS
                             * queries): 0 = built on the first lookup, 1 = built with the tier, -1 = never (lookups then run
                             * on the backward-search kernels) */

@@ -150,9 +150,9 @@ def test_wide_layout_at_100mbp(tmp_path):
             ref[(mode, out, strands, "S")] = narrow.query_chunks(bases, offs, lens, k, mode, out, strands, True)
         assert np.array_equal(ref[(mode, out, fg.STRANDS_LAZY)][:len(sample)].astype(np.int64), oi.query_packed(sample, k, omode, oord))
     narrow.close()
-    for shift in (10, 16):
-        wide = fg.Index.load(prefix, use_klcp=True, sb_shift_log2=shift)
-        assert wide.wide and not wide.dict and wide.multistep == 0
+    for shift, ms in ((10, -1), (16, 3), (12, 0)):  # multi-step sectors of the wide layout: auto (2 bases per probe), 3, off
+        wide = fg.Index.load(prefix, use_klcp=True, sb_shift_log2=shift, multistep=ms)
+        assert wide.wide and not wide.dict and wide.multistep == {-1: 2}.get(ms, ms)
         for mode, out, omode, oord in combos:
             for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
                 assert np.array_equal(wide.query_kmers(kmers, k, mode, out, strands), ref[(mode, out, strands)]), (shift, mode, out, strands)

@@ -70,7 +70,9 @@ def test_unit_goldens_on_device(t):
 
 
 TIER_KW = {"auto": {}, "backward": {"dict": 0}, "backward_t0": {"dict": 0, "prefix_t": 0}, "backward_ms0": {"dict": 0, "multistep": 0},
-           "backward_ms3": {"dict": 0, "multistep": 3}, "backward_t0_ms2": {"dict": 0, "prefix_t": 0, "multistep": 2}}
+           "backward_ms3": {"dict": 0, "multistep": 3}, "backward_t0_ms2": {"dict": 0, "prefix_t": 0, "multistep": 2},
+           # the wide layout (N >= 2^32) forced on small indexes: 64-bit positions, multi-step sectors of 192 rows
+           "wide": {"sb_shift_log2": 1, "prefix_t": 1}, "wide_ms3": {"sb_shift_log2": 2, "prefix_t": 0, "multistep": 3}}
 
 
 @pytest.mark.parametrize("tier", list(TIER_KW))
@@ -116,8 +118,8 @@ def _random_kmers(rng, ms_codes, k, n):
 
 
 @pytest.mark.parametrize("case", golden_cases())
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "nodict", "dict_t1", "dict_t3", "dict_auto", "fold_t1", "fold_t3",
-                                     "ms0", "ms2_t0", "ms2_t2", "ms3", "ms3_t1"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "wide_ms0", "wide_ms3_t0", "nodict", "dict_t1", "dict_t3", "dict_auto", "fold_t1",
+                                     "fold_t3", "ms0", "ms2_t0", "ms2_t2", "ms3", "ms3_t1"])
 def test_device_matches_oracle(case, variant):
     d = os.path.join(GOLDEN, case)
     meta = json.load(open(os.path.join(d, "meta.json")))
@@ -126,7 +128,10 @@ def test_device_matches_oracle(case, variant):
     # the ROWS phase and the overflow list -> backward-search fixup launch of dict.cuh. fold_t1 / fold_t3: the
     # same for the strand-folded dictionary (fold.cuh): every bucket is binary-searched in rows[].
     # auto = strand-folded dictionary at the automatic depth; dict_auto = SA-ordered dictionary there.
+    # wide* = the layout of indexes with 2^32 rows and more (64-bit positions, superblock counter bases), forced on small
+    # indexes; its multi-step sectors carry a 64-bit counter and 192 rows (auto = 2 bases per probe, like nodict)
     kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "nodict": {"dict": 0},
+          "wide_ms0": {"sb_shift_log2": 1, "prefix_t": 2, "multistep": 0}, "wide_ms3_t0": {"sb_shift_log2": 2, "prefix_t": 0, "multistep": 3},
           "dict_t1": {"dict": 1, "prefix_t": 1}, "dict_t3": {"dict": 1, "prefix_t": 3}, "dict_auto": {"dict": 1},
           "fold_t1": {"dict": 2, "prefix_t": 1}, "fold_t3": {"dict": 2, "prefix_t": 3},
           # backward search with the multi-step rank arrays (multistep.cuh): off / 2 / 3 bases per probe, at table depths
@@ -140,12 +145,10 @@ def test_device_matches_oracle(case, variant):
     gi = fg.Index.load(prefix, use_klcp=meta["klcp"], **kw)
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.n == oi.n and gi.k == k and gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
-    assert gi.wide == (variant == "wide")
-    assert gi.dict == (variant not in ("t0", "wide", "nodict") and not variant.startswith("ms") and k <= 32)
-    if variant.startswith("ms") or variant == "nodict":
-        assert gi.multistep == {"ms0": 0, "ms3": 3, "ms3_t1": 3}.get(variant, 2)
-    if variant == "wide":
-        assert gi.multistep == 0
+    assert gi.wide == variant.startswith("wide")
+    assert gi.dict == (variant not in ("t0", "nodict") and not variant.startswith(("ms", "wide")) and k <= 32)
+    if variant.startswith(("ms", "wide")) or variant == "nodict":
+        assert gi.multistep == {"ms0": 0, "ms3": 3, "ms3_t1": 3, "wide_ms0": 0, "wide_ms3_t0": 3}.get(variant, 2)
     if gi.dict:  # the tier asked for, unless the payload would not fit a row (k - t > 30: k = 32 at depth 1)
         fold_ok = k - gi.dict_t <= 30
         assert gi.dict_kind == (2 if variant in ("auto", "fold_t1", "fold_t3") and fold_ok else 1)
@@ -317,7 +320,7 @@ def _chunks_of(seq_codes_list, k, max_kmers):
 
 
 @pytest.mark.parametrize("case", ["syn_k31_max", "syn_k31_min", "syn_k9_max", "syn_k9_min", "syn_k5_min", "data_k13", "data_k31", "syn_k32", "quirks_k3_nonmax"])
-@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "backward_ms3"])
+@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "backward_ms3", "wide", "wide_ms3"])
 def test_chunks_streaming_and_single_match_oracle(case, tier):
     """Chunks of text, streamed (-S) and single, LAZY and BOTH strands, all three outputs, against the oracle. With
     `auto` a dictionary tier answers streamed chunks too; the dict = 0 tiers put stream_kernel (query_kmers_streaming,
@@ -366,7 +369,7 @@ def test_chunks_streaming_and_single_match_oracle(case, tier):
 
 
 @pytest.mark.parametrize("case", ["syn_k47_max", "syn_k64_min", "syn_k97_noklcp"])
-@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "ms0", "ms3"])
+@pytest.mark.parametrize("variant", ["auto", "t0", "wide", "wide_ms0", "wide_ms3", "ms0", "ms3"])
 def test_long_k_chunks_match_oracle(case, variant):
     """k > 32 (longk_kernels.cuh): k-mers are searched from the packed text, 32 pattern characters per
     register window. Every mode, LAZY and BOTH strands, with and without `streaming`, chunks of assorted
@@ -375,9 +378,10 @@ def test_long_k_chunks_match_oracle(case, variant):
     meta = json.load(open(os.path.join(d, "meta.json")))
     k = meta["k"]
     prefix = os.path.join(d, "ms.fa")
-    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "ms0": {"multistep": 0}, "ms3": {"multistep": 3}}[variant]
+    kw = {"auto": {}, "t0": {"prefix_t": 0}, "wide": {"sb_shift_log2": 1, "prefix_t": 2}, "ms0": {"multistep": 0}, "ms3": {"multistep": 3},
+          "wide_ms0": {"sb_shift_log2": 1, "prefix_t": 2, "multistep": 0}, "wide_ms3": {"sb_shift_log2": 1, "prefix_t": 1, "multistep": 3}}[variant]
     gi = fg.Index.load(prefix, use_klcp=meta["klcp"], **kw)
-    assert gi.multistep == {"wide": 0, "ms0": 0, "ms3": 3}.get(variant, 2)
+    assert gi.multistep == {"wide_ms0": 0, "ms0": 0, "ms3": 3, "wide_ms3": 3}.get(variant, 2) and gi.wide == variant.startswith("wide")
     oi = OracleIndex.load(prefix, use_klcp=meta["klcp"])
     assert gi.k == k and not gi.dict
     ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])

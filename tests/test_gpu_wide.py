@@ -25,6 +25,13 @@ N_ROWS = (1 << 32) + (1 << 27) + 12345
 K = 31
 
 
+_PREFIX = {}
+
+
+def wide_prefix(gi):
+    return _PREFIX[id(gi)]
+
+
 def lf_walk(oi, row, steps):
     """Characters preceding the suffix of `row`, nearest first, by walking the LF-mapping with the oracle's rank();
     stops at the '$' row. Returns (codes, last row)."""
@@ -61,6 +68,7 @@ def wide(tmp_path_factory):
     subprocess.run([TOOL, prefix, str(N_ROWS), str(K), "7"], check=True, capture_output=True)
     oi = OracleIndex.load(prefix, use_klcp=True)
     gi = fg.Index.load(prefix, use_klcp=True)
+    _PREFIX[id(gi)] = prefix
     yield oi, gi
     gi.close()
     oi.close()
@@ -68,7 +76,7 @@ def wide(tmp_path_factory):
 
 def test_wide_index_shape_and_building_blocks(wide):
     oi, gi = wide
-    assert gi.n == oi.n == N_ROWS and gi.wide and not gi.dict and gi.multistep == 0 and gi.has_klcp
+    assert gi.n == oi.n == N_ROWS and gi.wide and not gi.dict and gi.multistep == 2 and gi.has_klcp  # 64-bit multi-step counters
     assert gi.counts == oi.counts() and gi.dollar_position == oi.dollar()
     assert gi.mask_ones == oi.mask_rank(oi.n) > (1 << 32)
     rng = np.random.default_rng(1)
@@ -164,3 +172,32 @@ def test_wide_index_queries_match_oracle(wide):
     assert gi.query_reads(texts, K, fg.MODE_ALL, fg.OUT_PRESENCE, fg.STRANDS_LAZY, False).mean() > 0.5
     # general (f-MS) mode on the wide layout: 1..inf == or
     assert np.array_equal(gi.query_kmers_general(kmers, "1-1000000", K), gi.query_kmers(kmers, K, fg.MODE_OR))
+
+
+@pytest.mark.parametrize("ms", [0, 3])
+def test_wide_index_single_and_three_steps_per_probe(wide, ms):
+    """The same index with the multi-step arrays off (one LF-step per probe) and with 3 bases per probe (28 GB of
+    192-row sectors at this size): k-mer and streamed answers must equal those of the default load, which the tests above
+    hold against the oracle."""
+    oi, gi = wide
+    rng = np.random.default_rng(3)
+    present = occurring_sequences(oi, rng, 200, K)
+    kmers = np.concatenate([synth.pack_rows(np.stack(present)), synth.revcomp_packed(synth.pack_rows(np.stack(present[:80])), K),
+                            rng.integers(0, 1 << 62, size=200, dtype=np.uint64)])
+    reads = occurring_sequences(oi, rng, 30, 150)
+    for r in range(0, len(reads), 2):
+        reads[r] = synth.revcomp_codes(reads[r])
+    texts = [synth.codes_to_ascii(r) for r in reads]
+    other = fg.Index.load(wide_prefix(gi), use_klcp=True, multistep=ms)
+    try:
+        assert other.wide and other.multistep == ms
+        for mode, out in ((fg.MODE_OR, fg.OUT_PRESENCE), (fg.MODE_ALL, fg.OUT_PRESENCE), (fg.MODE_OR, fg.OUT_ORDERS)):
+            for strands in (fg.STRANDS_LAZY, fg.STRANDS_BOTH):
+                assert np.array_equal(other.query_kmers(kmers, K, mode, out, strands), gi.query_kmers(kmers, K, mode, out, strands)), (ms, mode, out, strands)
+            for streaming in (False, True):
+                assert np.array_equal(other.query_reads(texts, K, mode, out, fg.STRANDS_LAZY, streaming),
+                                      gi.query_reads(texts, K, mode, out, fg.STRANDS_LAZY, streaming)), (ms, mode, out, streaming)
+        want = oi.query_packed(kmers, K, MODE_OR, True)
+        assert other.query_kmers(kmers, K, fg.MODE_OR, fg.OUT_ORDERS).astype(np.int64).tolist() == want.tolist()
+    finally:
+        other.close()
