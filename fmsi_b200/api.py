@@ -40,7 +40,7 @@ class FmsiGpuError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("prefix_t", C.c_int32), ("sb_shift_log2", C.c_int32), ("dict", C.c_int32), ("multistep", C.c_int32),
-                ("fold_ids", C.c_int32), ("reserved32", C.c_int32), ("reserved", C.c_int64 * 4)]
+                ("fold_ids", C.c_int32), ("locality", C.c_int32), ("reserved", C.c_int64 * 4)]
 
 
 class Function(C.Structure):
@@ -60,7 +60,8 @@ class IndexInfo(C.Structure):
         ("n_bwt", C.c_uint64), ("counts", C.c_uint64 * 4), ("dollar_position", C.c_uint64),
         ("mask_ones", C.c_uint64), ("hbm_bytes", C.c_uint64), ("k", C.c_int32), ("has_klcp", C.c_int32),
         ("prefix_t", C.c_int32), ("wide", C.c_int32), ("device", C.c_int32), ("dict", C.c_int32),
-        ("dict_t", C.c_int32), ("multistep", C.c_int32), ("fold_ids", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("dict_t", C.c_int32), ("multistep", C.c_int32), ("fold_ids", C.c_int32), ("locality", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -177,6 +178,7 @@ class Index:
         self.dict_t = int(info.dict_t)
         self.multistep = int(info.multistep)
         self.fold_ids = bool(info.fold_ids)
+        self.locality = int(info.locality)  # minimizer length of the resident minimizer-bucketed dictionary (0 = none)
         self.hbm_bytes = int(info.hbm_bytes)
         self.mask_ones = int(info.mask_ones)
         return self
@@ -184,21 +186,21 @@ class Index:
     # ---- construction -------------------------------------------------------------------------
     @staticmethod
     def load(prefix: str, use_klcp: bool = True, device: int = 0, prefix_t: int = -1, sb_shift_log2: int = 0,
-             dict: int = -1, multistep: int = -1, fold_ids: int = 0) -> "Index":
+             dict: int = -1, multistep: int = -1, fold_ids: int = 0, locality: int = 0) -> "Index":
         """load_index(fn, use_klcp) — reference src/fms_index.h:502."""
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep, fold_ids=fold_ids)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep, fold_ids=fold_ids, locality=locality)
         h = C.c_void_p()
         _check(lib().fmsi_gpu_index_load(os.fsencode(prefix), int(use_klcp), device, C.byref(opts), C.byref(h)))
         return Index(h)
 
     @staticmethod
     def from_bits(ac_gt, ac, gt, mask, counts, dollar_position, klcp=None, k=31, device=0, prefix_t=-1,
-                  sb_shift_log2=0, dict=-1, multistep=-1, fold_ids=0) -> "Index":
+                  sb_shift_log2=0, dict=-1, multistep=-1, fold_ids=0, locality=0) -> "Index":
         """In-memory fixture, the form of tests/fms_index_test.h:10-69."""
         arrs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (ac_gt, ac, gt, mask)]
         kl = np.ascontiguousarray(klcp if klcp is not None else [], dtype=np.uint8)
         cnt = _u64(counts)
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep, fold_ids=fold_ids)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=sb_shift_log2, dict=dict, multistep=multistep, fold_ids=fold_ids, locality=locality)
         h = C.c_void_p()
         _check(lib().fmsi_gpu_index_from_bits(
             _ptr(arrs[0], C.c_uint8), arrs[0].size, _ptr(arrs[1], C.c_uint8), arrs[1].size,
@@ -209,10 +211,10 @@ class Index:
 
     @staticmethod
     def build(ms, k: int, with_klcp: bool = True, device: int = 0, prefix_t: int = -1, n: int | None = None,
-              mem: int = MEM_HOST, dict: int = -1, multistep: int = -1, fold_ids: int = 0) -> "Index":
+              mem: int = MEM_HOST, dict: int = -1, multistep: int = -1, fold_ids: int = 0, locality: int = 0) -> "Index":
         """construct(ms, k, use_klcp) on the GPU (reference src/fms_index.h:397). ms: mask-cased ASCII
         bytes (host) or a raw device pointer (int) with n and mem=MEM_DEVICE."""
-        opts = Options(prefix_t=prefix_t, sb_shift_log2=0, dict=dict, multistep=multistep, fold_ids=fold_ids)
+        opts = Options(prefix_t=prefix_t, sb_shift_log2=0, dict=dict, multistep=multistep, fold_ids=fold_ids, locality=locality)
         h = C.c_void_p()
         if isinstance(ms, int):
             ptr, length = ms, int(n)

@@ -79,6 +79,15 @@ def build_tools(force: bool = False, verbose: bool = True) -> None:
     exe = os.path.join(BIN, "randbw")
     if force or _newer(exe, [src]):
         _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src], verbose)
+    for tool in ("randbw2", "locbw"):  # further design microbenchmarks (profiles/README.md)
+        src = os.path.join(CSRC, "tools", tool + ".cu")
+        exe = os.path.join(BIN, tool)
+        if force or _newer(exe, [src]):
+            _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src], verbose)
+    src = os.path.join(CSRC, "tools", "loc_key_check.cu")  # host-only check of loc.cuh's key function (tests/test_loc_key.py)
+    exe = os.path.join(BIN, "loc_key_check")
+    if force or _newer(exe, [src, os.path.join(CSRC, "loc.cuh"), os.path.join(CSRC, "fold.cuh")]):
+        _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", exe, src], verbose)
     src = os.path.join(CSRC, "tools", "fasta_dump.cpp")  # input-parser test tool (tests/test_fasta_blocks.py)
     exe = os.path.join(BIN, "fasta_dump")
     if force or _newer(exe, [src, os.path.join(CSRC, "fasta_blocks.hpp")]):

@@ -877,6 +877,7 @@ int ms_query(int argc, char *argv[], bool output_orders) {
     opts.prefix_t = -1;
     opts.dict = 0;
     opts.multistep = -1;
+    opts.locality = -1;  // like the dictionary tiers: the host parser cannot feed it fast enough to repay its build
     int rc = fmsi_gpu_index_load(fn.c_str(), has_klcp ? 1 : 0, device, &opts, &idx);
     if (rc == FMSI_GPU_ERR_IO) {
         std::cerr << "ERROR: index not correctly loaded. Ensure that you correctly call `fmsi index` before." << std::endl;

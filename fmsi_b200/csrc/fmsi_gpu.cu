@@ -19,6 +19,7 @@
 #include "device_index.cuh"
 #include "dict.cuh"
 #include "fold.cuh"
+#include "loc.cuh"
 #include "index_build.cuh"
 #include "index_convert.cuh"
 #include "index_layout.hpp"
@@ -74,6 +75,11 @@ struct fmsi_gpu_index {
     void *d_rank = nullptr, *d_aux = nullptr, *d_table = nullptr, *d_sb = nullptr, *d_counts = nullptr, *d_rows = nullptr;
     void *d_fbuckets = nullptr, *d_frows = nullptr, *d_fids = nullptr;  // strand-folded dictionary (fold.cuh)
     void *d_multi = nullptr;                                            // multi-step rank arrays (multistep.cuh)
+    void *d_ldir = nullptr, *d_lrows = nullptr;                         // minimizer-bucketed dictionary (loc.cuh)
+    size_t b_ldir = 0, b_lrows = 0;
+    LocView loc{};
+    int loc_policy = 0;        // fmsi_gpu_options.locality: 0 = on the first large text call, 1 = at load, -1 = never
+    bool loc_failed = false;   // the build did not fit / failed once: text calls stay on the other tiers
     size_t b_multi = 0;
     size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
     size_t b_fbuckets = 0, b_frows = 0, b_fids = 0;
@@ -268,6 +274,29 @@ int launch_fold(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out
 // does the strand-folded dictionary answer this query shape? (then reads can feed it directly: ReadSrc)
 bool fold_answers(const fmsi_gpu_index *idx, int k, int mode, int output) {
     return !idx->wide && mode != 2 && idx->fold.enabled && (u32)k == idx->fold.k && (output != FMSI_GPU_OUT_ORDERS || idx->fold.ids);
+}
+
+// Minimizer-bucketed dictionary (loc.cuh): text-derived queries with presence outputs.
+bool loc_answers(const fmsi_gpu_index *idx, int k, int mode, int output) {
+    return !idx->wide && mode != 2 && idx->loc.enabled && (u32)k == idx->loc.g.k && output == FMSI_GPU_OUT_PRESENCE;
+}
+template <int MODE, int STRANDS>
+int launch_loc_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const ReadSrc &rs) {
+    auto kern = loc_query_kernel<MODE, STRANDS>;
+    const int grid = persistent_grid(idx, kern, kQueryBlock);
+    CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
+    kern<<<grid, kQueryBlock, 0, st>>>(idx->loc, kmers, (u64)n, (unsigned char *)out, ls.ctr, pick_chunk(n, grid, kQueryBlock), probe_ctr(idx), rs);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return FMSI_GPU_OK;
+}
+int launch_loc(const fmsi_gpu_index *idx, int mode, int strands, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st,
+               const ReadSrc &rs) {
+    if (mode == FMSI_GPU_MODE_ALL)
+        return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_ALL, K_STRANDS_BOTH>(idx, kmers, n, out, ls, st, rs)
+                                                : launch_loc_v<K_MODE_ALL, K_STRANDS_LAZY>(idx, kmers, n, out, ls, st, rs);
+    return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_OR, K_STRANDS_BOTH>(idx, kmers, n, out, ls, st, rs)
+                                            : launch_loc_v<K_MODE_OR, K_STRANDS_LAZY>(idx, kmers, n, out, ls, st, rs);
 }
 
 template <int MODE, int OUT, int STRANDS>
@@ -496,6 +525,58 @@ void ensure_fold_ids(fmsi_gpu_index *idx) {
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 }
 
+// The minimizer-bucketed dictionary (loc.cuh) answers k-mers that come out of a text — reads, chunks — at about half a
+// memory request per k-mer, where the strand-folded dictionary needs one. It costs a second copy of the rows (8 bytes per
+// distinct k-mer + 8 bytes per bucket), so unless asked for at load (locality = 1) it is built here, by the first text call
+// that is large enough to pay for the build. Out of memory is not an error: text calls then stay on the other tiers.
+constexpr size_t kLocLazyResults = (size_t)1 << 24;
+void ensure_loc(fmsi_gpu_index *idx, int k, size_t n_results, bool at_load) {
+    if (idx->loc.enabled || idx->loc_failed || idx->loc_policy < 0 || idx->wide) return;
+    const HostIndex &h = idx->meta;
+    if (k != h.k || h.k < 1 || h.k > 32 || h.n >= (1ull << 32) - 256) return;
+    if (!at_load && (idx->loc_policy != 0 || n_results < kLocLazyResults)) return;
+    u32 m = loc_pick_m(h.n, (u32)h.k);
+    if (const char *e = std::getenv("FMSI_GPU_LOC_M")) m = (u32)std::atoi(e);
+    u32 t = 1;
+    while (t < 15 && t < m && (1ull << (2 * (t + 1))) <= h.n) ++t;
+    if (const char *e = std::getenv("FMSI_GPU_LOC_T")) t = (u32)std::atoi(e);
+    if (!loc_fits((u32)h.k, m, t)) {
+        idx->loc_failed = true;
+        return;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || loc_build_peak_bytes(h.n, t) > free_b - free_b / 16) {
+        idx->loc_failed = true;
+        fprintf(stderr, "[fmsi] note: not enough free device memory for the minimizer-bucketed dictionary; reads use the other tiers\n");
+        return;
+    }
+    LocArrays la;
+    uint64_t launches = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    try {
+        build_loc_on_device(idx->dev, h.counts, (u32)h.k, m, t, la, &launches);
+    } catch (const std::exception &e) {
+        cudaGetLastError();
+        idx->loc_failed = true;
+        fprintf(stderr, "[fmsi] note: minimizer-bucketed dictionary not built (%s); reads use the other tiers\n", e.what());
+        return;
+    }
+    g_launches.fetch_add(launches);
+    idx->d_ldir = la.dir;
+    idx->d_lrows = la.rows;
+    idx->b_ldir = (8ull << (2 * t));
+    idx->b_lrows = (la.n_rows + 4) * sizeof(u64);
+    idx->hbm_bytes += idx->b_ldir + idx->b_lrows;
+    idx->loc.dir = la.dir;
+    idx->loc.rows = la.rows;
+    idx->loc.n_rows = la.n_rows;
+    idx->loc.g = loc_geom((u32)h.k, m, t);
+    idx->loc.enabled = 1;
+    if (std::getenv("FMSI_GPU_TIMING"))
+        fprintf(stderr, "[fmsi timing] minimizer-bucketed dictionary (m = %u, t = %u, %llu rows) built in %.3f s\n", m, t,
+                (unsigned long long)la.n_rows, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+
 int select_device(fmsi_gpu_index *idx) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -593,6 +674,8 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
     if (const char *e = std::getenv("FMSI_GPU_DICT")) want_dict = std::atoi(e);
     idx->fold_ids_policy = opts ? opts->fold_ids : 0;
     if (const char *e = std::getenv("FMSI_GPU_FOLD_IDS")) idx->fold_ids_policy = std::atoi(e);
+    idx->loc_policy = opts ? opts->locality : 0;
+    if (const char *e = std::getenv("FMSI_GPU_LOCALITY")) idx->loc_policy = std::atoi(e);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     if (const char *e = std::getenv("FMSI_GPU_FREE_CAP")) free_b = std::min<size_t>(free_b, (size_t)std::atoll(e));  // test hook: a busier GPU
@@ -673,6 +756,7 @@ int finish_device_setup(fmsi_gpu_index *idx, const fmsi_gpu_options *opts) {
                         "using %s — single k-mer queries run several times slower\n",
                 free_b / 1e9, fold_build_peak_bytes(h.n, (u32)auto_depth(), false) / 1e9, idx->dict.enabled ? "the SA-ordered dictionary" : "backward search");
     if ((rc = setup_multistep(idx, opts))) return rc;
+    if (idx->loc_policy == 1) ensure_loc(idx, (int)h.k, 0, true);
     return alloc_slots(idx);
 }
 
@@ -1077,7 +1161,7 @@ int fmsi_gpu_index_free(fmsi_gpu_index *idx) {
     if (!idx) return FMSI_GPU_OK;
     cudaSetDevice(idx->device);
     for (void *p : {idx->d_rank, idx->d_aux, idx->d_table, idx->d_sb, idx->d_counts, idx->d_rows, idx->d_fbuckets, idx->d_frows, idx->d_fids,
-                    idx->d_multi, idx->d_user_bytes, (void *)idx->d_probes, (void *)idx->user.ctr, idx->user.ovf})
+                    idx->d_multi, idx->d_ldir, idx->d_lrows, idx->d_user_bytes, (void *)idx->d_probes, (void *)idx->user.ctr, idx->user.ovf})
         if (p) cudaFree(p);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
     for (cudaEvent_t ev : idx->piece_events) cudaEventDestroy(ev);
@@ -1110,6 +1194,7 @@ int fmsi_gpu_index_get_info(const fmsi_gpu_index *idx, fmsi_gpu_index_info *info
     info->device = idx->device;
     info->multistep = (int32_t)idx->dev.multi_m;
     info->fold_ids = idx->fold.enabled && idx->fold.ids ? 1 : 0;
+    info->locality = idx->loc.enabled ? (int32_t)idx->loc.g.m : 0;
     return FMSI_GPU_OK;
 }
 
@@ -1303,6 +1388,7 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     if (!text || !chunk_off || (!reads_mode && (!chunk_len || !res_off)) || !results) return fail(FMSI_GPU_ERR_ARG, "null buffer");
     CU(cudaSetDevice(idx->device));
     if (output == FMSI_GPU_OUT_ORDERS && (u32)k == idx->fold.k) ensure_fold_ids(idx);
+    if (output == FMSI_GPU_OUT_PRESENCE && mode != FMSI_GPU_MODE_GENERAL_) ensure_loc(idx, k, n_results, false);
     const DevIndex d = dev_for_k(idx, k);
     const size_t rbytes = result_bytes(output, strands);
     const bool on_host = mem == FMSI_GPU_MEM_HOST;
@@ -1326,7 +1412,8 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     // k-mer instead of an aux probe + an LF-step per k-mer and strand (profiles/r01d_modes_*.json).
     // k > 32: queries are start positions into the packed text (longk_kernels.cuh), with or without -S.
     const bool longk = k > 32;
-    const bool via_kmers = longk || !streaming || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k && (output != FMSI_GPU_OUT_ORDERS || idx->fold.ids)) ||
+    const bool via_loc = !longk && loc_answers(idx, k, mode, output);
+    const bool via_kmers = longk || !streaming || via_loc || (!idx->wide && ((idx->fold.enabled && (u32)k == idx->fold.k && (output != FMSI_GPU_OUT_ORDERS || idx->fold.ids)) ||
                                                          (idx->dict.enabled && (u32)k == idx->dict.k && d.t && n_results < (1ull << 32))));
     const size_t n_words = n_words_in + 4;
     size_t aux_need = n_words * 8;
@@ -1502,6 +1589,19 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
             int e = dispatch_long(idx->wide, idx->sm_count, d, mode, output, strands, gf, d_packed, d_slots + r0, r1 - r0, out_span, ls.ctr, q);
             if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)e));
             g_launches.fetch_add(2);
+        } else if (via_loc) {
+            // neighbouring k-mers of a text share their bucket in the minimizer-bucketed dictionary (loc.cuh)
+            if (reads_mode) {
+                const ReadSrc rs{d_packed, d_off, d_res, (u64)n_reads, (u64)r0};
+                int e = launch_loc(idx, mode, strands, nullptr, r1 - r0, out_span, ls, q, rs);
+                if (e) return e;
+            } else {
+                extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, (u64)n_bases, d_slots);
+                CU(cudaGetLastError());
+                g_launches.fetch_add(1);
+                int e = launch_loc(idx, mode, strands, d_slots + r0, r1 - r0, out_span, ls, q, ReadSrc{nullptr, nullptr, nullptr, 0, 0});
+                if (e) return e;
+            }
         } else if (via_kmers && reads_mode && fold_answers(idx, k, mode, output)) {
             // the dictionary kernel cuts its k-mers out of the reads itself (one chunk per read: d_off = first base,
             // d_res = first result slot of every read)
@@ -1762,6 +1862,11 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->dict = src->dict;
     r->fold = src->fold;
     r->fold_ids_policy = src->fold_ids_policy;
+    r->loc = src->loc;
+    r->loc_policy = src->loc_policy;
+    r->loc_failed = src->loc_failed;
+    r->b_ldir = src->b_ldir;
+    r->b_lrows = src->b_lrows;
     r->b_fbuckets = src->b_fbuckets;
     r->b_frows = src->b_frows;
     r->b_fids = src->b_fids;
@@ -1785,7 +1890,9 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
         (rc = replicate_array(&r->d_fbuckets, dev, src->d_fbuckets, src->device, src->b_fbuckets)) ||
         (rc = replicate_array(&r->d_frows, dev, src->d_frows, src->device, src->b_frows)) ||
         (rc = replicate_array(&r->d_fids, dev, src->d_fids, src->device, src->b_fids)) ||
-        (rc = replicate_array(&r->d_multi, dev, src->d_multi, src->device, src->b_multi)))
+        (rc = replicate_array(&r->d_multi, dev, src->d_multi, src->device, src->b_multi)) ||
+        (rc = replicate_array(&r->d_ldir, dev, src->d_ldir, src->device, src->b_ldir)) ||
+        (rc = replicate_array(&r->d_lrows, dev, src->d_lrows, src->device, src->b_lrows)))
         return bail(rc);
     r->dev.rank = reinterpret_cast<const RankBlock *>(r->d_rank);
     r->dev.aux = reinterpret_cast<const AuxBlock *>(r->d_aux);
@@ -1796,6 +1903,8 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->fold.buckets = r->d_fbuckets;
     r->fold.orows = reinterpret_cast<const u64 *>(r->d_frows);
     r->fold.ids = reinterpret_cast<const uint2 *>(r->d_fids);
+    r->loc.dir = reinterpret_cast<const uint2 *>(r->d_ldir);
+    r->loc.rows = reinterpret_cast<const u64 *>(r->d_lrows);
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(FMSI_GPU_ERR_CUDA, "cudaSetDevice"));
     if ((rc = alloc_slots(r.get()))) return bail(rc);
     *out = r.release();

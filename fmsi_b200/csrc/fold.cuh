@@ -371,33 +371,14 @@ inline u64 fold_build_peak_bytes(u64 N, u32 t, bool with_ids) {
 }
 inline u64 fold_resident_bytes(u64 N, u32 t, bool with_ids) { return (32ull << (2 * t)) + N + (with_ids ? 8ull * N : 0ull); }
 
-// want_table: buckets + overflow rows; want_ids: the lookup ids (row numbering is the same whichever is built).
-// Throws std::runtime_error (out of memory included); nothing is leaked then.
-inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, u32 t, bool want_table, bool want_ids, FoldArrays &out,
-                                 uint64_t *launches) {
+// The k-mer of every SA row (kmers[], validbits[]) and the first row of every run of equal k-mers (heads[0, M)): the
+// distinct k-mers of the index with their SA intervals. Shared by the dictionary builders (fold.cuh, loc.cuh).
+template <typename Stage, typename Lap>
+inline void derive_kmer_runs(const DevIndex &d, const u64 counts[4], u32 k, DevArr<u64> &kmers, DevArr<u32> &validbits, DevArr<u32> &heads, u64 &M,
+                             uint64_t &nl, Stage stage, Lap lap) {
     const u64 N = d.n;
-    const u32 B = k - t;
-    const u64 total = 1ull << (2 * t);
-    const u32 cap = B > 16 ? kFoldCap64 : kFoldCap32;
-    auto stage = [](const char *what) {  // surfaces asynchronous errors with the step that caused them
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
-    };
-    const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
-    const auto t0 = std::chrono::steady_clock::now();
-    size_t low_free = ~(size_t)0;  // lowest free device memory seen at the stage ends ($FMSI_GPU_TIMING): the build's peak
-    auto lap = [&](const char *what) {
-        if (!timing) return;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (free_b < low_free) low_free = free_b;
-        fprintf(stderr, "[fmsi timing] fold build: %s at %.3f s (device memory in use %.1f GB, peak so far %.1f GB)\n", what,
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), (total_b - free_b) / 1e9, (total_b - low_free) / 1e9);
-    };
-    uint64_t nl = 0;
-    DevArr<u64> kmers(N);
-    DevArr<u32> validbits((N >> 5) + 2);
+    kmers.alloc(N);
+    validbits.alloc((N >> 5) + 2);
     {
         const u32 c1 = (u32)counts[1], c2 = (u32)counts[2], c3 = (u32)counts[3];
         DevArr<u32> pa(N);
@@ -436,8 +417,6 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
         }
     }
     lap("k-mers of the SA rows");
-    DevArr<u32> heads;
-    u64 M = 0;
     {
         DevArr<u32> all(N);
         M = fold_select_heads(N, all.p, FoldRunHead{kmers.p, validbits.p});
@@ -451,6 +430,36 @@ inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, 
             all.p = nullptr;
         }
     }
+}
+
+// want_table: buckets + overflow rows; want_ids: the lookup ids (row numbering is the same whichever is built).
+// Throws std::runtime_error (out of memory included); nothing is leaked then.
+inline void build_fold_on_device(const DevIndex &d, const u64 counts[4], u32 k, u32 t, bool want_table, bool want_ids, FoldArrays &out,
+                                 uint64_t *launches) {
+    const u32 B = k - t;
+    const u64 total = 1ull << (2 * t);
+    const u32 cap = B > 16 ? kFoldCap64 : kFoldCap32;
+    auto stage = [](const char *what) {  // surfaces asynchronous errors with the step that caused them
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    const bool timing = std::getenv("FMSI_GPU_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t low_free = ~(size_t)0;  // lowest free device memory seen at the stage ends ($FMSI_GPU_TIMING): the build's peak
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (free_b < low_free) low_free = free_b;
+        fprintf(stderr, "[fmsi timing] fold build: %s at %.3f s (device memory in use %.1f GB, peak so far %.1f GB)\n", what,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), (total_b - free_b) / 1e9, (total_b - low_free) / 1e9);
+    };
+    uint64_t nl = 0;
+    DevArr<u64> kmers;
+    DevArr<u32> validbits, heads;
+    u64 M = 0;
+    derive_kmer_runs(d, counts, k, kmers, validbits, heads, M, nl, stage, lap);
     lap("run heads");
     DevArr<FoldBucket> buckets;
     if (want_table) buckets.alloc(total);

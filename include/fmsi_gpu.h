@@ -79,7 +79,10 @@ typedef struct {
     int32_t fold_ids;      /* lookup ids of the strand-folded dictionary (8 bytes per distinct k-mer, read only by OUT_ORDERS
                             * queries): 0 = built on the first lookup, 1 = built with the tier, -1 = never (lookups then run
                             * on the backward-search kernels) */
-    int32_t reserved32;
+    int32_t locality;      /* minimizer-bucketed dictionary for k-mers that come out of a text (reads, chunks; presence outputs):
+                            * neighbouring k-mers share their memory requests. A second copy of the dictionary rows (8 bytes per
+                            * distinct k-mer + 8 per bucket): 0 = built by the first text call of 2^24 k-mers or more,
+                            * 1 = built at load, -1 = never */
     int64_t reserved[4];
 } fmsi_gpu_options;
 
@@ -98,7 +101,8 @@ typedef struct {
     int32_t dict_t;      /* bucket depth of that tier (bases) */
     int32_t multistep;   /* bases per probe of the resident multi-step rank arrays (0 = none) */
     int32_t fold_ids;    /* 1 when the strand-folded dictionary's lookup ids are resident */
-    int32_t reserved[3];
+    int32_t locality;    /* minimizer length of the resident minimizer-bucketed dictionary (0 = not resident) */
+    int32_t reserved[2];
 } fmsi_gpu_index_info;
 
 const char *fmsi_gpu_last_error(void);

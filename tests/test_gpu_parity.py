@@ -72,7 +72,9 @@ def test_unit_goldens_on_device(t):
 TIER_KW = {"auto": {}, "backward": {"dict": 0}, "backward_t0": {"dict": 0, "prefix_t": 0}, "backward_ms0": {"dict": 0, "multistep": 0},
            "backward_ms3": {"dict": 0, "multistep": 3}, "backward_t0_ms2": {"dict": 0, "prefix_t": 0, "multistep": 2},
            # the wide layout (N >= 2^32) forced on small indexes: 64-bit positions, multi-step sectors of 192 rows
-           "wide": {"sb_shift_log2": 1, "prefix_t": 1}, "wide_ms3": {"sb_shift_log2": 2, "prefix_t": 0, "multistep": 3}}
+           "wide": {"sb_shift_log2": 1, "prefix_t": 1}, "wide_ms3": {"sb_shift_log2": 2, "prefix_t": 0, "multistep": 3},
+           # the minimizer-bucketed dictionary (loc.cuh) answers chunks / reads with presence outputs, next to either tier
+           "loc": {"locality": 1}, "loc_backward": {"dict": 0, "locality": 1}}
 
 
 @pytest.mark.parametrize("tier", list(TIER_KW))
@@ -82,7 +84,7 @@ def test_streaming_and_query_goldens_on_device(tier):
     suffix table, with single and multi-step probes."""
     kw = TIER_KW[tier]
     idx3 = gpu_fixture(3, **kw)
-    assert bool(idx3.dict) == (tier == "auto")
+    assert bool(idx3.dict) == (tier in ("auto", "loc")) and bool(idx3.locality) == tier.startswith("loc")
     # QUERY_KMERS_STREAMING :223-249 and _ORDERS :251-276 (results here do not depend on the predictor)
     for q, mo, want in [("CACATACA", False, "111001"), ("TGTATGTG", False, "100111"), ("CACATTGT", False, "111001"), ("CACATACA", True, "111001")]:
         got = idx3.query_chunks(q.encode(), [0], [len(q)], k=3, mode=fg.MODE_ALL if mo else fg.MODE_OR, streaming=True)
@@ -320,7 +322,7 @@ def _chunks_of(seq_codes_list, k, max_kmers):
 
 
 @pytest.mark.parametrize("case", ["syn_k31_max", "syn_k31_min", "syn_k9_max", "syn_k9_min", "syn_k5_min", "data_k13", "data_k31", "syn_k32", "quirks_k3_nonmax"])
-@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "backward_ms3", "wide", "wide_ms3"])
+@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "backward_ms3", "wide", "wide_ms3", "loc", "loc_backward"])
 def test_chunks_streaming_and_single_match_oracle(case, tier):
     """Chunks of text, streamed (-S) and single, LAZY and BOTH strands, all three outputs, against the oracle. With
     `auto` a dictionary tier answers streamed chunks too; the dict = 0 tiers put stream_kernel (query_kmers_streaming,
@@ -331,7 +333,7 @@ def test_chunks_streaming_and_single_match_oracle(case, tier):
     k = meta["k"]
     prefix = os.path.join(d, "ms.fa")
     gi = fg.Index.load(prefix, use_klcp=True, **TIER_KW[tier])
-    assert bool(gi.dict) == (tier == "auto")
+    assert bool(gi.dict) == (tier in ("auto", "loc")) and bool(gi.locality) == tier.startswith("loc")
     oi = OracleIndex.load(prefix, use_klcp=True)
     ms_codes = synth.ascii_to_codes(open(prefix, "rb").read().split(b"\n")[1])
     rng = np.random.default_rng(7)
@@ -555,7 +557,7 @@ def test_bit_packed_results_and_packed_text(tier):
     gi.close()
 
 
-@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0"])
+@pytest.mark.parametrize("tier", ["auto", "backward", "backward_t0", "backward_ms0", "loc", "loc_backward"])
 def test_reads_api_matches_chunk_calls(tier):
     """fmsi_gpu_query_reads_packed: the caller hands over whole reads (offsets into one 2-bit text), the device cuts them
     into the chunks its kernels take. Reads of every awkward length (empty, shorter than k, exactly k, 64 / 65 / 129
