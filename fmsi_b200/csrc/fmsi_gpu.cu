@@ -78,7 +78,7 @@ struct fmsi_gpu_index {
     void *d_ldir = nullptr, *d_lrows = nullptr;                         // minimizer-bucketed dictionary (loc.cuh)
     size_t b_ldir = 0, b_lrows = 0;
     LocView loc{};
-    int loc_policy = 0;        // fmsi_gpu_options.locality: 0 = on the first large text call, 1 = at load, -1 = never
+    int loc_policy = 0;        // fmsi_gpu_options.locality: 0 / -1 = never, 1 = at load, 2 = on the first large text call
     bool loc_failed = false;   // the build did not fit / failed once: text calls stay on the other tiers
     size_t b_multi = 0;
     size_t b_rank = 0, b_aux = 0, b_table = 0, b_sb = 0, b_rows = 0;  // bytes of the device arrays (replication)
@@ -527,14 +527,14 @@ void ensure_fold_ids(fmsi_gpu_index *idx) {
 
 // The minimizer-bucketed dictionary (loc.cuh) answers k-mers that come out of a text — reads, chunks — at about half a
 // memory request per k-mer, where the strand-folded dictionary needs one. It costs a second copy of the rows (8 bytes per
-// distinct k-mer + 8 bytes per bucket), so unless asked for at load (locality = 1) it is built here, by the first text call
-// that is large enough to pay for the build. Out of memory is not an error: text calls then stay on the other tiers.
+// distinct k-mer + 8 bytes per bucket), so it is opt-in: built at load (locality = 1) or here (locality = 2), by the first
+// text call that is large enough to pay for the build. Out of memory is not an error: text calls then stay on the other tiers.
 constexpr size_t kLocLazyResults = (size_t)1 << 24;
 void ensure_loc(fmsi_gpu_index *idx, int k, size_t n_results, bool at_load) {
-    if (idx->loc.enabled || idx->loc_failed || idx->loc_policy < 0 || idx->wide) return;
+    if (idx->loc.enabled || idx->loc_failed || idx->loc_policy <= 0 || idx->wide) return;
     const HostIndex &h = idx->meta;
     if (k != h.k || h.k < 1 || h.k > 32 || h.n >= (1ull << 32) - 256) return;
-    if (!at_load && (idx->loc_policy != 0 || n_results < kLocLazyResults)) return;
+    if (!at_load && (idx->loc_policy != 2 || n_results < kLocLazyResults)) return;
     u32 m = loc_pick_m(h.n, (u32)h.k);
     if (const char *e = std::getenv("FMSI_GPU_LOC_M")) m = (u32)std::atoi(e);
     u32 t = 1;
@@ -1903,7 +1903,7 @@ int replicate_index(const fmsi_gpu_index *src, int dev, fmsi_gpu_index **out) {
     r->fold.buckets = r->d_fbuckets;
     r->fold.orows = reinterpret_cast<const u64 *>(r->d_frows);
     r->fold.ids = reinterpret_cast<const uint2 *>(r->d_fids);
-    r->loc.dir = reinterpret_cast<const uint2 *>(r->d_ldir);
+    r->loc.dir = reinterpret_cast<const u64 *>(r->d_ldir);
     r->loc.rows = reinterpret_cast<const u64 *>(r->d_lrows);
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(FMSI_GPU_ERR_CUDA, "cudaSetDevice"));
     if ((rc = alloc_slots(r.get()))) return bail(rc);

@@ -12,17 +12,20 @@
 // Rows are the same as in fold.cuh — one per distinct k-mer of the index in a strand-neutral orientation, carrying the
 // states (sf, sr) of the two SA intervals from which query_kmers_single (src/fms_index.h:263-331) derives every answer —
 // but keyed and laid out differently:
-//   pick(q)   the minimizer of {q, rc(q)}: hash h (a bijection of the m-mer, so h stands for it), the strand it was found
-//             on (ties: the strand with the smaller q * C first, then the leftmost position — a rule that does not depend
-//             on which strand the caller holds) and its position pos in that strand's k-mer o
-//   bucket    top 2t bits of h
-//   R         h's low 2m - 2t bits . pos . the k - m bases of o around the m-mer        (2k - 2t + pbits bits)
+//   pick(q)   the minimizer of {q, rc(q)}: among the m-mers of both strands the one whose ordering hash (its top 26 bits)
+//             is smallest; ties go to the strand with the smaller q * C, then to the leftmost position — a rule that does
+//             not depend on which strand the caller holds. o = that strand's k-mer, pos = the m-mer's position in it
+//   h'        a bijection of the m-mer on 2m bits (not the ordering hash: a minimum is a small number)
+//   bucket    top 2t bits of h'
+//   R         pos . h' low 2m - 2t bits . the k - m bases of o around the m-mer        (2k - 2t + pbits bits)
 //             (bucket, R) <-> o is one-to-one, so a row match is exact — no fingerprints
-//   dir[x]    {number of the bucket's first row, its row count}              8 bytes per bucket
-//   rows[]    R << 4 | sf | sr << 2, sorted by (bucket, R)                   8 bytes per distinct k-mer
-// A query reads dir[bucket] and then binary-searches the bucket's rows a sector (4 rows) per step: 2-3 dependent requests
-// for a k-mer on its own — worse than fold.cuh — but about half a request per k-mer when reads are streamed through it.
-// So this tier only answers text-derived queries (reads / chunks, presence outputs); packed single k-mers stay on fold.cuh.
+//   dir[x]    first row (32 bits) | row count (22) | smallest pos (5) | pos span (5)        8 bytes per bucket
+//   rows[]    R << 4 | sf | sr << 2, sorted by (bucket, R)                                   8 bytes per distinct k-mer
+// A query reads dir[bucket]; a pos outside the bucket's range is absent at once; otherwise the bucket's rows — sorted by
+// pos first — are probed where pos interpolates to, a sector (4 rows) at a time, and bisected from there. 2-3 dependent
+// requests for a k-mer on its own — worse than fold.cuh — but a fraction of a request per k-mer when the 32 lanes of a
+// warp hold 32 consecutive k-mers of a read. So this tier only answers text-derived queries (reads / chunks, presence
+// outputs); packed single k-mers stay on fold.cuh.
 //
 // Built on the device like fold.cuh (shared: the k-mer of every SA row by pointer doubling, the runs of equal k-mers);
 // entries are sorted by their 64 low key bits in passes over aligned bucket ranges, which makes the bits a 2k + pbits > 64
@@ -71,58 +74,63 @@ inline bool loc_fits(u32 k, u32 m, u32 t) {
 }
 
 struct LocView {
-    const uint2 *dir;  // [4^t]
+    const u64 *dir;    // [4^t]
     const u64 *rows;   // [n_rows]
     u64 n_rows;
     LocGeom g;
     u32 enabled;
 };
 
-constexpr u32 kLocMul1 = 0x9E3779B1u, kLocMul2 = 0x85EBCA6Bu;
-// a bijection of [0, 4^m), m <= 16
-__host__ __device__ __forceinline__ u32 loc_hash(u32 x, u32 m, u32 mask) {
-    x = (x * kLocMul1) & mask;
+constexpr u32 kLocMul1 = 0x9E3779B1u, kLocMul3 = 0xC2B2AE35u, kLocMul4 = 0x27D4EB2Fu;
+constexpr u32 kLocCandBits = 6;  // 2 w <= 34 candidates
+// ordering value of candidate `cand` (an m-mer x): top 26 bits of x * C, then the candidate's number
+__host__ __device__ __forceinline__ u32 loc_order(u32 x, u32 cand) { return ((x * kLocMul1) & ~((1u << kLocCandBits) - 1u)) | cand; }
+// a bijection of [0, 4^m), m <= 16: the key hash of an m-mer
+__host__ __device__ __forceinline__ u32 loc_spread(u32 x, u32 m, u32 mask) {
+    x = (x * kLocMul3) & mask;
     x ^= x >> m;
-    x = (x * kLocMul2) & mask;
+    x = (x * kLocMul4) & mask;
+    x ^= x >> m;
     return x;
 }
 
-// The minimizer of {q, rc}: its hash, the strand it sits on (sw: not the caller's q) and that strand's k-mer o, its position.
-__host__ __device__ __forceinline__ void loc_pick(u64 q, u64 rc, const LocGeom &g, u32 &h, u32 &pos, bool &sw, u64 &o) {
+// The minimizer of {q, rc}: the strand it sits on (sw: not the caller's q), that strand's k-mer o, its position, its value.
+__host__ __device__ __forceinline__ void loc_pick(u64 q, u64 rc, const LocGeom &g, u32 &x, u32 &pos, bool &sw, u64 &o) {
     const bool fs = rc * kFoldMul < q * kFoldMul;
     const u64 a = fs ? rc : q, b = fs ? q : rc;
     const u32 mask = g.m < 16 ? (1u << (2 * g.m)) - 1u : 0xFFFFFFFFu;
-    u32 best = loc_hash((u32)(a >> g.fbits) & mask, g.m, mask), bp = 0;
-    bool bs = false;
-    for (u32 p = 1; p < g.w; ++p) {
-        const u32 hx = loc_hash((u32)(a >> (g.fbits - 2 * p)) & mask, g.m, mask);
-        if (hx < best) {
-            best = hx;
-            bp = p;
-        }
-    }
+    u32 best = 0xFFFFFFFFu;
     for (u32 p = 0; p < g.w; ++p) {
-        const u32 hx = loc_hash((u32)(b >> (g.fbits - 2 * p)) & mask, g.m, mask);
-        if (hx < best) {
-            best = hx;
-            bp = p;
-            bs = true;
-        }
+        const u32 va = loc_order((u32)(a >> (g.fbits - 2 * p)) & mask, p);
+        const u32 vb = loc_order((u32)(b >> (g.fbits - 2 * p)) & mask, g.w + p);
+        best = va < best ? va : best;
+        best = vb < best ? vb : best;
     }
-    h = best;
-    pos = bp;
+    const u32 cand = best & ((1u << kLocCandBits) - 1u);
+    const bool bs = cand >= g.w;
+    pos = bs ? cand - g.w : cand;
     sw = fs != bs;
     o = bs ? b : a;
+    x = (u32)(o >> (g.fbits - 2 * pos)) & mask;
 }
 // bucket and R of a pick
-__host__ __device__ __forceinline__ void loc_key(u32 h, u32 pos, u64 o, const LocGeom &g, u32 &bucket, u64 &R) {
+__host__ __device__ __forceinline__ void loc_key(u32 x, u32 pos, u64 o, const LocGeom &g, u32 &bucket, u64 &R) {
+    const u32 mask = g.m < 16 ? (1u << (2 * g.m)) - 1u : 0xFFFFFFFFu;
+    const u32 h = loc_spread(x, g.m, mask);
     const u32 rl = g.fbits - 2 * pos;  // bits of the bases behind the m-mer
     const u64 right = rl ? (o & ((1ull << rl) - 1ull)) : 0ull;
     const u64 left = pos ? (o >> (2 * (g.k - pos))) : 0ull;
     const u64 flanks = rl ? ((left << rl) | right) : left;
-    const u64 hl = g.hlow ? (u64)(h & ((g.hlow < 32 ? (1u << g.hlow) : 0u) - 1u)) : 0ull;
-    bucket = g.hlow < 32 ? (h >> g.hlow) : 0u;
-    R = (hl << (g.pbits + g.fbits)) | ((u64)pos << g.fbits) | flanks;
+    const u64 hl = g.hlow ? (u64)(h & ((1u << g.hlow) - 1u)) : 0ull;  // hlow <= 30
+    bucket = h >> g.hlow;
+    R = ((u64)pos << (g.hlow + g.fbits)) | (hl << g.fbits) | flanks;
+}
+__host__ __device__ __forceinline__ u32 loc_pos_of_row(u64 row, const LocGeom &g) { return (u32)((row >> 4) >> (g.hlow + g.fbits)); }
+
+// directory entry
+constexpr u32 kLocCountBits = 22;
+__host__ __device__ __forceinline__ u64 loc_dir_entry(u32 first, u32 count, u32 pmin, u32 pspan) {
+    return (u64)first | ((u64)count << 32) | ((u64)pmin << 54) | ((u64)pspan << 59);
 }
 
 // ------------------------------------------------------------------------------------------- build
@@ -208,15 +216,23 @@ __global__ void loc_rows_kernel(const u64 *__restrict__ keys, const u64 *__restr
     if (first) bfirst[x] = (u32)gi;
     if (last) bcount[x] = (u32)(gi + 1);
 }
-__global__ void loc_dir_kernel(const u32 *__restrict__ bfirst, const u32 *__restrict__ bcount, const u64 nb, const u64 g0, uint2 *__restrict__ dir) {
+// rows: this pass's rows (local numbering); a bucket with more rows than the entry can count raises *too_many
+__global__ void loc_dir_kernel(const u32 *__restrict__ bfirst, const u32 *__restrict__ bcount, const u64 *__restrict__ rows, const u64 nb, const u64 g0,
+                               const LocGeom g, u64 *__restrict__ dir, u32 *__restrict__ too_many) {
     const u64 x = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     if (x >= nb) return;
     const u32 cnt = bcount[x] ? bcount[x] - bfirst[x] : 0u;
-    dir[x] = cnt ? make_uint2((u32)(g0 + bfirst[x]), cnt) : make_uint2(0u, 0u);
+    if (!cnt) {
+        dir[x] = 0ull;
+        return;
+    }
+    if (cnt >> kLocCountBits) atomicExch(too_many, 1u);
+    const u32 pmin = loc_pos_of_row(rows[bfirst[x]], g), pmax = loc_pos_of_row(rows[bfirst[x] + cnt - 1], g);  // rows are sorted by pos first
+    dir[x] = loc_dir_entry((u32)(g0 + bfirst[x]), cnt, pmin, pmax - pmin);
 }
 
 struct LocArrays {  // device arrays of a built tier (ownership passes to the caller)
-    uint2 *dir = nullptr;
+    u64 *dir = nullptr;
     u64 *rows = nullptr;
     u64 n_rows = 0;
 };
@@ -281,7 +297,9 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
         max_mp = std::max<u64>(max_mp, h_hist[p]);
         sum += h_hist[p];
     }
-    DevArr<uint2> dir(total);
+    DevArr<u64> dir(total);
+    DevArr<u32> too_many(1);
+    BCU(cudaMemset(too_many.p, 0, 4));
     DevArr<u64> rows(sum + 4);  // rows <= valid runs
     DevArr<u32> sel(max_mp + 1), gs(max_mp + 1);
     DevArr<u64> keys(max_mp), vals(max_mp), keys_alt(max_mp), vals_alt(max_mp);
@@ -306,12 +324,17 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
         if (G0 + G > sum) throw std::runtime_error("more rows than runs");
         if (G) loc_rows_kernel<<<nblocks_for(G), 256>>>(keys.p, vals.p, gs.p, G, Mp, g, x_lo, lmask, rows.p + G0, bfirst.p, bcount.p);
         stage("rows");
-        loc_dir_kernel<<<nblocks_for(nb), 256>>>(bfirst.p, bcount.p, nb, G0, dir.p + x_lo);
+        loc_dir_kernel<<<nblocks_for(nb), 256>>>(bfirst.p, bcount.p, rows.p + G0, nb, G0, g, dir.p + x_lo, too_many.p);
         stage("directory");
         nl += 6;
         G0 += G;
     }
     if (G0 >= (1ull << 32)) throw std::runtime_error("more than 2^32 rows");
+    {
+        u32 h_too_many = 0;
+        BCU(cudaMemcpy(&h_too_many, too_many.p, 4, cudaMemcpyDeviceToHost));
+        if (h_too_many) throw std::runtime_error("a minimizer is shared by more than 2^22 distinct k-mers");
+    }
     BCU(cudaMemset(rows.p + G0, 0xff, (sum + 4 - G0) * sizeof(u64)));  // a sector read may run past the last row
     sel.release();
     gs.release();
@@ -339,167 +362,191 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
 }
 
 // ------------------------------------------------------------------------------------------- query
-enum { LP_DIR = 0, LP_SEARCH = 1 };
-
-__device__ __forceinline__ uint2 ld_loc_dir(const uint2 *p) {
-    uint2 r;
-    asm volatile("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+__device__ __forceinline__ u64 ld_loc_dir(const u64 *p) {
+    u64 r;
+    asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
 
+// One tile = 32 consecutive queries of the launch, one per lane, walked in lockstep: DIR (the bucket's entry), then SEARCH
+// rounds until every lane has its row (or knows there is none). Lanes that hold neighbouring k-mers of a read ask for the
+// same directory entry and the same row sectors in the same instruction, which the load unit merges.
+struct LocTile {
+    u64 R;       // the lane's key inside its bucket
+    u32 lo, hi;  // SEARCH: rows still possible; DIR: lo = bucket
+    u32 r0;      // SEARCH: first row of the sector to probe
+    u32 st;      // the answer: sf | sr << 2 (0 = absent)
+    u32 pos;
+    bool active, swapped;
+};
+
 // Presence outputs only (K_OUT_PRESENCE). Queries come from a k-mer array whose neighbours are neighbouring k-mers of
-// a text (extract_kmers_kernel) or straight from reads (ReadSrc), as in fold_query_kernel.
+// a text (extract_kmers_kernel) or straight from reads (ReadSrc), as in fold_query_kernel. Every warp keeps TWO tiles in
+// flight (a lane has two independent requests outstanding).
 template <int MODE, int STRANDS>
 __global__ void __launch_bounds__(kQueryBlock)
 loc_query_kernel(const LocView lv, const u64 *__restrict__ kmers, const u64 n, unsigned char *__restrict__ out,
                  unsigned long long *__restrict__ cursor, const u32 chunk, unsigned long long *__restrict__ probe_ctr, const ReadSrc rs) {
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
-    const u32 lt_mask = (1u << lane) - 1u;
     const LocGeom g = lv.g;
     const u32 k = g.k;
-
-    bool active = false, swapped = false;
-    u32 phase = LP_DIR, bx = 0, lo = 0, hi = 0, st = 0;
-    u64 idx = 0, R = 0;
-    u64 cend = 0, wnext = 0, tile_base = 0, bufA = 0, bufB = 0;
-    bool exhausted = false;
-    u32 nprobe = 0;
     const bool from_reads = rs.text != nullptr;
-    u64 rd_hint = 0;
-    auto fetch = [&](u64 q) -> u64 {
-        if (q >= cend) return 0ull;
-        if (!from_reads) return kmers[q];
-        const u64 slot = rs.slot0 + q;
-        const u64 r = read_of_slot(rs, slot, rd_hint);
-        return window64(rs.text, __ldg(rs.roff + r) + (slot - __ldg(rs.rbase + r)), k);
+
+    u64 cnext = 0, cend = 0;  // the warp's grab: queries [cnext, cend) are still to be started (warp-uniform)
+    u64 rd_hint = 0;          // from_reads: a read at or before the one of query cnext
+    bool exhausted = false;
+
+    LocTile T[2];
+    u64 tbase[2] = {0, 0};  // first query of the tile
+    u32 phase[2] = {2, 2};  // 0 = DIR, 1 = SEARCH, 2 = empty (warp-uniform)
+    // the NEXT tile, prepared while the loads of the current ones are in flight: k-mers fetched, minimizers picked
+    LocTile P;
+    u64 pbase = 0;
+    bool pvalid = false;
+
+    auto count_requests = [&](bool mine, const void *addr) {  // requests after merging: distinct 128-byte lines of a warp instruction
+        if (!probe_ctr) return;
+        const unsigned act = __ballot_sync(FULL, mine);
+        if (mine) {
+            const unsigned same = __match_any_sync(act, (unsigned long long)addr >> 7);
+            if ((u32)(__ffs(same) - 1) == lane) atomicAdd(probe_ctr, 1ull);
+        }
     };
-    auto advance_hint = [&](u64 first_q) {
-        if (!from_reads) return;
-        u64 r = 0;
-        if (lane == 0 && first_q < cend) r = read_of_slot(rs, rs.slot0 + first_q, rd_hint);
-        r = __shfl_sync(FULL, r, 0);
-        if (first_q < cend) rd_hint = r;
+    auto write_result = [&](const LocTile &t, u64 q) {
+        u32 sf = t.st & 3u, sr = t.st >> 2;
+        if (t.swapped) {
+            const u32 x = sf;
+            sf = sr;
+            sr = x;
+        }
+        const int vf = fold_presence<MODE>(sf), vr = fold_presence<MODE>(sr);
+        unsigned char v;
+        if (STRANDS == K_STRANDS_BOTH) v = (unsigned char)((vf + 1) | ((vr + 1) << 2));
+        else if (MODE == K_MODE_ALL) v = (unsigned char)((vf != -1 ? vf : vr) == 1);  // fms_index.h:294-298
+        else v = (unsigned char)(vf == 1 || vr == 1);                                  // :289-293
+        out[q] = v;
+    };
+    // prepare the next tile: fetch its k-mers, pick the minimizers (P.lo = bucket)
+    auto prepare = [&]() {
+        if (cnext >= cend) {
+            unsigned long long c0 = 0;
+            if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)chunk);
+            c0 = __shfl_sync(FULL, c0, 0);
+            if (c0 >= n) {
+                exhausted = true;
+                return;
+            }
+            cnext = c0;
+            cend = (c0 + chunk < n) ? c0 + chunk : n;
+            rd_hint = 0;
+        }
+        const u64 q = cnext + lane;
+        const bool have = q < cend;
+        u64 km = 0;
+        if (have) {
+            if (!from_reads) {
+                km = kmers[q];
+            } else {
+                const u64 slot = rs.slot0 + q;
+                const u64 r = read_of_slot(rs, slot, rd_hint);
+                km = window64(rs.text, __ldg(rs.roff + r) + (slot - __ldg(rs.rbase + r)), k);
+                if (lane == 0) rd_hint = r;
+            }
+        }
+        if (from_reads) rd_hint = __shfl_sync(FULL, rd_hint, 0);  // lane 0 holds the tile's first query
+        P.active = have;
+        P.st = 0;
+        if (have) {
+            if (k < 32) km &= (1ull << (2 * k)) - 1ull;
+            u32 x;
+            u64 o;
+            loc_pick(km, revcomp_packed(km, k), g, x, P.pos, P.swapped, o);
+            loc_key(x, P.pos, o, g, P.lo, P.R);
+        }
+        pbase = cnext;
+        pvalid = true;
+        cnext = (cnext + 32 < cend) ? cnext + 32 : cend;
     };
 
     for (;;) {
-        // ---------------------------------------------------------------- refill idle lanes (as in fold_query_kernel)
-        const unsigned need = __ballot_sync(FULL, !active);
-        if (need && !exhausted) {
-            if (wnext >= cend) {
-                unsigned long long c0 = 0;
-                if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)chunk);
-                c0 = __shfl_sync(FULL, c0, 0);
-                if (c0 >= n) {
-                    exhausted = true;
-                } else {
-                    wnext = tile_base = c0;
-                    cend = (c0 + chunk < n) ? c0 + chunk : n;
-                    if (from_reads) {
-                        rd_hint = 0;
-                        advance_hint(tile_base);
-                    }
-                    bufA = fetch(tile_base + lane);
-                    bufB = fetch(tile_base + 32 + lane);
-                }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (phase[s] == 2 && pvalid) {
+                T[s] = P;
+                tbase[s] = pbase;
+                phase[s] = 0;
+                pvalid = false;
             }
-            if (!exhausted) {
-                const u32 pre = __popc(need & lt_mask);
-                const u64 my = wnext + pre;
-                const bool take = !active && my < cend;
-                const u32 src = (u32)(my - tile_base);
-                u64 km = __shfl_sync(FULL, bufA, src & 31u);
-                if (__any_sync(FULL, take && src >= 32u)) {
-                    const u64 kb = __shfl_sync(FULL, bufB, src & 31u);
-                    if (src >= 32u) km = kb;
-                }
-                const u64 left = cend - wnext;
-                const u32 want = __popc(need);
-                wnext += (want < left) ? want : left;
-                if (wnext - tile_base >= 32) {
-                    tile_base += 32;
-                    bufA = bufB;
-                    advance_hint(tile_base);
-                    bufB = fetch(tile_base + 32 + lane);
-                }
-                if (take) {
-                    active = true;
-                    idx = my;
-                    if (k < 32) km &= (1ull << (2 * k)) - 1ull;
-                    u32 h, pos;
-                    u64 o;
-                    loc_pick(km, revcomp_packed(km, k), g, h, pos, swapped, o);
-                    loc_key(h, pos, o, g, bx, R);
-                    phase = LP_DIR;
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) {
-            if (exhausted) break;
-            continue;
-        }
+        if (phase[0] == 2 && phase[1] == 2 && exhausted) break;
 
-        // ---------------------------------------------------------------- issue this round's loads
-        const bool isD = active && phase == LP_DIR;
-        const bool isS = active && phase == LP_SEARCH;
-        const u32 r0 = (lo + ((hi - lo) >> 1)) & ~3u;  // sector probed (row number of its first entry)
-        uint2 de = make_uint2(0u, 0u);
-        u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        if (isD) de = ld_loc_dir(lv.dir + bx);
-        if (isS) ld_sector_l1(lv.rows + r0, a0, a1, a2, a3);
-        nprobe += (u32)(isD || isS);
+        // ---------------------------------------------------------------- issue both tiles' loads
+        u64 de[2] = {0, 0};
+        u64 a0[2], a1[2], a2[2], a3[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            a0[s] = a1[s] = a2[s] = a3[s] = 0;
+            const bool on = phase[s] != 2 && T[s].active;
+            if (on && phase[s] == 0) de[s] = ld_loc_dir(lv.dir + T[s].lo);
+            if (on && phase[s] == 1) ld_sector_l1(lv.rows + T[s].r0, a0[s], a1[s], a2[s], a3[s]);
+            if (phase[s] != 2) count_requests(on, phase[s] == 0 ? (const void *)(lv.dir + T[s].lo) : (const void *)(lv.rows + T[s].r0));
+        }
+        // ---------------------------------------------------------------- meanwhile: the next tile
+        if (!pvalid && !exhausted) prepare();
 
         // ---------------------------------------------------------------- consume
-        bool done = false;
-        if (isD) {
-            st = 0;
-            lo = de.x;
-            hi = de.x + de.y;
-            if (de.y == 0) done = true;
-            else phase = LP_SEARCH;
-        } else if (isS) {
-            // invariant: rows before lo are smaller than R, rows from hi on are larger
-            const u32 w0 = r0 > lo ? r0 : lo, w1 = (r0 + 4 < hi) ? r0 + 4 : hi;
-            bool found = false;
-            u64 first = 0, last = 0;
 #pragma unroll
-            for (u32 s = 0; s < 4; ++s) {
-                const u64 rw = s == 0 ? a0 : s == 1 ? a1 : s == 2 ? a2 : a3;
-                const u32 r = r0 + s;
-                if (r >= w0 && r < w1) {
-                    const u64 key = rw >> 4;
-                    if (r == w0) first = key;
-                    last = key;
-                    if (key == R) {
-                        found = true;
-                        st = (u32)rw & 15u;
+        for (int s = 0; s < 2; ++s) {
+            if (phase[s] == 2) continue;
+            LocTile &t = T[s];
+            bool done = false;
+            if (t.active && phase[s] == 0) {
+                const u32 first = (u32)de[s], cnt = (u32)(de[s] >> 32) & ((1u << kLocCountBits) - 1u);
+                const u32 pmin = (u32)(de[s] >> 54) & 31u, pspan = (u32)(de[s] >> 59);
+                if (cnt == 0 || t.pos < pmin || t.pos > pmin + pspan) {
+                    done = true;  // empty bucket, or no row of it has the minimizer at this position
+                } else {
+                    t.lo = first;
+                    t.hi = first + cnt;
+                    // rows are sorted by pos first: start where pos interpolates to
+                    const u32 guess = first + (u32)(((u64)(2 * (t.pos - pmin) + 1) * cnt) / (2 * (pspan + 1)));
+                    t.r0 = (guess < t.hi ? guess : t.hi - 1) & ~3u;
+                }
+            } else if (t.active) {
+                // invariant: rows before lo are smaller than R, rows from hi on are larger
+                const u32 r0 = t.r0;
+                const u32 w0 = r0 > t.lo ? r0 : t.lo, w1 = (r0 + 4 < t.hi) ? r0 + 4 : t.hi;
+                bool found = false;
+                u64 first = 0, last = 0;
+#pragma unroll
+                for (u32 e = 0; e < 4; ++e) {
+                    const u64 rw = e == 0 ? a0[s] : e == 1 ? a1[s] : e == 2 ? a2[s] : a3[s];
+                    const u32 r = r0 + e;
+                    if (r >= w0 && r < w1) {
+                        const u64 key = rw >> 4;
+                        if (r == w0) first = key;
+                        last = key;
+                        if (key == t.R) {
+                            found = true;
+                            t.st = (u32)rw & 15u;
+                        }
                     }
                 }
+                if (found) done = true;
+                else if (last < t.R) t.lo = w1;
+                else if (first > t.R) t.hi = w0;
+                else done = true;  // R falls between two rows of this sector: absent
+                if (!done && t.lo >= t.hi) done = true;
+                if (!done) t.r0 = (t.lo + ((t.hi - t.lo) >> 1)) & ~3u;
             }
-            if (found) done = true;
-            else if (last < R) lo = w1;
-            else if (first > R) hi = w0;
-            else done = true;  // R falls between two rows of this sector: absent
-            if (!done && lo >= hi) done = true;
-        }
-
-        if (done) {
-            u32 sf = st & 3u, sr = st >> 2;
-            if (swapped) {
-                const u32 x = sf;
-                sf = sr;
-                sr = x;
+            if (done) {
+                write_result(t, tbase[s] + lane);
+                t.active = false;
             }
-            const int vf = fold_presence<MODE>(sf), vr = fold_presence<MODE>(sr);
-            unsigned char v;
-            if (STRANDS == K_STRANDS_BOTH) v = (unsigned char)((vf + 1) | ((vr + 1) << 2));
-            else if (MODE == K_MODE_ALL) v = (unsigned char)((vf != -1 ? vf : vr) == 1);  // fms_index.h:294-298
-            else v = (unsigned char)(vf == 1 || vr == 1);                                  // :289-293
-            out[idx] = v;
-            active = false;
+            if (phase[s] == 0) phase[s] = 1;
+            if (!__any_sync(FULL, t.active)) phase[s] = 2;
         }
     }
-    count_probes(probe_ctr, nprobe);
 }
 
 }  // namespace fmsi

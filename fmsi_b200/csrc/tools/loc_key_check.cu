@@ -2,7 +2,7 @@
 // (tests/test_loc_key.py). For every k-mer of a small alphabet space (exhaustive) or a seeded random sample:
 //   * q and its reverse complement get the same (bucket, R), with opposite `sw` unless q is its own reverse complement;
 //   * distinct strand pairs {q, rc} get distinct (bucket, R)  (exhaustive runs only);
-//   * bucket < 4^t, R < 2^rbits, and the pick is a minimum: no m-mer of either strand hashes below it.
+//   * bucket < 4^t, R < 2^rbits, and the pick is a minimum: no m-mer of either strand orders below it.
 // usage: loc_key_check k m t [samples seed]   -> prints one JSON line, exit code 1 on any violation
 #include <cstdio>
 #include <cstdlib>
@@ -57,11 +57,12 @@ int main(int argc, char **argv) {
         if ((u64)b1 >> (2 * t)) ++bad;
         if (g.rbits < 64 && (R1 >> g.rbits)) ++bad;
         if (p1 >= g.w) ++bad;
-        for (u32 p = 0; p < g.w; ++p) {  // the pick is a minimum over both strands
-            if (loc_hash((u32)(q >> (g.fbits - 2 * p)) & mmask, m, mmask) < h1) ++bad;
-            if (loc_hash((u32)(rc >> (g.fbits - 2 * p)) & mmask, m, mmask) < h1) ++bad;
+        const u32 omask = ~((1u << kLocCandBits) - 1u);
+        for (u32 p = 0; p < g.w; ++p) {  // the pick is a minimum (of the ordering value's hash part) over both strands
+            if ((loc_order((u32)(q >> (g.fbits - 2 * p)) & mmask, 0) & omask) < (loc_order(h1, 0) & omask)) ++bad;
+            if ((loc_order((u32)(rc >> (g.fbits - 2 * p)) & mmask, 0) & omask) < (loc_order(h1, 0) & omask)) ++bad;
         }
-        if (loc_hash((u32)(o1 >> (g.fbits - 2 * p1)) & mmask, m, mmask) != h1) ++bad;
+        if (((u32)(o1 >> (g.fbits - 2 * p1)) & mmask) != h1) ++bad;  // h1 = the m-mer itself
         if (!samples) {
             const u64 canon = q < rc ? q : rc;
             auto r = seen.emplace(std::make_pair(b1, R1), canon);

@@ -81,8 +81,8 @@ typedef struct {
                             * on the backward-search kernels) */
     int32_t locality;      /* minimizer-bucketed dictionary for k-mers that come out of a text (reads, chunks; presence outputs):
                             * neighbouring k-mers share their memory requests. A second copy of the dictionary rows (8 bytes per
-                            * distinct k-mer + 8 per bucket): 0 = built by the first text call of 2^24 k-mers or more,
-                            * 1 = built at load, -1 = never */
+                            * distinct k-mer + 8 per bucket), opt-in: 0 = off, 1 = built at load, 2 = built by the first text
+                            * call of 2^24 k-mers or more */
     int64_t reserved[4];
 } fmsi_gpu_options;
 
