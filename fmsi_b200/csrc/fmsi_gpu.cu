@@ -281,22 +281,29 @@ bool loc_answers(const fmsi_gpu_index *idx, int k, int mode, int output) {
     return !idx->wide && mode != 2 && idx->loc.enabled && (u32)k == idx->loc.g.k && output == FMSI_GPU_OUT_PRESENCE;
 }
 template <int MODE, int STRANDS>
-int launch_loc_v(const fmsi_gpu_index *idx, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st, const ReadSrc &rs) {
-    auto kern = loc_query_kernel<MODE, STRANDS>;
-    const int grid = persistent_grid(idx, kern, kQueryBlock);
+int launch_loc_v(const fmsi_gpu_index *idx, const u64 *packed, u64 n_bases, const u64 *coff, const u32 *clen, const u64 *roff, size_t n_chunks, void *out,
+                 LaunchScratch &ls, cudaStream_t st) {
+    auto kern = loc_stream_kernel<MODE, STRANDS>;
+    const size_t smem = loc_stream_smem(idx->loc.g);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLocBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = idx->sm_count * per_sm;
+    const size_t warps = (size_t)grid * (kLocBlock / 32);
+    size_t grab = n_chunks / (warps * 8 + 1);  // ~8 grabs per warp, whole tiles of 32 chunks
+    grab = grab < 32 ? 32 : (grab > 1024 ? 1024 : grab / 32 * 32);
     CU(cudaMemsetAsync(ls.ctr, 0, 4 * sizeof(unsigned long long), st));
-    kern<<<grid, kQueryBlock, 0, st>>>(idx->loc, kmers, (u64)n, (unsigned char *)out, ls.ctr, pick_chunk(n, grid, kQueryBlock), probe_ctr(idx), rs);
+    kern<<<grid, kLocBlock, smem, st>>>(idx->loc, packed, n_bases, coff, clen, roff, (u64)n_chunks, (unsigned char *)out, ls.ctr, (u32)grab, probe_ctr(idx));
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return FMSI_GPU_OK;
 }
-int launch_loc(const fmsi_gpu_index *idx, int mode, int strands, const u64 *kmers, size_t n, void *out, LaunchScratch &ls, cudaStream_t st,
-               const ReadSrc &rs) {
+int launch_loc(const fmsi_gpu_index *idx, int mode, int strands, const u64 *packed, u64 n_bases, const u64 *coff, const u32 *clen, const u64 *roff,
+               size_t n_chunks, void *out, LaunchScratch &ls, cudaStream_t st) {
     if (mode == FMSI_GPU_MODE_ALL)
-        return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_ALL, K_STRANDS_BOTH>(idx, kmers, n, out, ls, st, rs)
-                                                : launch_loc_v<K_MODE_ALL, K_STRANDS_LAZY>(idx, kmers, n, out, ls, st, rs);
-    return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_OR, K_STRANDS_BOTH>(idx, kmers, n, out, ls, st, rs)
-                                            : launch_loc_v<K_MODE_OR, K_STRANDS_LAZY>(idx, kmers, n, out, ls, st, rs);
+        return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_ALL, K_STRANDS_BOTH>(idx, packed, n_bases, coff, clen, roff, n_chunks, out, ls, st)
+                                                : launch_loc_v<K_MODE_ALL, K_STRANDS_LAZY>(idx, packed, n_bases, coff, clen, roff, n_chunks, out, ls, st);
+    return strands == FMSI_GPU_STRANDS_BOTH ? launch_loc_v<K_MODE_OR, K_STRANDS_BOTH>(idx, packed, n_bases, coff, clen, roff, n_chunks, out, ls, st)
+                                            : launch_loc_v<K_MODE_OR, K_STRANDS_LAZY>(idx, packed, n_bases, coff, clen, roff, n_chunks, out, ls, st);
 }
 
 template <int MODE, int OUT, int STRANDS>
@@ -565,7 +572,7 @@ void ensure_loc(fmsi_gpu_index *idx, int k, size_t n_results, bool at_load) {
     idx->d_ldir = la.dir;
     idx->d_lrows = la.rows;
     idx->b_ldir = (8ull << (2 * t));
-    idx->b_lrows = (la.n_rows + 4) * sizeof(u64);
+    idx->b_lrows = (la.n_rows + 8) * sizeof(u64);
     idx->hbm_bytes += idx->b_ldir + idx->b_lrows;
     idx->loc.dir = la.dir;
     idx->loc.rows = la.rows;
@@ -1590,18 +1597,10 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
             if (e) return fail(FMSI_GPU_ERR_CUDA, std::string("long-k kernel launch: ") + cudaGetErrorString((cudaError_t)e));
             g_launches.fetch_add(2);
         } else if (via_loc) {
-            // neighbouring k-mers of a text share their bucket in the minimizer-bucketed dictionary (loc.cuh)
-            if (reads_mode) {
-                const ReadSrc rs{d_packed, d_off, d_res, (u64)n_reads, (u64)r0};
-                int e = launch_loc(idx, mode, strands, nullptr, r1 - r0, out_span, ls, q, rs);
-                if (e) return e;
-            } else {
-                extract_kmers_kernel<<<slot_blocks(r1 - r0), 256, 0, q>>>(d_packed, d_off, d_len, d_res, (u64)c0, (u64)c1, (u64)r0, (u64)r1, (u32)k, (u64)n_bases, d_slots);
-                CU(cudaGetLastError());
-                g_launches.fetch_add(1);
-                int e = launch_loc(idx, mode, strands, d_slots + r0, r1 - r0, out_span, ls, q, ReadSrc{nullptr, nullptr, nullptr, 0, 0});
-                if (e) return e;
-            }
+            // neighbouring k-mers of a text share their bucket in the minimizer-bucketed dictionary (loc.cuh): one lane per
+            // chunk (reads mode: per read), results written at their slots of d_results
+            int e = launch_loc(idx, mode, strands, d_packed, (u64)n_bases, d_off + c0, d_len + c0, d_res + c0, c1 - c0, d_results, ls, q);
+            if (e) return e;
         } else if (via_kmers && reads_mode && fold_answers(idx, k, mode, output)) {
             // the dictionary kernel cuts its k-mers out of the reads itself (one chunk per read: d_off = first base,
             // d_res = first result slot of every read)

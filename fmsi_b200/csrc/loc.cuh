@@ -12,14 +12,14 @@
 // Rows are the same as in fold.cuh — one per distinct k-mer of the index in a strand-neutral orientation, carrying the
 // states (sf, sr) of the two SA intervals from which query_kmers_single (src/fms_index.h:263-331) derives every answer —
 // but keyed and laid out differently:
-//   pick(q)   the minimizer of {q, rc(q)}: among the m-mers of both strands the one whose ordering hash (its top 26 bits)
-//             is smallest; ties go to the strand with the smaller q * C, then to the leftmost position — a rule that does
-//             not depend on which strand the caller holds. o = that strand's k-mer, pos = the m-mer's position in it
+//   pick(q)   the minimizer of {q, rc(q)}: the place whose canonical m-mer (the smaller of the m-mer and its reverse
+//             complement) has the smallest ordering hash; o = the strand on which it reads canonical, pos = its position
+//             in o (ties: loc_pick below — a rule that does not depend on which strand the caller holds)
 //   h'        a bijection of the m-mer on 2m bits (not the ordering hash: a minimum is a small number)
 //   bucket    top 2t bits of h'
 //   R         pos . h' low 2m - 2t bits . the k - m bases of o around the m-mer        (2k - 2t + pbits bits)
 //             (bucket, R) <-> o is one-to-one, so a row match is exact — no fingerprints
-//   dir[x]    first row (32 bits) | row count (22) | smallest pos (5) | pos span (5)        8 bytes per bucket
+//   dir[x]    first row (32 bits) | row count (21) | simple (1) | smallest pos (5) | pos span (5)   8 bytes per bucket
 //   rows[]    R << 4 | sf | sr << 2, sorted by (bucket, R)                                   8 bytes per distinct k-mer
 // A query reads dir[bucket]; a pos outside the bucket's range is absent at once; otherwise the bucket's rows — sorted by
 // pos first — are probed where pos interpolates to, a sector (4 rows) at a time, and bisected from there. 2-3 dependent
@@ -82,10 +82,9 @@ struct LocView {
 };
 
 constexpr u32 kLocMul1 = 0x9E3779B1u, kLocMul3 = 0xC2B2AE35u, kLocMul4 = 0x27D4EB2Fu;
-constexpr u32 kLocCandBits = 6;  // 2 w <= 34 candidates
-// ordering value of candidate `cand` (an m-mer x): top 26 bits of x * C, then the candidate's number
-__host__ __device__ __forceinline__ u32 loc_order(u32 x, u32 cand) { return ((x * kLocMul1) & ~((1u << kLocCandBits) - 1u)) | cand; }
-// a bijection of [0, 4^m), m <= 16: the key hash of an m-mer
+// ordering value of a canonical m-mer (an injection: equal values <=> equal m-mers)
+__host__ __device__ __forceinline__ u32 loc_order(u32 c) { return c * kLocMul1; }
+// a bijection of [0, 4^m), m <= 16: the key hash of a canonical m-mer
 __host__ __device__ __forceinline__ u32 loc_spread(u32 x, u32 m, u32 mask) {
     x = (x * kLocMul3) & mask;
     x ^= x >> m;
@@ -93,24 +92,48 @@ __host__ __device__ __forceinline__ u32 loc_spread(u32 x, u32 m, u32 mask) {
     x ^= x >> m;
     return x;
 }
+// reverse complement of an m-mer (m <= 16)
+__host__ __device__ __forceinline__ u32 loc_revcomp_m(u32 x, u32 m) {
+    x = ~x;
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    x = (x >> 16) | (x << 16);
+    return x >> (32 - 2 * m);
+}
 
-// The minimizer of {q, rc}: the strand it sits on (sw: not the caller's q), that strand's k-mer o, its position, its value.
+// The minimizer of the strand pair {q, rc}. At position p of q sits the m-mer x_p; the same place read on the other strand
+// is y_p = revcomp(x_p), at position w - 1 - p of rc. The place with the smallest order(min(x_p, y_p)) wins, and the k-mer
+// is oriented so that the winning m-mer reads as its canonical (smaller) form: (o, pos) = (q, p) if x_p < y_p, (rc, w-1-p)
+// if y_p < x_p. Ties — the same canonical m-mer at several places, or a palindromic one (x_p == y_p: both orientations) —
+// go to the candidate (o, pos) with the smallest pos, then to the strand with the smaller q * C: a rule stated in terms of
+// the physical strands, so both strands of a pair pick the same (o, pos).
+// Returns the canonical m-mer x, o, pos and sw (o is not the caller's q).
 __host__ __device__ __forceinline__ void loc_pick(u64 q, u64 rc, const LocGeom &g, u32 &x, u32 &pos, bool &sw, u64 &o) {
-    const bool fs = rc * kFoldMul < q * kFoldMul;
-    const u64 a = fs ? rc : q, b = fs ? q : rc;
     const u32 mask = g.m < 16 ? (1u << (2 * g.m)) - 1u : 0xFFFFFFFFu;
     u32 best = 0xFFFFFFFFu;
     for (u32 p = 0; p < g.w; ++p) {
-        const u32 va = loc_order((u32)(a >> (g.fbits - 2 * p)) & mask, p);
-        const u32 vb = loc_order((u32)(b >> (g.fbits - 2 * p)) & mask, g.w + p);
-        best = va < best ? va : best;
-        best = vb < best ? vb : best;
+        const u32 xf = (u32)(q >> (g.fbits - 2 * p)) & mask, yr = (u32)(rc >> (2 * p)) & mask;
+        const u32 v = loc_order(xf < yr ? xf : yr);
+        best = v < best ? v : best;
     }
-    const u32 cand = best & ((1u << kLocCandBits) - 1u);
-    const bool bs = cand >= g.w;
-    pos = bs ? cand - g.w : cand;
-    sw = fs != bs;
-    o = bs ? b : a;
+    const u32 lq = (rc * kFoldMul < q * kFoldMul) ? 1u : 0u;  // label of strand q (0 = the strand with the smaller q * C)
+    u32 bkey = 0xFFFFFFFFu;
+    for (u32 p = 0; p < g.w; ++p) {
+        const u32 xf = (u32)(q >> (g.fbits - 2 * p)) & mask, yr = (u32)(rc >> (2 * p)) & mask;
+        if (loc_order(xf < yr ? xf : yr) != best) continue;
+        if (xf <= yr) {  // candidate (q, p)
+            const u32 key = 2 * p + lq;
+            bkey = key < bkey ? key : bkey;
+        }
+        if (yr <= xf) {  // candidate (rc, w - 1 - p)
+            const u32 key = 2 * (g.w - 1 - p) + (1u - lq);
+            bkey = key < bkey ? key : bkey;
+        }
+    }
+    pos = bkey >> 1;
+    sw = (bkey & 1u) != lq;
+    o = sw ? rc : q;
     x = (u32)(o >> (g.fbits - 2 * pos)) & mask;
 }
 // bucket and R of a pick
@@ -127,10 +150,11 @@ __host__ __device__ __forceinline__ void loc_key(u32 x, u32 pos, u64 o, const Lo
 }
 __host__ __device__ __forceinline__ u32 loc_pos_of_row(u64 row, const LocGeom &g) { return (u32)((row >> 4) >> (g.hlow + g.fbits)); }
 
-// directory entry
-constexpr u32 kLocCountBits = 22;
-__host__ __device__ __forceinline__ u64 loc_dir_entry(u32 first, u32 count, u32 pmin, u32 pspan) {
-    return (u64)first | ((u64)count << 32) | ((u64)pmin << 54) | ((u64)pspan << 59);
+// directory entry: first row (32) | rows (21) | simple (1) | smallest pos (5) | pos span (5). simple = exactly one row for
+// every pos of the range, so the row of a pos is first + (pos - smallest pos), and a mismatch there means absent.
+constexpr u32 kLocCountBits = 21;
+__host__ __device__ __forceinline__ u64 loc_dir_entry(u32 first, u32 count, bool simple, u32 pmin, u32 pspan) {
+    return (u64)first | ((u64)count << 32) | ((u64)simple << 53) | ((u64)pmin << 54) | ((u64)pspan << 59);
 }
 
 // ------------------------------------------------------------------------------------------- build
@@ -228,7 +252,9 @@ __global__ void loc_dir_kernel(const u32 *__restrict__ bfirst, const u32 *__rest
     }
     if (cnt >> kLocCountBits) atomicExch(too_many, 1u);
     const u32 pmin = loc_pos_of_row(rows[bfirst[x]], g), pmax = loc_pos_of_row(rows[bfirst[x] + cnt - 1], g);  // rows are sorted by pos first
-    dir[x] = loc_dir_entry((u32)(g0 + bfirst[x]), cnt, pmin, pmax - pmin);
+    bool simple = cnt == pmax - pmin + 1;
+    for (u32 j = 1; simple && j + 1 < cnt; ++j) simple = loc_pos_of_row(rows[bfirst[x] + j], g) == pmin + j;
+    dir[x] = loc_dir_entry((u32)(g0 + bfirst[x]), cnt, simple, pmin, pmax - pmin);
 }
 
 struct LocArrays {  // device arrays of a built tier (ownership passes to the caller)
@@ -300,7 +326,7 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
     DevArr<u64> dir(total);
     DevArr<u32> too_many(1);
     BCU(cudaMemset(too_many.p, 0, 4));
-    DevArr<u64> rows(sum + 4);  // rows <= valid runs
+    DevArr<u64> rows(sum + 8);  // rows <= valid runs; a probe reads up to 8 rows from a sector boundary
     DevArr<u32> sel(max_mp + 1), gs(max_mp + 1);
     DevArr<u64> keys(max_mp), vals(max_mp), keys_alt(max_mp), vals_alt(max_mp);
     DevArr<u32> bfirst(nb), bcount(nb);
@@ -333,9 +359,9 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
     {
         u32 h_too_many = 0;
         BCU(cudaMemcpy(&h_too_many, too_many.p, 4, cudaMemcpyDeviceToHost));
-        if (h_too_many) throw std::runtime_error("a minimizer is shared by more than 2^22 distinct k-mers");
+        if (h_too_many) throw std::runtime_error("a minimizer is shared by more than 2^21 distinct k-mers");
     }
-    BCU(cudaMemset(rows.p + G0, 0xff, (sum + 4 - G0) * sizeof(u64)));  // a sector read may run past the last row
+    BCU(cudaMemset(rows.p + G0, 0xff, (sum + 8 - G0) * sizeof(u64)));  // a probe may run past the last row
     sel.release();
     gs.release();
     keys.release();
@@ -346,9 +372,9 @@ inline void build_loc_on_device(const DevIndex &d, const u64 counts[4], u32 k, u
     heads.release();
     pass_of.release();
     if (G0 * 10 < sum * 9) {  // far fewer rows than runs: exact-size rows
-        DevArr<u64> exact(G0 + 4);
+        DevArr<u64> exact(G0 + 8);
         BCU(cudaMemcpy(exact.p, rows.p, G0 * sizeof(u64), cudaMemcpyDeviceToDevice));
-        BCU(cudaMemset(exact.p + G0, 0xff, 4 * sizeof(u64)));
+        BCU(cudaMemset(exact.p + G0, 0xff, 8 * sizeof(u64)));
         std::swap(exact.p, rows.p);
         std::swap(exact.n, rows.n);
     }
@@ -368,185 +394,296 @@ __device__ __forceinline__ u64 ld_loc_dir(const u64 *p) {
     return r;
 }
 
-// One tile = 32 consecutive queries of the launch, one per lane, walked in lockstep: DIR (the bucket's entry), then SEARCH
-// rounds until every lane has its row (or knows there is none). Lanes that hold neighbouring k-mers of a read ask for the
-// same directory entry and the same row sectors in the same instruction, which the load unit merges.
-struct LocTile {
-    u64 R;       // the lane's key inside its bucket
-    u32 lo, hi;  // SEARCH: rows still possible; DIR: lo = bucket
-    u32 r0;      // SEARCH: first row of the sector to probe
-    u32 st;      // the answer: sf | sr << 2 (0 = absent)
-    u32 pos;
-    bool active, swapped;
-};
+// The query kernel gives every LANE a chunk of text (a read) and walks it k-mer by k-mer; the 32 lanes of a warp start 32
+// chunks together. What makes a k-mer cheap:
+//   * the minimizer is kept ROLLING: one new m-mer (both strands) per k-mer, its ordering value pushed into a per-lane
+//     ring in shared memory; the window minimum is updated in O(1), and rescanned from the ring only when it leaves the
+//     window. Ties (equal canonical m-mers in one window, palindromic m-mers) are rare and go through loc_pick, the one
+//     exact definition;
+//   * the bucket of a minimizer is resolved once (DIR: one 8-byte entry) and serves the whole run of k-mers that share
+//     it; a `simple` bucket then costs one 8-byte row per k-mer, any other an 8-row window where pos interpolates to,
+//     bisected on if need be — lines the lane has just touched, so they mostly come from L1 / L2;
+//   * a pos outside the bucket's range, or an empty bucket, is absent without touching the rows.
+// Per k-mer that is a fraction of a DRAM request (the directory entry and the rows of a run are fetched once) and a few
+// dozen instructions per lane, against one DRAM request per k-mer in fold.cuh.
+constexpr int kLocBlock = 256;
 
-// Presence outputs only (K_OUT_PRESENCE). Queries come from a k-mer array whose neighbours are neighbouring k-mers of
-// a text (extract_kmers_kernel) or straight from reads (ReadSrc), as in fold_query_kernel. Every warp keeps TWO tiles in
-// flight (a lane has two independent requests outstanding).
+__device__ __forceinline__ void loc_probe8(const u64 *rows, u32 r0, u64 (&v)[8]) {
+    ld_sector_l1(rows + r0, v[0], v[1], v[2], v[3]);
+    ld_sector_l1(rows + r0 + 4, v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ u64 ld_loc_row(const u64 *p) {
+    u64 r;
+    asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+// first row of the 8-row window (sector aligned) around row c of [lo, hi)
+__device__ __forceinline__ u32 loc_window(u32 c, u32 lo) {
+    u32 r0 = (c >= 2u ? c - 2u : 0u) & ~3u;
+    const u32 l4 = lo & ~3u;
+    return r0 < l4 ? l4 : r0;
+}
+// rows [r0, r0 + 8) against R4 = R << 4 inside [lo, hi): true = settled (st = the row's states, 0 = no such row); else
+// [lo, hi) shrinks. A row is key << 4 | states, so key < R <=> row < R4 and key == R <=> R4 <= row < R4 + 16.
+__device__ __forceinline__ bool loc_consume8(const u64 (&v)[8], u32 r0, u64 R4, u32 &lo, u32 &hi, u32 &st) {
+    const u32 w0 = r0 > lo ? r0 : lo, w1 = (r0 + 8 < hi) ? r0 + 8 : hi;
+    const u32 vm = ((1u << (w1 - r0)) - 1u) & ~((1u << (w0 - r0)) - 1u);  // rows of the window that belong to [lo, hi)
+    u32 n_lt = 0;
+    bool found = false;
+#pragma unroll
+    for (u32 e = 0; e < 8; ++e) {
+        const bool valid = (vm >> e) & 1u;
+        n_lt += (u32)(valid && v[e] < R4);
+        if (valid && (v[e] - R4) < 16ull) {
+            found = true;
+            st = (u32)v[e] & 15u;
+        }
+    }
+    if (found) return true;
+    if (n_lt == w1 - w0) lo = w1;  // every row of the window is smaller
+    else if (n_lt == 0) hi = w0;   // every row is larger
+    else return true;              // R falls between two rows: absent
+    return lo >= hi;
+}
+
 template <int MODE, int STRANDS>
-__global__ void __launch_bounds__(kQueryBlock)
-loc_query_kernel(const LocView lv, const u64 *__restrict__ kmers, const u64 n, unsigned char *__restrict__ out,
-                 unsigned long long *__restrict__ cursor, const u32 chunk, unsigned long long *__restrict__ probe_ctr, const ReadSrc rs) {
+__device__ __forceinline__ unsigned char loc_result(u32 st, bool swapped) {
+    u32 sf = st & 3u, sr = st >> 2;
+    if (swapped) {
+        const u32 x = sf;
+        sf = sr;
+        sr = x;
+    }
+    const int vf = fold_presence<MODE>(sf), vr = fold_presence<MODE>(sr);
+    if (STRANDS == K_STRANDS_BOTH) return (unsigned char)((vf + 1) | ((vr + 1) << 2));
+    if (MODE == K_MODE_ALL) return (unsigned char)((vf != -1 ? vf : vr) == 1);  // fms_index.h:294-298
+    return (unsigned char)(vf == 1 || vr == 1);                                  // :289-293
+}
+
+enum { LS_NEW = 0, LS_DIR = 1, LS_LOOK = 2, LS_PROBE = 3, LS_ROW = 4, LS_END = 5 };
+
+// Presence outputs only (K_OUT_PRESENCE). Chunk c = bases [coff[c], coff[c] + clen[c]) of the 2-bit packed text; its k-mers
+// go to result slots roff[c], roff[c] + 1, ... (the layout of stream_kernel; chunks may be of any length here).
+// Dynamic shared memory: 2 * w * blockDim u32 (the rings).
+template <int MODE, int STRANDS>
+__global__ void __launch_bounds__(kLocBlock)
+loc_stream_kernel(const LocView lv, const u64 *__restrict__ packed, const u64 n_bases, const u64 *__restrict__ coff,
+                  const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks, unsigned char *__restrict__ out,
+                  unsigned long long *__restrict__ cursor, const u32 grab, unsigned long long *__restrict__ probe_ctr) {
+    extern __shared__ u32 loc_ring[];
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const LocGeom g = lv.g;
-    const u32 k = g.k;
-    const bool from_reads = rs.text != nullptr;
+    const u32 k = g.k, W = g.w, m = g.m;
+    const u32 mask = m < 16 ? (1u << (2 * m)) - 1u : 0xFFFFFFFFu;
+    const u64 kmask = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
+    u32 *ring_o = loc_ring + threadIdx.x;                          // ring_o[(j % W) * blockDim]: ordering value of m-mer j
+    u32 *ring_x = loc_ring + (size_t)W * blockDim.x + threadIdx.x;  // its forward m-mer
+    const u32 rs = blockDim.x;
 
-    u64 cnext = 0, cend = 0;  // the warp's grab: queries [cnext, cend) are still to be started (warp-uniform)
-    u64 rd_hint = 0;          // from_reads: a read at or before the one of query cnext
-    bool exhausted = false;
-
-    LocTile T[2];
-    u64 tbase[2] = {0, 0};  // first query of the tile
-    u32 phase[2] = {2, 2};  // 0 = DIR, 1 = SEARCH, 2 = empty (warp-uniform)
-    // the NEXT tile, prepared while the loads of the current ones are in flight: k-mers fetched, minimizers picked
-    LocTile P;
-    u64 pbase = 0;
-    bool pvalid = false;
-
-    auto count_requests = [&](bool mine, const void *addr) {  // requests after merging: distinct 128-byte lines of a warp instruction
-        if (!probe_ctr) return;
-        const unsigned act = __ballot_sync(FULL, mine);
-        if (mine) {
-            const unsigned same = __match_any_sync(act, (unsigned long long)addr >> 7);
-            if ((u32)(__ffs(same) - 1) == lane) atomicAdd(probe_ctr, 1ull);
-        }
-    };
-    auto write_result = [&](const LocTile &t, u64 q) {
-        u32 sf = t.st & 3u, sr = t.st >> 2;
-        if (t.swapped) {
-            const u32 x = sf;
-            sf = sr;
-            sr = x;
-        }
-        const int vf = fold_presence<MODE>(sf), vr = fold_presence<MODE>(sr);
-        unsigned char v;
-        if (STRANDS == K_STRANDS_BOTH) v = (unsigned char)((vf + 1) | ((vr + 1) << 2));
-        else if (MODE == K_MODE_ALL) v = (unsigned char)((vf != -1 ? vf : vr) == 1);  // fms_index.h:294-298
-        else v = (unsigned char)(vf == 1 || vr == 1);                                  // :289-293
-        out[q] = v;
-    };
-    // prepare the next tile: fetch its k-mers, pick the minimizers (P.lo = bucket)
-    auto prepare = [&]() {
-        if (cnext >= cend) {
-            unsigned long long c0 = 0;
-            if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)chunk);
-            c0 = __shfl_sync(FULL, c0, 0);
-            if (c0 >= n) {
-                exhausted = true;
-                return;
-            }
-            cnext = c0;
-            cend = (c0 + chunk < n) ? c0 + chunk : n;
-            rd_hint = 0;
-        }
-        const u64 q = cnext + lane;
-        const bool have = q < cend;
-        u64 km = 0;
-        if (have) {
-            if (!from_reads) {
-                km = kmers[q];
-            } else {
-                const u64 slot = rs.slot0 + q;
-                const u64 r = read_of_slot(rs, slot, rd_hint);
-                km = window64(rs.text, __ldg(rs.roff + r) + (slot - __ldg(rs.rbase + r)), k);
-                if (lane == 0) rd_hint = r;
-            }
-        }
-        if (from_reads) rd_hint = __shfl_sync(FULL, rd_hint, 0);  // lane 0 holds the tile's first query
-        P.active = have;
-        P.st = 0;
-        if (have) {
-            if (k < 32) km &= (1ull << (2 * k)) - 1ull;
-            u32 x;
-            u64 o;
-            loc_pick(km, revcomp_packed(km, k), g, x, P.pos, P.swapped, o);
-            loc_key(x, P.pos, o, g, P.lo, P.R);
-        }
-        pbase = cnext;
-        pvalid = true;
-        cnext = (cnext + 32 < cend) ? cnext + 32 : cend;
-    };
+    u64 wnext = 0, wend = 0;  // the warp's grab of chunks (warp-uniform)
+    u32 nprobe = 0;
 
     for (;;) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-            if (phase[s] == 2 && pvalid) {
-                T[s] = P;
-                tbase[s] = pbase;
-                phase[s] = 0;
-                pvalid = false;
-            }
-        if (phase[0] == 2 && phase[1] == 2 && exhausted) break;
-
-        // ---------------------------------------------------------------- issue both tiles' loads
-        u64 de[2] = {0, 0};
-        u64 a0[2], a1[2], a2[2], a3[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            a0[s] = a1[s] = a2[s] = a3[s] = 0;
-            const bool on = phase[s] != 2 && T[s].active;
-            if (on && phase[s] == 0) de[s] = ld_loc_dir(lv.dir + T[s].lo);
-            if (on && phase[s] == 1) ld_sector_l1(lv.rows + T[s].r0, a0[s], a1[s], a2[s], a3[s]);
-            if (phase[s] != 2) count_requests(on, phase[s] == 0 ? (const void *)(lv.dir + T[s].lo) : (const void *)(lv.rows + T[s].r0));
+        // ---------------------------------------------------------------- 32 chunks, one per lane
+        if (wnext >= wend) {
+            unsigned long long c0 = 0;
+            if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)grab);
+            c0 = __shfl_sync(FULL, c0, 0);
+            if (c0 >= n_chunks) break;
+            wnext = c0;
+            wend = (c0 + grab < n_chunks) ? c0 + grab : n_chunks;
         }
-        // ---------------------------------------------------------------- meanwhile: the next tile
-        if (!pvalid && !exhausted) prepare();
+        const u64 c = wnext + lane;
+        wnext = (wnext + 32 < wend) ? wnext + 32 : wend;
+        u64 tpos = 0, res0 = 0;
+        u32 nk = 0;
+        if (c < wend) {
+            const u64 s0 = __ldg(coff + c);
+            const u32 len = __ldg(clen + c);
+            res0 = __ldg(roff + c);
+            if (len >= k && s0 + len <= n_bases) {
+                nk = len - k + 1;
+                tpos = s0;
+            }
+        }
+        if (!__any_sync(FULL, nk != 0)) continue;
+        // ---------------------------------------------------------------- the first k-mer, its w m-mers into the ring
+        u64 kf = nk ? window64(packed, tpos, k) : 0ull;
+        u64 kr = revcomp_packed(kf, k);
+        tpos += k;            // next base to take
+        u64 tbuf = 0;         // upcoming bases, first one highest
+        u32 tleft = 0;
+        u32 min_o = 0xFFFFFFFFu, min_j = 0;
+        bool tie = false;
+        for (u32 p = 0; p < W; ++p) {
+            const u32 xf = (u32)(kf >> (g.fbits - 2 * p)) & mask, yr = (u32)(kr >> (2 * p)) & mask;
+            const u32 ov = loc_order(xf < yr ? xf : yr);
+            ring_o[p * rs] = ov;
+            ring_x[p * rs] = xf;
+            if (ov < min_o) {
+                min_o = ov;
+                min_j = p;
+                tie = false;
+            } else if (ov == min_o) {
+                tie = true;
+            }
+        }
+        u32 i = 0;                // current k-mer of the chunk; its m-mers are j = i .. i + W - 1
+        u32 slot_w = W % W;       // ring slot of m-mer i + W (the next one to arrive) = (i + W) % W = i % W
+        u32 slot_i = 0;           // ring slot of m-mer i
+        // derived from the current minimizer (valid while cached_j == min_j)
+        u32 cached_j = 0xFFFFFFFFu, bucket = 0, hl = 0, d_first = 0, d_cnt = 0, d_pmin = 0, d_pspan = 0;
+        bool fwd = true, pal = false, dir_valid = false, d_simple = false;
+        // the current k-mer's search
+        u32 stage = nk ? LS_NEW : LS_END, lo = 0, hi = 0, r0 = 0, pos = 0, qbucket = 0;
+        u64 R4 = 0;
+        bool sw = false, slow = false;
 
-        // ---------------------------------------------------------------- consume
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (phase[s] == 2) continue;
-            LocTile &t = T[s];
-            bool done = false;
-            if (t.active && phase[s] == 0) {
-                const u32 first = (u32)de[s], cnt = (u32)(de[s] >> 32) & ((1u << kLocCountBits) - 1u);
-                const u32 pmin = (u32)(de[s] >> 54) & 31u, pspan = (u32)(de[s] >> 59);
-                if (cnt == 0 || t.pos < pmin || t.pos > pmin + pspan) {
-                    done = true;  // empty bucket, or no row of it has the minimizer at this position
-                } else {
-                    t.lo = first;
-                    t.hi = first + cnt;
-                    // rows are sorted by pos first: start where pos interpolates to
-                    const u32 guess = first + (u32)(((u64)(2 * (t.pos - pmin) + 1) * cnt) / (2 * (pspan + 1)));
-                    t.r0 = (guess < t.hi ? guess : t.hi - 1) & ~3u;
-                }
-            } else if (t.active) {
-                // invariant: rows before lo are smaller than R, rows from hi on are larger
-                const u32 r0 = t.r0;
-                const u32 w0 = r0 > t.lo ? r0 : t.lo, w1 = (r0 + 4 < t.hi) ? r0 + 4 : t.hi;
-                bool found = false;
-                u64 first = 0, last = 0;
-#pragma unroll
-                for (u32 e = 0; e < 4; ++e) {
-                    const u64 rw = e == 0 ? a0[s] : e == 1 ? a1[s] : e == 2 ? a2[s] : a3[s];
-                    const u32 r = r0 + e;
-                    if (r >= w0 && r < w1) {
-                        const u64 key = rw >> 4;
-                        if (r == w0) first = key;
-                        last = key;
-                        if (key == t.R) {
-                            found = true;
-                            t.st = (u32)rw & 15u;
+        while (__any_sync(FULL, stage != LS_END)) {
+            // ------------------------------------------------------------ a new k-mer: minimizer, key, what to load
+            if (stage == LS_NEW) {
+                if (min_j < i) {  // the minimum left the window: rescan the ring (m-mers i .. i + W - 1)
+                    min_o = 0xFFFFFFFFu;
+                    tie = false;
+                    u32 sl = slot_i;
+                    for (u32 p = 0; p < W; ++p) {
+                        const u32 ov = ring_o[sl * rs];
+                        if (ov < min_o) {
+                            min_o = ov;
+                            min_j = i + p;
+                            tie = false;
+                        } else if (ov == min_o) {
+                            tie = true;
                         }
+                        sl = sl + 1 == W ? 0 : sl + 1;
                     }
                 }
-                if (found) done = true;
-                else if (last < t.R) t.lo = w1;
-                else if (first > t.R) t.hi = w0;
-                else done = true;  // R falls between two rows of this sector: absent
-                if (!done && t.lo >= t.hi) done = true;
-                if (!done) t.r0 = (t.lo + ((t.hi - t.lo) >> 1)) & ~3u;
+                if (cached_j != min_j) {  // another minimizer: its canonical form, bucket
+                    u32 sl = slot_i + (min_j - i);
+                    sl = sl >= W ? sl - W : sl;
+                    const u32 xf = ring_x[sl * rs], yr = loc_revcomp_m(xf, m);
+                    fwd = xf < yr;
+                    pal = xf == yr;
+                    const u32 h = loc_spread(fwd ? xf : yr, m, mask);
+                    bucket = h >> g.hlow;
+                    hl = g.hlow ? (h & ((1u << g.hlow) - 1u)) : 0u;
+                    dir_valid = false;
+                    cached_j = min_j;
+                }
+                u64 o;
+                slow = tie || pal;
+                if (slow) {  // the exact definition decides (and may pick another bucket)
+                    u32 x;
+                    u64 R;
+                    loc_pick(kf, kr, g, x, pos, sw, o);
+                    loc_key(x, pos, o, g, qbucket, R);
+                    R4 = R << 4;
+                    stage = LS_DIR;
+                } else {
+                    const u32 p = min_j - i;
+                    pos = fwd ? p : W - 1 - p;
+                    o = fwd ? kf : kr;
+                    sw = !fwd;
+                    const u32 rl = g.fbits - 2 * pos;
+                    const u64 right = rl ? (o & ((1ull << rl) - 1ull)) : 0ull;
+                    const u64 left = pos ? (o >> (2 * (k - pos))) : 0ull;
+                    const u64 flanks = rl ? ((left << rl) | right) : left;
+                    R4 = ((((u64)pos << g.hlow) | (u64)hl) << g.fbits | flanks) << 4;
+                    qbucket = bucket;
+                    stage = dir_valid ? LS_LOOK : LS_DIR;
+                }
             }
-            if (done) {
-                write_result(t, tbase[s] + lane);
-                t.active = false;
+            // with the bucket's entry at hand: absent at once, or where to look
+            bool settled = false;
+            u32 st = 0;
+            if (stage == LS_LOOK) {
+                if (d_cnt == 0 || pos < d_pmin || pos > d_pmin + d_pspan) {
+                    settled = true;
+                } else if (d_simple) {
+                    r0 = d_first + (pos - d_pmin);
+                    stage = LS_ROW;
+                } else {
+                    lo = d_first;
+                    hi = d_first + d_cnt;
+                    r0 = loc_window(d_first + ((2 * (pos - d_pmin) + 1) * d_cnt) / (2 * (d_pspan + 1)), lo);
+                    stage = LS_PROBE;
+                }
             }
-            if (phase[s] == 0) phase[s] = 1;
-            if (!__any_sync(FULL, t.active)) phase[s] = 2;
+            // ------------------------------------------------------------ one load per lane
+            u64 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            u64 de = 0;
+            const bool isD = stage == LS_DIR, isP = stage == LS_PROBE, isR = stage == LS_ROW;
+            if (isD) de = ld_loc_dir(lv.dir + qbucket);
+            if (isP) loc_probe8(lv.rows, r0, v);
+            if (isR) v[0] = ld_loc_row(lv.rows + r0);
+            nprobe += (u32)(isD || isP || isR);
+            // ------------------------------------------------------------ consume
+            if (isD) {
+                const u32 first = (u32)de, cnt = (u32)(de >> 32) & ((1u << kLocCountBits) - 1u);
+                const bool simple = (de >> 53) & 1ull;
+                const u32 pmin = (u32)(de >> 54) & 31u, pspan = (u32)(de >> 59);
+                if (!slow) {
+                    d_first = first;
+                    d_cnt = cnt;
+                    d_simple = simple;
+                    d_pmin = pmin;
+                    d_pspan = pspan;
+                    dir_valid = true;
+                    stage = LS_LOOK;  // decided at the top of the next round, which also issues the probe
+                } else if (cnt == 0 || pos < pmin || pos > pmin + pspan) {
+                    settled = true;
+                } else {
+                    lo = first;
+                    hi = first + cnt;
+                    r0 = loc_window(first + ((2 * (pos - pmin) + 1) * cnt) / (2 * (pspan + 1)), lo);
+                    stage = LS_PROBE;  // an ordinary bisection from here on (the cached entry stays the window minimum's)
+                }
+            } else if (isP) {
+                if (loc_consume8(v, r0, R4, lo, hi, st)) settled = true;
+                else r0 = loc_window(lo + ((hi - lo) >> 1), lo);
+            } else if (isR) {
+                if ((v[0] - R4) < 16ull) st = (u32)v[0] & 15u;
+                settled = true;
+            }
+            // ------------------------------------------------------------ result, next k-mer
+            if (settled) {
+                out[res0 + i] = loc_result<MODE, STRANDS>(st, sw);
+                ++i;
+                slot_i = slot_i + 1 == W ? 0 : slot_i + 1;
+                if (i >= nk) {
+                    stage = LS_END;
+                } else {
+                    if (tleft == 0) {
+                        tbuf = window64(packed, tpos, 32);
+                        tleft = 32;
+                    }
+                    const u32 b = (u32)(tbuf >> 62);
+                    tbuf <<= 2;
+                    --tleft;
+                    ++tpos;
+                    kf = ((kf << 2) | b) & kmask;
+                    kr = (kr >> 2) | ((u64)(3u - b) << (2 * (k - 1)));
+                    const u32 xf = (u32)kf & mask, yr = (u32)(kr >> g.fbits) & mask;  // the m-mer that entered: j = i + W - 1
+                    const u32 ov = loc_order(xf < yr ? xf : yr);
+                    ring_o[slot_w * rs] = ov;
+                    ring_x[slot_w * rs] = xf;
+                    slot_w = slot_w + 1 == W ? 0 : slot_w + 1;
+                    if (ov < min_o) {
+                        min_o = ov;
+                        min_j = i + W - 1;
+                        tie = false;
+                    } else if (ov == min_o) {
+                        tie = true;
+                    }
+                    stage = LS_NEW;
+                }
+            }
         }
     }
+    count_probes(probe_ctr, nprobe);
 }
+
+inline size_t loc_stream_smem(const LocGeom &g, int block = kLocBlock) { return (size_t)2 * g.w * block * sizeof(u32); }
 
 }  // namespace fmsi

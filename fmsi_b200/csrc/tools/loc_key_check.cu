@@ -57,12 +57,13 @@ int main(int argc, char **argv) {
         if ((u64)b1 >> (2 * t)) ++bad;
         if (g.rbits < 64 && (R1 >> g.rbits)) ++bad;
         if (p1 >= g.w) ++bad;
-        const u32 omask = ~((1u << kLocCandBits) - 1u);
-        for (u32 p = 0; p < g.w; ++p) {  // the pick is a minimum (of the ordering value's hash part) over both strands
-            if ((loc_order((u32)(q >> (g.fbits - 2 * p)) & mmask, 0) & omask) < (loc_order(h1, 0) & omask)) ++bad;
-            if ((loc_order((u32)(rc >> (g.fbits - 2 * p)) & mmask, 0) & omask) < (loc_order(h1, 0) & omask)) ++bad;
+        for (u32 p = 0; p < g.w; ++p) {  // the pick is a minimum over the canonical m-mers of every place
+            const u32 xf = (u32)(q >> (g.fbits - 2 * p)) & mmask, yr = loc_revcomp_m(xf, m);
+            if (yr != ((u32)(rc >> (2 * p)) & mmask)) ++bad;  // the same place read on the other strand
+            if (loc_order(xf < yr ? xf : yr) < loc_order(h1)) ++bad;
         }
-        if (((u32)(o1 >> (g.fbits - 2 * p1)) & mmask) != h1) ++bad;  // h1 = the m-mer itself
+        if (((u32)(o1 >> (g.fbits - 2 * p1)) & mmask) != h1) ++bad;  // h1 = the m-mer of o at pos ...
+        if (h1 > loc_revcomp_m(h1, m)) ++bad;                          // ... in its canonical form
         if (!samples) {
             const u64 canon = q < rc ? q : rc;
             auto r = seen.emplace(std::make_pair(b1, R1), canon);
