@@ -395,22 +395,32 @@ __device__ __forceinline__ u64 ld_loc_dir(const u64 *p) {
 }
 
 // The query kernel gives every LANE a chunk of text (a read) and walks it k-mer by k-mer; the 32 lanes of a warp start 32
-// chunks together. What makes a k-mer cheap:
-//   * the minimizer is kept ROLLING: one new m-mer (both strands) per k-mer, its ordering value pushed into a per-lane
-//     ring in shared memory; the window minimum is updated in O(1), and rescanned from the ring only when it leaves the
-//     window. Ties (equal canonical m-mers in one window, palindromic m-mers) are rare and go through loc_pick, the one
-//     exact definition;
-//   * the bucket of a minimizer is resolved once (DIR: one 8-byte entry) and serves the whole run of k-mers that share
-//     it; a `simple` bucket then costs one 8-byte row per k-mer, any other an 8-row window where pos interpolates to,
-//     bisected on if need be — lines the lane has just touched, so they mostly come from L1 / L2;
-//   * a pos outside the bucket's range, or an empty bucket, is absent without touching the rows.
-// Per k-mer that is a fraction of a DRAM request (the directory entry and the rows of a run are fetched once) and a few
-// dozen instructions per lane, against one DRAM request per k-mer in fold.cuh.
+// chunks together and stay in LOCKSTEP — every lane is at the same k-mer number, in the same code — so the warp's
+// instructions are spent on 32 k-mers each. What makes a k-mer cheap:
+//   * the minimizer is kept ROLLING: one new m-mer per k-mer. Its ordering value (top 26 bits) goes into a per-lane ring
+//     in shared memory; the ring is cut into blocks of w m-mers, and the minimum of a window is the better of a suffix
+//     minimum of the previous block (computed in place when the block completes: one loop for the whole warp) and the
+//     running prefix minimum of the current one. Ties — equal ordering bits in one window, palindromic m-mers — are rare
+//     and go through loc_pick, the one exact definition;
+//   * a k-mer is two loads, and the loads of neighbouring k-mers overlap: while k-mer i's rows and k-mer i + 1's directory
+//     entry are in flight, k-mer i + 2 is rolled and keyed. The k-mers of a run share their bucket, so its directory entry
+//     and rows come from DRAM once and from L1 / L2 afterwards;
+//   * a pos outside the bucket's range, or an empty bucket, is absent without touching the rows; a lane whose 8-row
+//     window does not settle its k-mer (a bucket of many rows) parks that search in a per-warp queue in shared memory,
+//     and whenever 32 are waiting the warp finishes them together by bisection — nobody waits for a neighbour.
+// Per k-mer that is a fraction of a DRAM request and a few instructions per lane, against one DRAM request in fold.cuh.
 constexpr int kLocBlock = 256;
+#ifndef FMSI_LOC_MINBLOCKS
+#define FMSI_LOC_MINBLOCKS 2
+#endif
+#ifndef FMSI_LOC_ROWS
+#define FMSI_LOC_ROWS 8
+#endif
+constexpr u32 kLocRows = FMSI_LOC_ROWS;  // rows per probe: 8 (two sectors) or 4 (one)
 
-__device__ __forceinline__ void loc_probe8(const u64 *rows, u32 r0, u64 (&v)[8]) {
+__device__ __forceinline__ void loc_probe8(const u64 *rows, u32 r0, u64 (&v)[kLocRows]) {
     ld_sector_l1(rows + r0, v[0], v[1], v[2], v[3]);
-    ld_sector_l1(rows + r0 + 4, v[4], v[5], v[6], v[7]);
+    if (kLocRows == 8) ld_sector_l1(rows + r0 + 4, v[kLocRows - 4], v[kLocRows - 3], v[kLocRows - 2], v[kLocRows - 1]);
 }
 __device__ __forceinline__ u64 ld_loc_row(const u64 *p) {
     u64 r;
@@ -419,19 +429,20 @@ __device__ __forceinline__ u64 ld_loc_row(const u64 *p) {
 }
 // first row of the 8-row window (sector aligned) around row c of [lo, hi)
 __device__ __forceinline__ u32 loc_window(u32 c, u32 lo) {
+    if (kLocRows == 4) return c & ~3u;
     u32 r0 = (c >= 2u ? c - 2u : 0u) & ~3u;
     const u32 l4 = lo & ~3u;
     return r0 < l4 ? l4 : r0;
 }
 // rows [r0, r0 + 8) against R4 = R << 4 inside [lo, hi): true = settled (st = the row's states, 0 = no such row); else
 // [lo, hi) shrinks. A row is key << 4 | states, so key < R <=> row < R4 and key == R <=> R4 <= row < R4 + 16.
-__device__ __forceinline__ bool loc_consume8(const u64 (&v)[8], u32 r0, u64 R4, u32 &lo, u32 &hi, u32 &st) {
-    const u32 w0 = r0 > lo ? r0 : lo, w1 = (r0 + 8 < hi) ? r0 + 8 : hi;
+__device__ __forceinline__ bool loc_consume8(const u64 (&v)[kLocRows], u32 r0, u64 R4, u32 &lo, u32 &hi, u32 &st) {
+    const u32 w0 = r0 > lo ? r0 : lo, w1 = (r0 + kLocRows < hi) ? r0 + kLocRows : hi;
     const u32 vm = ((1u << (w1 - r0)) - 1u) & ~((1u << (w0 - r0)) - 1u);  // rows of the window that belong to [lo, hi)
     u32 n_lt = 0;
     bool found = false;
 #pragma unroll
-    for (u32 e = 0; e < 8; ++e) {
+    for (u32 e = 0; e < kLocRows; ++e) {
         const bool valid = (vm >> e) & 1u;
         n_lt += (u32)(valid && v[e] < R4);
         if (valid && (v[e] - R4) < 16ull) {
@@ -460,29 +471,73 @@ __device__ __forceinline__ unsigned char loc_result(u32 st, bool swapped) {
     return (unsigned char)(vf == 1 || vr == 1);                                  // :289-293
 }
 
-enum { LS_NEW = 0, LS_DIR = 1, LS_LOOK = 2, LS_PROBE = 3, LS_ROW = 4, LS_END = 5 };
+constexpr u32 kLocTailCap = 64;  // parked searches per warp
+struct LocTailQ {
+    u64 q[kLocTailCap];   // result slot | swapped << 63
+    u64 R4[kLocTailCap];
+    u32 lo[kLocTailCap], hi[kLocTailCap];
+};
+// ring entry: top 26 bits of the ordering value | tie << 5 | position inside its block
+constexpr u32 kLocTie = 32u;
+__device__ __forceinline__ u32 loc_entry(u32 ord, u32 p) { return (ord & ~63u) | p; }
+// the better of two entries, a covering the earlier positions
+__device__ __forceinline__ u32 loc_combine(u32 a, u32 b) {
+    const u32 ka = a >> 6, kb = b >> 6;
+    return ka < kb ? a : (kb < ka ? b : (a | kLocTie));
+}
 
 // Presence outputs only (K_OUT_PRESENCE). Chunk c = bases [coff[c], coff[c] + clen[c]) of the 2-bit packed text; its k-mers
 // go to result slots roff[c], roff[c] + 1, ... (the layout of stream_kernel; chunks may be of any length here).
-// Dynamic shared memory: 2 * w * blockDim u32 (the rings).
+// Dynamic shared memory: loc_stream_smem().
 template <int MODE, int STRANDS>
-__global__ void __launch_bounds__(kLocBlock)
+__global__ void __launch_bounds__(kLocBlock, FMSI_LOC_MINBLOCKS)
 loc_stream_kernel(const LocView lv, const u64 *__restrict__ packed, const u64 n_bases, const u64 *__restrict__ coff,
                   const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks, unsigned char *__restrict__ out,
                   unsigned long long *__restrict__ cursor, const u32 grab, unsigned long long *__restrict__ probe_ctr) {
-    extern __shared__ u32 loc_ring[];
+    extern __shared__ __align__(8) u32 loc_smem[];
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
+    const u32 lt_mask = (1u << lane) - 1u;
     const LocGeom g = lv.g;
     const u32 k = g.k, W = g.w, m = g.m;
     const u32 mask = m < 16 ? (1u << (2 * m)) - 1u : 0xFFFFFFFFu;
     const u64 kmask = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
-    u32 *ring_o = loc_ring + threadIdx.x;                          // ring_o[(j % W) * blockDim]: ordering value of m-mer j
-    u32 *ring_x = loc_ring + (size_t)W * blockDim.x + threadIdx.x;  // its forward m-mer
     const u32 rs = blockDim.x;
+    u32 *ring = loc_smem + threadIdx.x;  // ring[p * rs]: block position p
+    LocTailQ &tq = reinterpret_cast<LocTailQ *>(loc_smem + (size_t)W * rs)[threadIdx.x >> 5];
 
     u64 wnext = 0, wend = 0;  // the warp's grab of chunks (warp-uniform)
+    u32 qcount = 0;           // parked searches (warp-uniform)
     u32 nprobe = 0;
+
+    // finish up to 32 parked searches together (bisection, 8 rows per probe)
+    auto drain = [&]() {
+        const u32 nb = qcount < 32u ? qcount : 32u;
+        const u32 e = qcount - nb + lane;
+        bool busy = lane < nb;
+        u64 q = 0, R4 = 0;
+        u32 lo = 0, hi = 0, st = 0;
+        if (busy) {
+            q = tq.q[e];
+            R4 = tq.R4[e];
+            lo = tq.lo[e];
+            hi = tq.hi[e];
+        }
+        qcount -= nb;
+        while (__any_sync(FULL, busy)) {
+            u64 v[kLocRows] = {};
+            const u32 r0 = loc_window(lo + ((hi - lo) >> 1), lo);
+            if (busy) {
+                loc_probe8(lv.rows, r0, v);
+                ++nprobe;
+                if (loc_consume8(v, r0, R4, lo, hi, st)) {
+                    out[q & ~(1ull << 63)] = loc_result<MODE, STRANDS>(st, (q >> 63) != 0);
+                    busy = false;
+                }
+            }
+        }
+        __syncwarp();
+    };
 
     for (;;) {
         // ---------------------------------------------------------------- 32 chunks, one per lane
@@ -507,183 +562,163 @@ loc_stream_kernel(const LocView lv, const u64 *__restrict__ packed, const u64 n_
                 tpos = s0;
             }
         }
-        if (!__any_sync(FULL, nk != 0)) continue;
-        // ---------------------------------------------------------------- the first k-mer, its w m-mers into the ring
-        u64 kf = nk ? window64(packed, tpos, k) : 0ull;
+        const u32 nk_max = __reduce_max_sync(FULL, nk);
+        if (nk_max == 0) continue;
+        // ---------------------------------------------------------------- the first k-mer: its w m-mers are block 0
+        u64 kf = window64(packed, tpos, k);
         u64 kr = revcomp_packed(kf, k);
-        tpos += k;            // next base to take
-        u64 tbuf = 0;         // upcoming bases, first one highest
-        u32 tleft = 0;
-        u32 min_o = 0xFFFFFFFFu, min_j = 0;
-        bool tie = false;
-        for (u32 p = 0; p < W; ++p) {
-            const u32 xf = (u32)(kf >> (g.fbits - 2 * p)) & mask, yr = (u32)(kr >> (2 * p)) & mask;
-            const u32 ov = loc_order(xf < yr ? xf : yr);
-            ring_o[p * rs] = ov;
-            ring_x[p * rs] = xf;
-            if (ov < min_o) {
-                min_o = ov;
-                min_j = p;
-                tie = false;
-            } else if (ov == min_o) {
-                tie = true;
+        tpos += k;       // next base to take
+        u64 tbuf = 0;    // upcoming bases, first one highest
+        u32 tleft = 0;   // warp-uniform
+        u32 pm = 0;      // running prefix minimum of the current block
+        for (u32 P = 0; P < W; ++P) {
+            const u32 xf = (u32)(kf >> (g.fbits - 2 * P)) & mask, yr = (u32)(kr >> (2 * P)) & mask;
+            const u32 e = loc_entry(loc_order(xf < yr ? xf : yr), P);
+            ring[P * rs] = e;
+            pm = P ? loc_combine(pm, e) : e;
+        }
+        u32 wm = pm;             // minimum of the current k-mer's window
+        bool from_prev = false;  // it lies in the previous block
+        {                        // block 0 is complete: suffix minima in place
+            u32 cur = ring[(W - 1) * rs];
+            for (u32 P = W - 1; P-- > 0;) {
+                cur = loc_combine(ring[P * rs], cur);
+                ring[P * rs] = cur;
             }
         }
-        u32 i = 0;                // current k-mer of the chunk; its m-mers are j = i .. i + W - 1
-        u32 slot_w = W % W;       // ring slot of m-mer i + W (the next one to arrive) = (i + W) % W = i % W
-        u32 slot_i = 0;           // ring slot of m-mer i
-        // derived from the current minimizer (valid while cached_j == min_j)
-        u32 cached_j = 0xFFFFFFFFu, bucket = 0, hl = 0, d_first = 0, d_cnt = 0, d_pmin = 0, d_pspan = 0;
-        bool fwd = true, pal = false, dir_valid = false, d_simple = false;
-        // the current k-mer's search
-        u32 stage = nk ? LS_NEW : LS_END, lo = 0, hi = 0, r0 = 0, pos = 0, qbucket = 0;
-        u64 R4 = 0;
-        bool sw = false, slow = false;
+        u32 P = W - 1, blockbase = 0;  // block position and block of the newest m-mer (warp-uniform)
 
-        while (__any_sync(FULL, stage != LS_END)) {
-            // ------------------------------------------------------------ a new k-mer: minimizer, key, what to load
-            if (stage == LS_NEW) {
-                if (min_j < i) {  // the minimum left the window: rescan the ring (m-mers i .. i + W - 1)
-                    min_o = 0xFFFFFFFFu;
-                    tie = false;
-                    u32 sl = slot_i;
-                    for (u32 p = 0; p < W; ++p) {
-                        const u32 ov = ring_o[sl * rs];
-                        if (ov < min_o) {
-                            min_o = ov;
-                            min_j = i + p;
-                            tie = false;
-                        } else if (ov == min_o) {
-                            tie = true;
-                        }
-                        sl = sl + 1 == W ? 0 : sl + 1;
+        // key of the k-mer in (kf, kr), number i, whose window minimum is (wm, from_prev)
+        auto derive = [&](u32 i, u32 &bucket, u64 &R4, u32 &pos, bool &sw) {
+            const u32 j = (from_prev ? blockbase - W : blockbase) + (wm & 31u);
+            const u32 p = j - i;
+            const u32 xf = (u32)(kf >> (g.fbits - 2 * p)) & mask, yr = (u32)(kr >> (2 * p)) & mask;
+            u64 o, R;
+            if ((wm & kLocTie) || xf == yr) {  // the exact definition decides
+                u32 x;
+                loc_pick(kf, kr, g, x, pos, sw, o);
+                loc_key(x, pos, o, g, bucket, R);
+            } else {
+                const bool fwd = xf < yr;
+                pos = fwd ? p : W - 1 - p;
+                o = fwd ? kf : kr;
+                sw = !fwd;
+                loc_key(fwd ? xf : yr, pos, o, g, bucket, R);
+            }
+            R4 = R << 4;
+        };
+
+        // pipeline registers: K2 = k-mer i (directory entry in flight), K1 = k-mer i - 1 (rows in flight)
+        u32 b2 = 0, pos2 = 0;
+        u64 R4_2 = 0, de2 = 0;
+        bool sw2 = false, have2 = nk != 0;
+        derive(0, b2, R4_2, pos2, sw2);
+        if (have2) {
+            de2 = ld_loc_dir(lv.dir + b2);
+            ++nprobe;
+        }
+        u64 R4_1 = 0, q1 = 0;
+        u32 lo1 = 0, hi1 = 0, r0_1 = 0;
+        bool sw1 = false, have1 = false;
+        u64 v[kLocRows] = {};
+
+        for (u32 i = 0; i <= nk_max; ++i) {
+            // ------------------------------------------------------------ roll to k-mer i + 1, key it, ask for its directory entry
+            u32 b3 = 0, pos3 = 0;
+            u64 R4_3 = 0, de3 = 0;
+            bool sw3 = false;
+            const bool have3 = i + 1 < nk;
+            if (i + 1 < nk_max) {
+                if (tleft == 0) {
+                    tbuf = tpos < n_bases ? window64(packed, tpos, 32) : 0ull;
+                    tleft = 32;
+                }
+                const u32 b = (u32)(tbuf >> 62);
+                tbuf <<= 2;
+                --tleft;
+                ++tpos;
+                kf = ((kf << 2) | b) & kmask;
+                kr = (kr >> 2) | ((u64)(3u - b) << (2 * (k - 1)));
+                const u32 xf = (u32)kf & mask, yr = (u32)(kr >> g.fbits) & mask;  // the m-mer that entered
+                P = P + 1 == W ? 0 : P + 1;
+                if (P == 0) blockbase += W;
+                const u32 e = loc_entry(loc_order(xf < yr ? xf : yr), P);
+                const u32 sfx = P + 1 < W ? ring[(P + 1) * rs] : 0u;  // suffix minimum of the previous block
+                ring[P * rs] = e;
+                pm = P ? loc_combine(pm, e) : e;
+                if (P + 1 == W) {  // the window is this block; the block is complete: suffix minima in place
+                    wm = pm;
+                    from_prev = false;
+                    u32 cur = e;
+                    for (u32 Q = W - 1; Q-- > 0;) {
+                        cur = loc_combine(ring[Q * rs], cur);
+                        ring[Q * rs] = cur;
                     }
-                }
-                if (cached_j != min_j) {  // another minimizer: its canonical form, bucket
-                    u32 sl = slot_i + (min_j - i);
-                    sl = sl >= W ? sl - W : sl;
-                    const u32 xf = ring_x[sl * rs], yr = loc_revcomp_m(xf, m);
-                    fwd = xf < yr;
-                    pal = xf == yr;
-                    const u32 h = loc_spread(fwd ? xf : yr, m, mask);
-                    bucket = h >> g.hlow;
-                    hl = g.hlow ? (h & ((1u << g.hlow) - 1u)) : 0u;
-                    dir_valid = false;
-                    cached_j = min_j;
-                }
-                u64 o;
-                slow = tie || pal;
-                if (slow) {  // the exact definition decides (and may pick another bucket)
-                    u32 x;
-                    u64 R;
-                    loc_pick(kf, kr, g, x, pos, sw, o);
-                    loc_key(x, pos, o, g, qbucket, R);
-                    R4 = R << 4;
-                    stage = LS_DIR;
                 } else {
-                    const u32 p = min_j - i;
-                    pos = fwd ? p : W - 1 - p;
-                    o = fwd ? kf : kr;
-                    sw = !fwd;
-                    const u32 rl = g.fbits - 2 * pos;
-                    const u64 right = rl ? (o & ((1ull << rl) - 1ull)) : 0ull;
-                    const u64 left = pos ? (o >> (2 * (k - pos))) : 0ull;
-                    const u64 flanks = rl ? ((left << rl) | right) : left;
-                    R4 = ((((u64)pos << g.hlow) | (u64)hl) << g.fbits | flanks) << 4;
-                    qbucket = bucket;
-                    stage = dir_valid ? LS_LOOK : LS_DIR;
+                    wm = loc_combine(sfx, pm);
+                    from_prev = (sfx >> 6) <= (pm >> 6);
+                }
+                derive(i + 1, b3, R4_3, pos3, sw3);
+                if (have3) {
+                    de3 = ld_loc_dir(lv.dir + b3);
+                    ++nprobe;
                 }
             }
-            // with the bucket's entry at hand: absent at once, or where to look
-            bool settled = false;
-            u32 st = 0;
-            if (stage == LS_LOOK) {
-                if (d_cnt == 0 || pos < d_pmin || pos > d_pmin + d_pspan) {
-                    settled = true;
-                } else if (d_simple) {
-                    r0 = d_first + (pos - d_pmin);
-                    stage = LS_ROW;
-                } else {
-                    lo = d_first;
-                    hi = d_first + d_cnt;
-                    r0 = loc_window(d_first + ((2 * (pos - d_pmin) + 1) * d_cnt) / (2 * (d_pspan + 1)), lo);
-                    stage = LS_PROBE;
+            // ------------------------------------------------------------ k-mer i - 1: its rows have arrived
+            {
+                bool park = false;
+                if (have1) {
+                    u32 st = 0;
+                    if (loc_consume8(v, r0_1, R4_1, lo1, hi1, st)) out[q1] = loc_result<MODE, STRANDS>(st, sw1);
+                    else park = true;
                 }
-            }
-            // ------------------------------------------------------------ one load per lane
-            u64 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            u64 de = 0;
-            const bool isD = stage == LS_DIR, isP = stage == LS_PROBE, isR = stage == LS_ROW;
-            if (isD) de = ld_loc_dir(lv.dir + qbucket);
-            if (isP) loc_probe8(lv.rows, r0, v);
-            if (isR) v[0] = ld_loc_row(lv.rows + r0);
-            nprobe += (u32)(isD || isP || isR);
-            // ------------------------------------------------------------ consume
-            if (isD) {
-                const u32 first = (u32)de, cnt = (u32)(de >> 32) & ((1u << kLocCountBits) - 1u);
-                const bool simple = (de >> 53) & 1ull;
-                const u32 pmin = (u32)(de >> 54) & 31u, pspan = (u32)(de >> 59);
-                if (!slow) {
-                    d_first = first;
-                    d_cnt = cnt;
-                    d_simple = simple;
-                    d_pmin = pmin;
-                    d_pspan = pspan;
-                    dir_valid = true;
-                    stage = LS_LOOK;  // decided at the top of the next round, which also issues the probe
-                } else if (cnt == 0 || pos < pmin || pos > pmin + pspan) {
-                    settled = true;
-                } else {
-                    lo = first;
-                    hi = first + cnt;
-                    r0 = loc_window(first + ((2 * (pos - pmin) + 1) * cnt) / (2 * (pspan + 1)), lo);
-                    stage = LS_PROBE;  // an ordinary bisection from here on (the cached entry stays the window minimum's)
-                }
-            } else if (isP) {
-                if (loc_consume8(v, r0, R4, lo, hi, st)) settled = true;
-                else r0 = loc_window(lo + ((hi - lo) >> 1), lo);
-            } else if (isR) {
-                if ((v[0] - R4) < 16ull) st = (u32)v[0] & 15u;
-                settled = true;
-            }
-            // ------------------------------------------------------------ result, next k-mer
-            if (settled) {
-                out[res0 + i] = loc_result<MODE, STRANDS>(st, sw);
-                ++i;
-                slot_i = slot_i + 1 == W ? 0 : slot_i + 1;
-                if (i >= nk) {
-                    stage = LS_END;
-                } else {
-                    if (tleft == 0) {
-                        tbuf = window64(packed, tpos, 32);
-                        tleft = 32;
+                const unsigned pmask = __ballot_sync(FULL, park);
+                if (pmask) {
+                    if (qcount + (u32)__popc(pmask) > kLocTailCap) drain();
+                    if (park) {
+                        const u32 e = qcount + (u32)__popc(pmask & lt_mask);
+                        tq.q[e] = q1 | ((u64)sw1 << 63);
+                        tq.R4[e] = R4_1;
+                        tq.lo[e] = lo1;
+                        tq.hi[e] = hi1;
                     }
-                    const u32 b = (u32)(tbuf >> 62);
-                    tbuf <<= 2;
-                    --tleft;
-                    ++tpos;
-                    kf = ((kf << 2) | b) & kmask;
-                    kr = (kr >> 2) | ((u64)(3u - b) << (2 * (k - 1)));
-                    const u32 xf = (u32)kf & mask, yr = (u32)(kr >> g.fbits) & mask;  // the m-mer that entered: j = i + W - 1
-                    const u32 ov = loc_order(xf < yr ? xf : yr);
-                    ring_o[slot_w * rs] = ov;
-                    ring_x[slot_w * rs] = xf;
-                    slot_w = slot_w + 1 == W ? 0 : slot_w + 1;
-                    if (ov < min_o) {
-                        min_o = ov;
-                        min_j = i + W - 1;
-                        tie = false;
-                    } else if (ov == min_o) {
-                        tie = true;
-                    }
-                    stage = LS_NEW;
+                    qcount += (u32)__popc(pmask);
+                    __syncwarp();
+                    if (qcount >= 32u) drain();
                 }
             }
+            // ------------------------------------------------------------ k-mer i: its directory entry has arrived
+            have1 = false;
+            if (have2) {
+                const u32 first = (u32)de2, cnt = (u32)(de2 >> 32) & ((1u << kLocCountBits) - 1u);
+                const u32 pmin = (u32)(de2 >> 54) & 31u, pspan = (u32)(de2 >> 59);
+                if (cnt == 0 || pos2 < pmin || pos2 > pmin + pspan) {
+                    out[res0 + i] = loc_result<MODE, STRANDS>(0u, sw2);  // empty bucket, or no row of it has the minimizer at this position
+                } else {
+                    lo1 = first;
+                    hi1 = first + cnt;
+                    // rows are sorted by pos first: look where pos interpolates to
+                    r0_1 = loc_window(first + ((2 * (pos2 - pmin) + 1) * cnt) / (2 * (pspan + 1)), lo1);
+                    loc_probe8(lv.rows, r0_1, v);
+                    ++nprobe;
+                    R4_1 = R4_2;
+                    sw1 = sw2;
+                    q1 = res0 + i;
+                    have1 = true;
+                }
+            }
+            b2 = b3;
+            pos2 = pos3;
+            R4_2 = R4_3;
+            de2 = de3;
+            sw2 = sw3;
+            have2 = have3;
         }
     }
+    while (qcount) drain();
     count_probes(probe_ctr, nprobe);
 }
 
-inline size_t loc_stream_smem(const LocGeom &g, int block = kLocBlock) { return (size_t)2 * g.w * block * sizeof(u32); }
+inline size_t loc_stream_smem(const LocGeom &g, int block = kLocBlock) { return (size_t)g.w * block * sizeof(u32) + (size_t)(block / 32) * sizeof(LocTailQ); }
 
 }  // namespace fmsi
