@@ -1436,7 +1436,8 @@ int query_chunks_impl(fmsi_gpu_index *idx, int mode, int output, int strands, in
     const bool pipelined = on_host && n_bases > 2 * kPiece;
     // reads mode: the streaming kernel takes chunks of <= 64 k-mers, every other path one chunk per read
     const size_t n_reads = reads_mode ? n_chunks : 0;
-    const u32 read_max_kmers = (reads_mode && !via_kmers) ? FMSI_GPU_MAX_STREAM_KMERS : 0u;
+    // (the minimizer-bucketed tier walks tiles of 32 k-mers: reads cut into chunks of 32 give it full tiles)
+    const u32 read_max_kmers = !reads_mode ? 0u : via_loc ? 32u : !via_kmers ? FMSI_GPU_MAX_STREAM_KMERS : 0u;
     if (reads_mode) n_chunks = read_max_kmers ? n_reads + n_results / read_max_kmers + 1 : n_reads;  // capacity of the device chunk arrays
     auto bad_stream_chunk = [&](size_t c) { return chunk_len[c] < (u32)k || chunk_len[c] - (u32)k + 1 > FMSI_GPU_MAX_STREAM_KMERS; };
     const char *kBadStreamChunk = "streaming chunks must hold between 1 and FMSI_GPU_MAX_STREAM_KMERS k-mers";

@@ -394,24 +394,21 @@ __device__ __forceinline__ u64 ld_loc_dir(const u64 *p) {
     return r;
 }
 
-// The query kernel gives every LANE a chunk of text (a read) and walks it k-mer by k-mer; the 32 lanes of a warp start 32
-// chunks together and stay in LOCKSTEP — every lane is at the same k-mer number, in the same code — so the warp's
-// instructions are spent on 32 k-mers each. What makes a k-mer cheap:
-//   * the minimizer is kept ROLLING: one new m-mer per k-mer. Its ordering value (top 26 bits) goes into a per-lane ring
-//     in shared memory; the ring is cut into blocks of w m-mers, and the minimum of a window is the better of a suffix
-//     minimum of the previous block (computed in place when the block completes: one loop for the whole warp) and the
-//     running prefix minimum of the current one. Ties — equal ordering bits in one window, palindromic m-mers — are rare
-//     and go through loc_pick, the one exact definition;
-//   * a k-mer is two loads, and the loads of neighbouring k-mers overlap: while k-mer i's rows and k-mer i + 1's directory
-//     entry are in flight, k-mer i + 2 is rolled and keyed. The k-mers of a run share their bucket, so its directory entry
-//     and rows come from DRAM once and from L1 / L2 afterwards;
-//   * a pos outside the bucket's range, or an empty bucket, is absent without touching the rows; a lane whose 8-row
-//     window does not settle its k-mer (a bucket of many rows) parks that search in a per-warp queue in shared memory,
-//     and whenever 32 are waiting the warp finishes them together by bisection — nobody waits for a neighbour.
-// Per k-mer that is a fraction of a DRAM request and a few instructions per lane, against one DRAM request in fold.cuh.
+// The query kernel walks TILES: 32 consecutive k-mers of one chunk of text (a read), one per lane.
+//   * Minimizers: lane l hashes ONE m-mer — the one that starts at the tile's base l (lanes below w - 1 a second one, at
+//     base 32 + l) — and the minimum of every lane's window of w places comes out of a sliding-window minimum ACROSS the
+//     lanes (log2 w rounds of shuffles), instead of 2 w hashes per lane. Ties — equal ordering bits in one window,
+//     palindromic m-mers — are rare and go through loc_pick, the one exact definition (as do windows that are not a
+//     power of two: small k).
+//   * Lookups: a fixed two-load pipeline per tile — DIR (the bucket's entry: empty bucket or a pos outside its range is
+//     absent at once; else where pos interpolates to), WIDE (8 rows around that place). Lanes that hold neighbouring
+//     k-mers ask for the same entry and the same lines of rows in one instruction, which the load unit merges into one
+//     request. A lane whose window does not settle its k-mer (a bucket of many rows) parks that search in a per-warp
+//     queue in shared memory; whenever 32 are waiting the warp finishes them together by bisection.
+//   * Overlap: WIDE of tile i and DIR of tile i + 1 are in flight while tile i + 2 is fetched and keyed.
 constexpr int kLocBlock = 256;
 #ifndef FMSI_LOC_MINBLOCKS
-#define FMSI_LOC_MINBLOCKS 2
+#define FMSI_LOC_MINBLOCKS 3
 #endif
 #ifndef FMSI_LOC_ROWS
 #define FMSI_LOC_ROWS 8
@@ -477,39 +474,48 @@ struct LocTailQ {
     u64 R4[kLocTailCap];
     u32 lo[kLocTailCap], hi[kLocTailCap];
 };
-// ring entry: top 26 bits of the ordering value | tie << 5 | position inside its block
-constexpr u32 kLocTie = 32u;
-__device__ __forceinline__ u32 loc_entry(u32 ord, u32 p) { return (ord & ~63u) | p; }
+// window entry: top 25 bits of the ordering value | tie << 6 | m-mer position inside the tile (0 .. 62)
+constexpr u32 kLocTie = 64u, kLocInf = 0xFFFFFFFFu;
+__device__ __forceinline__ u32 loc_entry(u32 ord, u32 p) { return (ord & ~127u) | p; }
 // the better of two entries, a covering the earlier positions
 __device__ __forceinline__ u32 loc_combine(u32 a, u32 b) {
-    const u32 ka = a >> 6, kb = b >> 6;
+    const u32 ka = a >> 7, kb = b >> 7;
     return ka < kb ? a : (kb < ka ? b : (a | kLocTie));
 }
 
 // Presence outputs only (K_OUT_PRESENCE). Chunk c = bases [coff[c], coff[c] + clen[c]) of the 2-bit packed text; its k-mers
-// go to result slots roff[c], roff[c] + 1, ... (the layout of stream_kernel; chunks may be of any length here).
-// Dynamic shared memory: loc_stream_smem().
+// go to result slots roff[c], roff[c] + 1, ... (the layout of stream_kernel; chunks may be of any length, and a caller that
+// cuts reads into chunks of 32 k-mers gets full tiles). Dynamic shared memory: loc_stream_smem().
 template <int MODE, int STRANDS>
 __global__ void __launch_bounds__(kLocBlock, FMSI_LOC_MINBLOCKS)
 loc_stream_kernel(const LocView lv, const u64 *__restrict__ packed, const u64 n_bases, const u64 *__restrict__ coff,
                   const u32 *__restrict__ clen, const u64 *__restrict__ roff, const u64 n_chunks, unsigned char *__restrict__ out,
                   unsigned long long *__restrict__ cursor, const u32 grab, unsigned long long *__restrict__ probe_ctr) {
     extern __shared__ __align__(8) u32 loc_smem[];
+    LocTailQ &tq = reinterpret_cast<LocTailQ *>(loc_smem)[threadIdx.x >> 5];
     const unsigned FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u;
     const u32 lt_mask = (1u << lane) - 1u;
     const LocGeom g = lv.g;
     const u32 k = g.k, W = g.w, m = g.m;
     const u32 mask = m < 16 ? (1u << (2 * m)) - 1u : 0xFFFFFFFFu;
-    const u64 kmask = k < 32 ? (1ull << (2 * k)) - 1ull : ~0ull;
-    const u32 rs = blockDim.x;
-    u32 *ring = loc_smem + threadIdx.x;  // ring[p * rs]: block position p
-    LocTailQ &tq = reinterpret_cast<LocTailQ *>(loc_smem + (size_t)W * rs)[threadIdx.x >> 5];
+    const bool pow2 = (W & (W - 1)) == 0;  // the sliding-window minimum below takes windows of 1, 2, 4, 8, 16 places
 
-    u64 wnext = 0, wend = 0;  // the warp's grab of chunks (warp-uniform)
-    u32 qcount = 0;           // parked searches (warp-uniform)
-    u32 nprobe = 0;
+    // the warp's place in the work: chunks [cc, cend) of its grab, tiles of the current chunk from k-mer cb on (warp-uniform)
+    u64 cc = 0, cend = 0, cs = 0, cres = 0;
+    u32 cnk = 0, cb = 0;
+    bool exhausted = false;
+    u32 qcount = 0;  // parked searches (warp-uniform)
+    u32 nreq = 0;    // requests after merging, counted by the leader lanes when probe_ctr is given
 
+    auto count_requests = [&](bool mine, const void *addr) {  // distinct 128-byte lines of a warp instruction
+        if (!probe_ctr) return;
+        const unsigned act = __ballot_sync(FULL, mine);
+        if (mine) {
+            const unsigned same = __match_any_sync(act, (unsigned long long)addr >> 7);
+            if ((u32)(__ffs(same) - 1) == lane) ++nreq;
+        }
+    };
     // finish up to 32 parked searches together (bisection, 8 rows per probe)
     auto drain = [&]() {
         const u32 nb = qcount < 32u ? qcount : 32u;
@@ -527,198 +533,163 @@ loc_stream_kernel(const LocView lv, const u64 *__restrict__ packed, const u64 n_
         while (__any_sync(FULL, busy)) {
             u64 v[kLocRows] = {};
             const u32 r0 = loc_window(lo + ((hi - lo) >> 1), lo);
-            if (busy) {
-                loc_probe8(lv.rows, r0, v);
-                ++nprobe;
-                if (loc_consume8(v, r0, R4, lo, hi, st)) {
-                    out[q & ~(1ull << 63)] = loc_result<MODE, STRANDS>(st, (q >> 63) != 0);
-                    busy = false;
-                }
+            if (busy) loc_probe8(lv.rows, r0, v);
+            count_requests(busy, lv.rows + r0);
+            if (busy && loc_consume8(v, r0, R4, lo, hi, st)) {
+                out[q & ~(1ull << 63)] = loc_result<MODE, STRANDS>(st, (q >> 63) != 0);
+                busy = false;
             }
         }
         __syncwarp();
     };
-
-    for (;;) {
-        // ---------------------------------------------------------------- 32 chunks, one per lane
-        if (wnext >= wend) {
-            unsigned long long c0 = 0;
-            if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)grab);
-            c0 = __shfl_sync(FULL, c0, 0);
-            if (c0 >= n_chunks) break;
-            wnext = c0;
-            wend = (c0 + grab < n_chunks) ? c0 + grab : n_chunks;
-        }
-        const u64 c = wnext + lane;
-        wnext = (wnext + 32 < wend) ? wnext + 32 : wend;
-        u64 tpos = 0, res0 = 0;
-        u32 nk = 0;
-        if (c < wend) {
-            const u64 s0 = __ldg(coff + c);
-            const u32 len = __ldg(clen + c);
-            res0 = __ldg(roff + c);
-            if (len >= k && s0 + len <= n_bases) {
-                nk = len - k + 1;
-                tpos = s0;
+    // the next tile: its k-mers, their minimizers and keys. false = no tiles left (warp-uniform)
+    auto prepare = [&](u64 &res, bool &have, bool &sw, u32 &bucket, u32 &pos, u64 &R4) -> bool {
+        while (cb >= cnk) {  // next chunk
+            if (cc >= cend) {
+                unsigned long long c0 = 0;
+                if (lane == 0) c0 = atomicAdd(cursor, (unsigned long long)grab);
+                c0 = __shfl_sync(FULL, c0, 0);
+                if (c0 >= n_chunks) {
+                    exhausted = true;
+                    return false;
+                }
+                cc = c0;
+                cend = (c0 + grab < n_chunks) ? c0 + grab : n_chunks;
             }
+            const u64 s0 = __ldg(coff + cc);
+            const u32 len = __ldg(clen + cc);
+            cres = __ldg(roff + cc);
+            cs = s0;
+            cnk = (len >= k && s0 + len <= n_bases) ? len - k + 1 : 0u;
+            cb = 0;
+            ++cc;
         }
-        const u32 nk_max = __reduce_max_sync(FULL, nk);
-        if (nk_max == 0) continue;
-        // ---------------------------------------------------------------- the first k-mer: its w m-mers are block 0
-        u64 kf = window64(packed, tpos, k);
-        u64 kr = revcomp_packed(kf, k);
-        tpos += k;       // next base to take
-        u64 tbuf = 0;    // upcoming bases, first one highest
-        u32 tleft = 0;   // warp-uniform
-        u32 pm = 0;      // running prefix minimum of the current block
-        for (u32 P = 0; P < W; ++P) {
-            const u32 xf = (u32)(kf >> (g.fbits - 2 * P)) & mask, yr = (u32)(kr >> (2 * P)) & mask;
-            const u32 e = loc_entry(loc_order(xf < yr ? xf : yr), P);
-            ring[P * rs] = e;
-            pm = P ? loc_combine(pm, e) : e;
-        }
-        u32 wm = pm;             // minimum of the current k-mer's window
-        bool from_prev = false;  // it lies in the previous block
-        {                        // block 0 is complete: suffix minima in place
-            u32 cur = ring[(W - 1) * rs];
-            for (u32 P = W - 1; P-- > 0;) {
-                cur = loc_combine(ring[P * rs], cur);
-                ring[P * rs] = cur;
+        const u64 s = cs + cb;
+        const u32 nt = cnk - cb < 32u ? cnk - cb : 32u;  // k-mers of this tile; its m-mers sit at bases 0 .. nt + W - 2
+        res = cres + cb;
+        cb += 32;
+        have = lane < nt;
+        const u64 full = window64(packed, s + lane, 32);  // 32 bases from base `lane` of the tile (the text has that much slack)
+        const u64 kf = full >> (64 - 2 * k), kr = revcomp_packed(kf, k);
+        u32 x = 0, wm;
+        u64 o, R;
+        if (pow2) {
+            // entries of the m-mers at bases lane and 32 + lane
+            const u32 x1 = (u32)(full >> (64 - 2 * m)), y1 = (u32)kr & mask;
+            const u64 f31 = __shfl_sync(FULL, full, 31);  // bases 31 .. 62
+            const u32 x2 = (u32)((f31 << (2 * (1 + (lane & 15u)))) >> (64 - 2 * m)), y2 = loc_revcomp_m(x2, m);
+            u32 e1 = lane < nt + W - 1 ? loc_entry(loc_order(x1 < y1 ? x1 : y1), lane) : kLocInf;
+            u32 e2 = (lane < W - 1 && 32 + lane < nt + W - 1) ? loc_entry(loc_order(x2 < y2 ? x2 : y2), 32 + lane) : kLocInf;
+            // sliding-window minimum across the lanes: after the round for d, e1 / e2 cover d + d places from their base on
+            for (u32 d = 1; d < W; d <<= 1) {
+                const u32 src = (lane + d) & 31u;
+                const u32 a1 = __shfl_sync(FULL, e1, src), a2 = __shfl_sync(FULL, e2, src);
+                const u32 n1 = lane + d < 32u ? a1 : a2;  // base lane + d
+                const u32 n2 = lane + d < 32u ? a2 : kLocInf;  // base 32 + lane + d
+                e1 = loc_combine(e1, n1);
+                e2 = loc_combine(e2, n2);
             }
+            wm = e1;
+        } else {
+            wm = kLocTie;
         }
-        u32 P = W - 1, blockbase = 0;  // block position and block of the newest m-mer (warp-uniform)
-
-        // key of the k-mer in (kf, kr), number i, whose window minimum is (wm, from_prev)
-        auto derive = [&](u32 i, u32 &bucket, u64 &R4, u32 &pos, bool &sw) {
-            const u32 j = (from_prev ? blockbase - W : blockbase) + (wm & 31u);
-            const u32 p = j - i;
+        if (have) {
+            u32 p = (wm & 63u) - lane;
+            p = p < W ? p : 0u;  // (meaningless when the exact definition decides below)
             const u32 xf = (u32)(kf >> (g.fbits - 2 * p)) & mask, yr = (u32)(kr >> (2 * p)) & mask;
-            u64 o, R;
             if ((wm & kLocTie) || xf == yr) {  // the exact definition decides
-                u32 x;
                 loc_pick(kf, kr, g, x, pos, sw, o);
-                loc_key(x, pos, o, g, bucket, R);
             } else {
                 const bool fwd = xf < yr;
                 pos = fwd ? p : W - 1 - p;
                 o = fwd ? kf : kr;
                 sw = !fwd;
-                loc_key(fwd ? xf : yr, pos, o, g, bucket, R);
+                x = fwd ? xf : yr;
             }
+            loc_key(x, pos, o, g, bucket, R);
             R4 = R << 4;
-        };
-
-        // pipeline registers: K2 = k-mer i (directory entry in flight), K1 = k-mer i - 1 (rows in flight)
-        u32 b2 = 0, pos2 = 0;
-        u64 R4_2 = 0, de2 = 0;
-        bool sw2 = false, have2 = nk != 0;
-        derive(0, b2, R4_2, pos2, sw2);
-        if (have2) {
-            de2 = ld_loc_dir(lv.dir + b2);
-            ++nprobe;
         }
-        u64 R4_1 = 0, q1 = 0;
-        u32 lo1 = 0, hi1 = 0, r0_1 = 0;
-        bool sw1 = false, have1 = false;
+        return true;
+    };
+
+    // tile A: its DIR entry consumed, WIDE window chosen; tile B: prepared, DIR load issued
+    u64 resA = 0, R4A = 0, resB = 0, R4B = 0, deB = 0;
+    u32 loA = 0, hiA = 0, r0A = 0, bucketB = 0, posB = 0;
+    bool okA = false, actA = false, swA = false, okB = false, haveB = false, swB = false;
+    okB = prepare(resB, haveB, swB, bucketB, posB, R4B);
+    if (okB && haveB) deB = ld_loc_dir(lv.dir + bucketB);
+    if (okB) count_requests(haveB, lv.dir + bucketB);
+
+    while (okA || okB) {
+        // ---------------------------------------------------------------- WIDE of tile A goes out (DIR of tile B is in flight)
         u64 v[kLocRows] = {};
-
-        for (u32 i = 0; i <= nk_max; ++i) {
-            // ------------------------------------------------------------ roll to k-mer i + 1, key it, ask for its directory entry
-            u32 b3 = 0, pos3 = 0;
-            u64 R4_3 = 0, de3 = 0;
-            bool sw3 = false;
-            const bool have3 = i + 1 < nk;
-            if (i + 1 < nk_max) {
-                if (tleft == 0) {
-                    tbuf = tpos < n_bases ? window64(packed, tpos, 32) : 0ull;
-                    tleft = 32;
-                }
-                const u32 b = (u32)(tbuf >> 62);
-                tbuf <<= 2;
-                --tleft;
-                ++tpos;
-                kf = ((kf << 2) | b) & kmask;
-                kr = (kr >> 2) | ((u64)(3u - b) << (2 * (k - 1)));
-                const u32 xf = (u32)kf & mask, yr = (u32)(kr >> g.fbits) & mask;  // the m-mer that entered
-                P = P + 1 == W ? 0 : P + 1;
-                if (P == 0) blockbase += W;
-                const u32 e = loc_entry(loc_order(xf < yr ? xf : yr), P);
-                const u32 sfx = P + 1 < W ? ring[(P + 1) * rs] : 0u;  // suffix minimum of the previous block
-                ring[P * rs] = e;
-                pm = P ? loc_combine(pm, e) : e;
-                if (P + 1 == W) {  // the window is this block; the block is complete: suffix minima in place
-                    wm = pm;
-                    from_prev = false;
-                    u32 cur = e;
-                    for (u32 Q = W - 1; Q-- > 0;) {
-                        cur = loc_combine(ring[Q * rs], cur);
-                        ring[Q * rs] = cur;
-                    }
-                } else {
-                    wm = loc_combine(sfx, pm);
-                    from_prev = (sfx >> 6) <= (pm >> 6);
-                }
-                derive(i + 1, b3, R4_3, pos3, sw3);
-                if (have3) {
-                    de3 = ld_loc_dir(lv.dir + b3);
-                    ++nprobe;
-                }
+        if (okA && actA) loc_probe8(lv.rows, r0A, v);
+        if (okA) count_requests(actA, lv.rows + r0A);
+        // ---------------------------------------------------------------- meanwhile: tile C
+        u64 resC = 0, R4C = 0;
+        u32 bucketC = 0, posC = 0;
+        bool haveC = false, swC = false, okC = false;
+        if (!exhausted) okC = prepare(resC, haveC, swC, bucketC, posC, R4C);
+        // ---------------------------------------------------------------- tile A: results, or park the search
+        if (okA) {
+            u32 st = 0;
+            bool park = false;
+            if (actA) {
+                if (loc_consume8(v, r0A, R4A, loA, hiA, st)) out[resA + lane] = loc_result<MODE, STRANDS>(st, swA);
+                else park = true;
             }
-            // ------------------------------------------------------------ k-mer i - 1: its rows have arrived
-            {
-                bool park = false;
-                if (have1) {
-                    u32 st = 0;
-                    if (loc_consume8(v, r0_1, R4_1, lo1, hi1, st)) out[q1] = loc_result<MODE, STRANDS>(st, sw1);
-                    else park = true;
+            const unsigned pmask = __ballot_sync(FULL, park);
+            if (pmask) {
+                if (qcount + (u32)__popc(pmask) > kLocTailCap) drain();  // leaves at most 32 parked
+                if (park) {
+                    const u32 e = qcount + (u32)__popc(pmask & lt_mask);
+                    tq.q[e] = (resA + lane) | ((u64)swA << 63);
+                    tq.R4[e] = R4A;
+                    tq.lo[e] = loA;
+                    tq.hi[e] = hiA;
                 }
-                const unsigned pmask = __ballot_sync(FULL, park);
-                if (pmask) {
-                    if (qcount + (u32)__popc(pmask) > kLocTailCap) drain();
-                    if (park) {
-                        const u32 e = qcount + (u32)__popc(pmask & lt_mask);
-                        tq.q[e] = q1 | ((u64)sw1 << 63);
-                        tq.R4[e] = R4_1;
-                        tq.lo[e] = lo1;
-                        tq.hi[e] = hi1;
-                    }
-                    qcount += (u32)__popc(pmask);
-                    __syncwarp();
-                    if (qcount >= 32u) drain();
-                }
+                qcount += (u32)__popc(pmask);
+                __syncwarp();
+                if (qcount >= 32u) drain();
             }
-            // ------------------------------------------------------------ k-mer i: its directory entry has arrived
-            have1 = false;
-            if (have2) {
-                const u32 first = (u32)de2, cnt = (u32)(de2 >> 32) & ((1u << kLocCountBits) - 1u);
-                const u32 pmin = (u32)(de2 >> 54) & 31u, pspan = (u32)(de2 >> 59);
-                if (cnt == 0 || pos2 < pmin || pos2 > pmin + pspan) {
-                    out[res0 + i] = loc_result<MODE, STRANDS>(0u, sw2);  // empty bucket, or no row of it has the minimizer at this position
-                } else {
-                    lo1 = first;
-                    hi1 = first + cnt;
-                    // rows are sorted by pos first: look where pos interpolates to
-                    r0_1 = loc_window(first + ((2 * (pos2 - pmin) + 1) * cnt) / (2 * (pspan + 1)), lo1);
-                    loc_probe8(lv.rows, r0_1, v);
-                    ++nprobe;
-                    R4_1 = R4_2;
-                    sw1 = sw2;
-                    q1 = res0 + i;
-                    have1 = true;
-                }
-            }
-            b2 = b3;
-            pos2 = pos3;
-            R4_2 = R4_3;
-            de2 = de3;
-            sw2 = sw3;
-            have2 = have3;
         }
+        // ---------------------------------------------------------------- tile B: DIR entry -> becomes tile A
+        okA = okB;
+        if (okB) {
+            resA = resB;
+            R4A = R4B;
+            swA = swB;
+            actA = false;
+            if (haveB) {
+                const u32 first = (u32)deB, cnt = (u32)(deB >> 32) & ((1u << kLocCountBits) - 1u);
+                const u32 pmin = (u32)(deB >> 54) & 31u, pspan = (u32)(deB >> 59);
+                if (cnt == 0 || posB < pmin || posB > pmin + pspan) {
+                    out[resB + lane] = loc_result<MODE, STRANDS>(0u, swB);  // empty bucket, or no row of it has the minimizer at this position
+                } else {
+                    actA = true;
+                    loA = first;
+                    hiA = first + cnt;
+                    // rows are sorted by pos first: look where pos interpolates to
+                    r0A = loc_window(first + ((2 * (posB - pmin) + 1) * cnt) / (2 * (pspan + 1)), loA);
+                }
+            }
+        }
+        // ---------------------------------------------------------------- tile C becomes tile B: its DIR load goes out
+        okB = okC;
+        resB = resC;
+        R4B = R4C;
+        swB = swC;
+        haveB = haveC;
+        bucketB = bucketC;
+        posB = posC;
+        deB = 0;
+        if (okB && haveB) deB = ld_loc_dir(lv.dir + bucketB);
+        if (okB) count_requests(haveB, lv.dir + bucketB);
     }
     while (qcount) drain();
-    count_probes(probe_ctr, nprobe);
+    if (probe_ctr) count_probes(probe_ctr, nreq);
 }
 
-inline size_t loc_stream_smem(const LocGeom &g, int block = kLocBlock) { return (size_t)g.w * block * sizeof(u32) + (size_t)(block / 32) * sizeof(LocTailQ); }
+inline size_t loc_stream_smem(const LocGeom &, int block = kLocBlock) { return (size_t)(block / 32) * sizeof(LocTailQ); }
 
 }  // namespace fmsi
