@@ -29,7 +29,7 @@ def human_loc():
     if free < 170e9 * (N_GENOME / 3.1e9):
         pytest.skip("not enough free device memory for the full-size index")
     codes, ascii_ = device_genome(N_GENOME, 4, K, dev)
-    gi = fg.Index.build(ascii_.data_ptr(), K, with_klcp=False, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=2, locality=1)
+    gi = fg.Index.build(ascii_.data_ptr(), K, with_klcp=True, device=0, n=N_GENOME, mem=fg.MEM_DEVICE, dict=2, locality=1)
     del ascii_
     torch.cuda.empty_cache()
     yield torch, dev, codes, gi
