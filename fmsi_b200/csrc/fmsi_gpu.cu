@@ -46,7 +46,7 @@ int fail(int code, const std::string &msg) {
             return fail(FMSI_GPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
     } while (0)
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;
 constexpr size_t kBatchKmers = 16u << 20;  // k-mers per pipelined host batch
 
 // Per-launch device scratch: ctr[0] = work cursor, ctr[1] = overflow count of the dictionary kernel,

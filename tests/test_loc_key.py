@@ -30,6 +30,21 @@ def test_exhaustive_small_spaces(k, m, t):
 
 
 @pytest.mark.skipif(not os.path.exists(TOOL), reason="fmsi_b200/bin/loc_key_check not built")
+def test_exhaustive_every_geometry_up_to_k6():
+    """Every (k, m, t) with t <= m <= k <= 6: windows of every width (1 .. 6 places), even and odd m (palindromic m-mers
+    exist only for even m), bucket depths from one base to the whole minimizer."""
+    n = 0
+    for k in range(1, 7):
+        for m in range(1, k + 1):
+            for t in range(1, m + 1):
+                rc, out = run(k, m, t)
+                assert rc == 0 and out["fits"] and out["violations"] == 0, (k, m, t, out)
+                assert out["distinct_rows"] == (4 ** k + out["self_complementary"]) // 2, (k, m, t)
+                n += 1
+    assert n == 56
+
+
+@pytest.mark.skipif(not os.path.exists(TOOL), reason="fmsi_b200/bin/loc_key_check not built")
 @pytest.mark.parametrize("k,m,t,rbits", [(31, 16, 15, 36), (32, 16, 15, 39), (23, 16, 15, 19), (31, 16, 7, 52), (13, 8, 7, 15), (32, 16, 5, 59)])
 def test_sampled_benchmark_geometries(k, m, t, rbits):
     rc, out = run(k, m, t, 100000, 7)
