@@ -472,13 +472,13 @@ def test_general_demasking_functions_properties(case):
             gi.close()
 
 
-@pytest.mark.parametrize("tier", ["auto", "backward"])
+@pytest.mark.parametrize("tier", ["auto", "backward", "loc"])
 def test_multi_gpu_pool_matches_single_index(tier):
     """The scheduler (fmsi_gpu_pool_*): replicas made by device-to-device copy answer contiguous
     shards from their own host threads; results must equal the single-index call, in query order.
     With one GPU the replicas share it (repeated ordinals), with more they spread over the GPUs.
     auto: replicas of the strand-folded dictionary (each builds its lookup ids on its first lookup);
-    backward: replicas carry the multi-step rank arrays."""
+    backward: replicas carry the multi-step rank arrays; loc: and the minimizer-bucketed dictionary (chunk calls)."""
     d = os.path.join(GOLDEN, "syn_k31_max")
     prefix = os.path.join(d, "ms.fa")
     k = 31
@@ -518,7 +518,7 @@ def test_multi_gpu_pool_matches_single_index(tier):
     gi.close()
 
 
-@pytest.mark.parametrize("tier", ["auto", "backward"])
+@pytest.mark.parametrize("tier", ["auto", "backward", "loc"])
 def test_bit_packed_results_and_packed_text(tier):
     """FMSI_GPU_OUT_PRESENCE_BITS (one bit per k-mer, packed on the device) must equal the byte results packed on the
     host, for every batch shape of the host path; fmsi_gpu_query_chunks_packed (2-bit text in) must equal the ASCII
